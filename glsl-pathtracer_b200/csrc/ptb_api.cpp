@@ -1,0 +1,857 @@
+// ptb_api.cpp — host side of libptb200.so: the C ABI of include/ptb200.h.
+//
+// Mirrors the host half of the reference's Renderer (reference src/core/Renderer.cpp): scene upload
+// (InitGPUDataBuffers :135-249), buffers (InitFBOs :281-379), feature selection (InitShaders :392-459), per-frame
+// uniforms and the wave loop that replaces the three GL draws of Render() (:546-590).
+// Built with -ffp-contract=off: the derived per-instance inverses and light planes must be bit-identical to what the
+// shader-side formulas give under IEEE arithmetic.
+#include "ptb200.h"
+#include "ptb_internal.h"
+#include <cuda_runtime_api.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+static thread_local std::string g_err;
+extern "C" const char* ptb_last_error(void) { return g_err.c_str(); }
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                    \
+            return e_ == cudaErrorMemoryAllocation ? PTB_ERR_OUT_OF_MEMORY : PTB_ERR_CUDA;                 \
+        }                                                                                                  \
+    } while (0)
+#define REQUIRE(cond, code, msg) do { if (!(cond)) { g_err = msg; return code; } } while (0)
+
+namespace {
+
+template <class T> struct DevBuf
+{
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* src, size_t count, cudaStream_t s)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// inverse(mat4) of the row-major reference Mat4 (adjugate / determinant, fp32, no contraction) — the GLSL `inverse(transMat)`
+// of closest_hit.glsl:163-164 evaluated once per instance at upload instead of twice per TLAS-leaf visit per ray.
+void inverse4(const float* a, float* b)
+{
+    float a00 = a[0], a01 = a[1], a02 = a[2], a03 = a[3], a10 = a[4], a11 = a[5], a12 = a[6], a13 = a[7];
+    float a20 = a[8], a21 = a[9], a22 = a[10], a23 = a[11], a30 = a[12], a31 = a[13], a32 = a[14], a33 = a[15];
+    float s0 = a00 * a11 - a10 * a01, s1 = a00 * a12 - a10 * a02, s2 = a00 * a13 - a10 * a03;
+    float s3 = a01 * a12 - a11 * a02, s4 = a01 * a13 - a11 * a03, s5 = a02 * a13 - a12 * a03;
+    float c5 = a22 * a33 - a32 * a23, c4 = a21 * a33 - a31 * a23, c3 = a21 * a32 - a31 * a22;
+    float c2 = a20 * a33 - a30 * a23, c1 = a20 * a32 - a30 * a22, c0 = a20 * a31 - a30 * a21;
+    float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    float id = 1.0f / det;
+    b[0] = (a11 * c5 - a12 * c4 + a13 * c3) * id;  b[1] = (-a01 * c5 + a02 * c4 - a03 * c3) * id;
+    b[2] = (a31 * s5 - a32 * s4 + a33 * s3) * id;  b[3] = (-a21 * s5 + a22 * s4 - a23 * s3) * id;
+    b[4] = (-a10 * c5 + a12 * c2 - a13 * c1) * id; b[5] = (a00 * c5 - a02 * c2 + a03 * c1) * id;
+    b[6] = (-a30 * s5 + a32 * s2 - a33 * s1) * id; b[7] = (a20 * s5 - a22 * s2 + a23 * s1) * id;
+    b[8] = (a10 * c4 - a11 * c2 + a13 * c0) * id;  b[9] = (-a00 * c4 + a01 * c2 - a03 * c0) * id;
+    b[10] = (a30 * s4 - a31 * s2 + a33 * s0) * id; b[11] = (-a20 * s4 + a21 * s2 - a23 * s0) * id;
+    b[12] = (-a10 * c3 + a11 * c1 - a12 * c0) * id; b[13] = (a00 * c3 - a01 * c1 + a02 * c0) * id;
+    b[14] = (-a30 * s3 + a31 * s1 - a32 * s0) * id; b[15] = (a20 * s3 - a21 * s1 + a22 * s0) * id;
+}
+// inverse(mat3(transform)) (closest_hit.glsl:244), row-major 3x3
+void inverse3(const float* m, float* b)
+{
+    float a00 = m[0], a01 = m[1], a02 = m[2], a10 = m[4], a11 = m[5], a12 = m[6], a20 = m[8], a21 = m[9], a22 = m[10];
+    float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    float det = a00 * c00 + a01 * c01 + a02 * c02;
+    float id = 1.0f / det;
+    b[0] = c00 * id; b[1] = (a02 * a21 - a01 * a22) * id; b[2] = (a01 * a12 - a02 * a11) * id;
+    b[3] = c01 * id; b[4] = (a00 * a22 - a02 * a20) * id; b[5] = (a02 * a10 - a00 * a12) * id;
+    b[6] = c02 * id; b[7] = (a01 * a20 - a00 * a21) * id; b[8] = (a00 * a11 - a01 * a10) * id;
+}
+
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+} // namespace
+
+struct PtbCtx
+{
+    int device = 0, numSMs = 148;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool profiling = false;
+
+    // host copies needed for re-derivation
+    std::vector<float> hNodes, hTransforms, hMaterials;
+    int numNodes = 0, topLevelIndex = 0;
+
+    DevBuf<float> nodes, lights, envImg, envCdf;
+    DevBuf<int> vertIndices;
+    DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre;
+    DevBuf<uchar4> textures;
+    DevScene S{};
+
+    PtbOptions opts{};
+    PtbCamera cam{};
+    FrameParams F{};
+
+    DevBuf<float4> accum, preview;
+    DevBuf<uchar4> out8;
+
+    // wave state
+    size_t slotCap = 0; bool stateGeneral = false;
+    DevBuf<float4> rayO, rayD, thr, rad, hit, med, medCol, shO[2], shD[2], shC[2];
+    DevBuf<uint4> rng;
+    DevBuf<int> hitInst;
+    DevBuf<float2> prevUV;
+    DevBuf<uint32_t> queue[2], counters;
+    DevBuf<DevStats> dstats;
+    uint32_t* hCount = nullptr;   // pinned
+
+    uint64_t samplesRendered = 0, launchesAtCreate = 0;
+    uint64_t lastTraceRays = 0;
+    bool timingValid = false;
+};
+
+namespace {
+
+LaunchCfg cfg(PtbCtx* c) { return LaunchCfg{c->numSMs, (void*)c->stream}; }
+
+uint32_t metaOf(const float* nodes, int idx, std::string& err)
+{
+    const float* n = nodes + (size_t)idx * 9;
+    int leaf = (int)n[8];
+    if (leaf == 0) return (PTB_K_INNER << 30) | (uint32_t)idx;
+    if (leaf > 0)
+    {
+        int first = (int)n[6], cnt = (int)n[7];
+        if (cnt > PTB_MAX_LEAF_TRIS || first < 0 || (uint32_t)first > PTB_MAX_LEAF_SLOT) { err = "leaf exceeds encoding limits"; return PTB_META_NONE; }
+        return (PTB_K_LEAF << 30) | ((uint32_t)cnt << 26) | (uint32_t)first;
+    }
+    return (PTB_K_INST << 30) | (uint32_t)(-leaf - 1);
+}
+
+// number of internal nodes on the deepest root-to-leaf path of the subtree at idx (iterative DFS)
+int innerDepth(const float* nodes, int root, int numNodes)
+{
+    int best = 0;
+    std::vector<std::pair<int, int>> st; st.push_back({root, 0});
+    while (!st.empty())
+    {
+        auto [i, d] = st.back(); st.pop_back();
+        if (i < 0 || i >= numNodes) continue;
+        const float* n = nodes + (size_t)i * 9;
+        if ((int)n[8] == 0) { st.push_back({(int)n[6], d + 1}); st.push_back({(int)n[7], d + 1}); }
+        else best = std::max(best, d);
+    }
+    return best;
+}
+
+// (Re)derive the packed inner nodes for canonical node range [begin,end), plus instTrav/instShade and the stack bound.
+int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
+{
+    const float* N = c->hNodes.data();
+    std::string err;
+    std::vector<float4> inner((size_t)(end - begin) * 4);
+    for (int i = begin; i < end; i++)
+    {
+        const float* n = N + (size_t)i * 9;
+        float4* q = &inner[(size_t)(i - begin) * 4];
+        if ((int)n[8] != 0) { q[0] = q[1] = q[2] = q[3] = make_float4(0, 0, 0, 0); continue; }
+        int l = (int)n[6], r = (int)n[7];
+        REQUIRE(l >= 0 && l < c->numNodes && r >= 0 && r < c->numNodes, PTB_ERR_INVALID_ARGUMENT, "child index out of range");
+        const float* L = N + (size_t)l * 9; const float* R = N + (size_t)r * 9;
+        uint32_t lm = metaOf(N, l, err), rm = metaOf(N, r, err);
+        REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+        q[0] = make_float4(L[0], L[1], L[2], L[3]);
+        q[1] = make_float4(L[4], L[5], R[0], R[1]);
+        q[2] = make_float4(R[2], R[3], R[4], R[5]);
+        q[3] = make_float4(u2f(lm), u2f(rm), 0.f, 0.f);
+    }
+    CK(c->inner.alloc((size_t)c->numNodes * 4));
+    if (end > begin) CK(cudaMemcpyAsync(c->inner.p + (size_t)begin * 4, inner.data(), inner.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+
+    // instance tables from the TLAS leaves (bvh_translator.cpp:70-78: LRLeaf = (blasRoot, materialID, -(inst+1)))
+    const int ni = (int)(c->hTransforms.size() / 16);
+    std::vector<float4> it((size_t)ni * 4), is((size_t)ni * 8);
+    std::vector<uint32_t> rootMeta(ni, PTB_META_NONE); std::vector<int> matID(ni, 0), blasRoot(ni, -1);
+    for (int i = c->topLevelIndex; i < c->numNodes; i++)
+    {
+        const float* n = N + (size_t)i * 9;
+        int leaf = (int)n[8];
+        if (leaf < 0)
+        {
+            int k = -leaf - 1;
+            if (k >= ni) continue;
+            int root = (int)n[6];
+            REQUIRE(root >= 0 && root < c->numNodes, PTB_ERR_INVALID_ARGUMENT, "BLAS root out of range");
+            rootMeta[k] = metaOf(N, root, err); matID[k] = (int)n[7]; blasRoot[k] = root;
+            REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+        }
+    }
+    int maxBlas = 0;
+    {
+        std::vector<int> seen;
+        for (int k = 0; k < ni; k++)
+            if (blasRoot[k] >= 0 && std::find(seen.begin(), seen.end(), blasRoot[k]) == seen.end())
+            { seen.push_back(blasRoot[k]); maxBlas = std::max(maxBlas, innerDepth(N, blasRoot[k], c->numNodes)); }
+    }
+    int tlasDepth = innerDepth(N, c->topLevelIndex, c->numNodes);
+    c->S.stackDepth = std::max(4, 1 + tlasDepth + 1 + maxBlas + 1);
+    REQUIRE(c->S.stackDepth <= 64, PTB_ERR_UNSUPPORTED, "BVH deeper than the 64-entry traversal stack of the reference shader");
+
+    for (int k = 0; k < ni; k++)
+    {
+        const float* D = &c->hTransforms[(size_t)k * 16];
+        float inv[16], inv3[9];
+        inverse4(D, inv); inverse3(D, inv3);
+        it[k * 4 + 0] = make_float4(inv[0], inv[1], inv[2], u2f(rootMeta[k]));
+        it[k * 4 + 1] = make_float4(inv[4], inv[5], inv[6], u2f((uint32_t)matID[k]));
+        it[k * 4 + 2] = make_float4(inv[8], inv[9], inv[10], 0.f);
+        it[k * 4 + 3] = make_float4(inv[12], inv[13], inv[14], 0.f);
+        for (int r = 0; r < 4; r++) is[k * 8 + r] = make_float4(D[r * 4 + 0], D[r * 4 + 1], D[r * 4 + 2], D[r * 4 + 3]);
+        for (int r = 0; r < 3; r++) is[k * 8 + 4 + r] = make_float4(inv3[r * 3 + 0], inv3[r * 3 + 1], inv3[r * 3 + 2], 0.f);
+        is[k * 8 + 7] = make_float4(0, 0, 0, 0);
+    }
+    CK(c->instTrav.upload(it.data(), it.size(), c->stream));
+    CK(c->instShade.upload(is.data(), is.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // staging vectors die at scope exit
+
+    c->S.rootMeta = metaOf(N, c->topLevelIndex, err);
+    REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+    c->S.inner = c->inner.p; c->S.instTrav = c->instTrav.p; c->S.instShade = c->instShade.p;
+    (void)all;
+    return PTB_OK;
+}
+
+void refreshDerivedFlags(PtbCtx* c)
+{
+    const uint32_t f = c->opts.features;
+    bool anyBlend = false, anyEmission = false;
+    const int nm = (int)(c->hMaterials.size() / 32);
+    for (int i = 0; i < nm; i++)
+    {
+        const float* m = &c->hMaterials[(size_t)i * 32];
+        if ((int)m[29] == 1) anyBlend = true;
+        if (m[4] != 0.f || m[5] != 0.f || m[6] != 0.f || m[27] >= 0.f) anyEmission = true;
+    }
+    FrameParams& F = c->F;
+    F.general = ((f & (PTB_OPT_ENVMAP | PTB_OPT_MEDIUM | PTB_OPT_ALPHA_TEST | PTB_OPT_ROUGHNESS_MOLLIFICATION)) != 0u) || c->S.numTextures > 0 || anyEmission;
+    F.inlineShadow = (((f & PTB_OPT_ALPHA_TEST) && !(f & PTB_OPT_MEDIUM) && anyBlend) || ((f & PTB_OPT_MEDIUM) && (f & PTB_OPT_VOL_MIS))) ? 1 : 0;
+}
+
+void refreshFrameParams(PtbCtx* c)
+{
+    FrameParams& F = c->F; const PtbOptions& o = c->opts; const PtbCamera& cam = c->cam;
+    F.features = o.features;
+    if (!(c->S.envImg && c->S.envW > 0)) F.features &= ~(uint32_t)PTB_OPT_ENVMAP;       // Renderer.cpp:404 needs scene->envMap
+    if (c->S.numLights == 0) F.features &= ~(uint32_t)PTB_OPT_LIGHTS;
+    F.maxDepth = o.maxDepth; F.rrDepth = o.rrDepth;
+    F.envMapIntensity = o.envMapIntensity; F.envMapRot = o.envMapRot / 360.0f; F.roughnessMollificationAmt = o.roughnessMollificationAmt;
+    memcpy(F.uniformLightCol, o.uniformLightCol, 12);
+    F.renderW = o.renderW; F.renderH = o.renderH; F.tileW = o.tileW; F.tileH = o.tileH;
+    F.invNumTilesX = (float)o.tileW / o.renderW; F.invNumTilesY = (float)o.tileH / o.renderH;           // Renderer.cpp:293-294
+    F.numTilesX = (int)ceilf((float)o.renderW / o.tileW); F.numTilesY = (int)ceilf((float)o.renderH / o.tileH);   // :296-297
+    memcpy(F.camPos, cam.position, 12); memcpy(F.camRight, cam.right, 12); memcpy(F.camUp, cam.up, 12); memcpy(F.camFwd, cam.forward, 12);
+    F.camScale = tanf(cam.fov * 0.5f); F.camFocalDist = cam.focalDist; F.camAperture = cam.aperture;
+    refreshDerivedFlags(c);
+}
+
+int buildLightsPre(PtbCtx* c, const float* lights, int n)
+{
+    std::vector<float4> lp((size_t)n * 8);
+    for (int i = 0; i < n; i++)
+    {
+        const float* p = lights + (size_t)i * 15;
+        float pos[3] = {p[0], p[1], p[2]}, em[3] = {p[3], p[4], p[5]}, u[3] = {p[6], p[7], p[8]}, v[3] = {p[9], p[10], p[11]};
+        float radius = p[12], area = p[13], type = p[14];
+        // closest_hit.glsl:49-53: normal = normalize(cross(u,v)); plane = (normal, dot(normal,position)); u *= 1/dot(u,u); v *= 1/dot(v,v)
+        float cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+        float len = sqrtf(cx * cx + cy * cy + cz * cz);
+        float nx = cx / len, ny = cy / len, nz = cz / len;
+        float planeW = nx * pos[0] + ny * pos[1] + nz * pos[2];
+        float su = 1.0f / (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), sv = 1.0f / (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        lp[i * 8 + 0] = make_float4(pos[0], pos[1], pos[2], type);
+        lp[i * 8 + 1] = make_float4(em[0], em[1], em[2], area);
+        lp[i * 8 + 2] = make_float4(u[0], u[1], u[2], radius);
+        lp[i * 8 + 3] = make_float4(v[0], v[1], v[2], 0.f);
+        lp[i * 8 + 4] = make_float4(nx, ny, nz, planeW);
+        lp[i * 8 + 5] = make_float4(u[0] * su, u[1] * su, u[2] * su, 0.f);
+        lp[i * 8 + 6] = make_float4(v[0] * sv, v[1] * sv, v[2] * sv, 0.f);
+        lp[i * 8 + 7] = make_float4(0, 0, 0, 0);
+    }
+    CK(c->lightsPre.upload(lp.data(), lp.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->S.lightsPre = c->lightsPre.p;
+    return PTB_OK;
+}
+
+int buildTris(PtbCtx* c, const PtbSceneDesc* d)
+{
+    std::vector<float4> t((size_t)d->numIndices * 3);
+    for (int s = 0; s < d->numIndices; s++)
+    {
+        const int32_t* vi = d->vertIndices + (size_t)s * 3;
+        REQUIRE(vi[0] >= 0 && vi[0] < d->numVertices && vi[1] >= 0 && vi[1] < d->numVertices && vi[2] >= 0 && vi[2] < d->numVertices,
+                PTB_ERR_INVALID_ARGUMENT, "vertex index out of range");
+        const float* v0 = d->verticesUVX + (size_t)vi[0] * 4; const float* v1 = d->verticesUVX + (size_t)vi[1] * 4; const float* v2 = d->verticesUVX + (size_t)vi[2] * 4;
+        // e0 = v1 - v0, e1 = v2 - v0 (closest_hit.glsl:128-129): one IEEE subtraction each, identical wherever it is evaluated
+        float e0[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e1[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+        t[s * 3 + 0] = make_float4(v0[0], v0[1], v0[2], e0[0]);
+        t[s * 3 + 1] = make_float4(e0[1], e0[2], e1[0], e1[1]);
+        t[s * 3 + 2] = make_float4(e1[2], u2f((uint32_t)vi[0]), 0.f, 0.f);
+    }
+    CK(c->tris.upload(t.data(), t.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->S.tris = c->tris.p;
+    return PTB_OK;
+}
+
+int ensureWaveState(PtbCtx* c, size_t slots)
+{
+    const bool gen = c->F.general != 0;
+    if (slots <= c->slotCap && (!gen || c->stateGeneral)) return PTB_OK;
+    size_t n = std::max(slots, c->slotCap);
+    CK(c->rayO.alloc(n)); CK(c->rayD.alloc(n)); CK(c->thr.alloc(n)); CK(c->rad.alloc(n)); CK(c->hit.alloc(n)); CK(c->rng.alloc(n)); CK(c->hitInst.alloc(n));
+    CK(c->queue[0].alloc(n)); CK(c->queue[1].alloc(n));
+    CK(c->shO[1].alloc(n)); CK(c->shD[1].alloc(n)); CK(c->shC[1].alloc(n));
+    if (gen || c->stateGeneral)
+    {
+        CK(c->med.alloc(n)); CK(c->medCol.alloc(n)); CK(c->prevUV.alloc(n));
+        CK(c->shO[0].alloc(n)); CK(c->shD[0].alloc(n)); CK(c->shC[0].alloc(n));
+        c->stateGeneral = true;
+    }
+    CK(c->counters.alloc((size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE));
+    c->slotCap = n;
+    return PTB_OK;
+}
+
+PathState pathState(PtbCtx* c)
+{
+    PathState P{};
+    P.rayO = c->rayO.p; P.rayD = c->rayD.p; P.thr = c->thr.p; P.rad = c->rad.p; P.rng = c->rng.p; P.hit = c->hit.p; P.hitInst = c->hitInst.p;
+    P.med = c->med.p; P.medCol = c->medCol.p; P.prevUV = c->prevUV.p;
+    for (int k = 0; k < 2; k++) { P.shO[k] = c->shO[k].p; P.shD[k] = c->shD[k].p; P.shC[k] = c->shC[k].p; P.queue[k] = c->queue[k].p; }
+    return P;
+}
+
+cudaEvent_t nextTraceEvent(PtbCtx* c)
+{
+    if (c->traceEventsUsed == c->traceEvents.size())
+    {
+        cudaEvent_t e; cudaEventCreate(&e); c->traceEvents.push_back(e);
+    }
+    return c->traceEvents[c->traceEventsUsed++];
+}
+
+// One wavefront: camera -> (trace, shade, shadow)* -> accumulate.
+int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut)
+{
+    W.vw = (W.rw + 7) & ~7; W.vh = (W.rh + 3) & ~3;
+    W.nSlots = (uint32_t)((size_t)W.vw * W.vh * W.nSamples);
+    int rc = ensureWaveState(c, W.nSlots);
+    if (rc) return rc;
+    PathState P = pathState(c);
+    LaunchCfg L = cfg(c);
+    uint32_t* ctr = c->counters.p;
+    CK(cudaMemsetAsync(ctr, 0, (size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE * sizeof(uint32_t), c->stream));
+    ptbk_camera(L, c->S, F, W, P, ctr);
+    const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
+    const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
+    const int nominal = F.maxDepth + 1;
+    int it = 0;
+    while (true)
+    {
+        uint32_t* ci = ctr + (size_t)it * PTB_CTR_STRIDE;
+        uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
+        if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
+        ptbk_trace(L, c->S, F, P, P.queue[it & 1], ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p);
+        if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
+        ptbk_shade(L, c->S, F, P, P.queue[it & 1], ci, cn, P.queue[(it + 1) & 1], c->dstats.p);
+        if (!F.inlineShadow)
+        {
+            if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
+                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
+            if (F.features & PTB_OPT_LIGHTS)
+                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p);
+        }
+        it++;
+        if (it >= PTB_MAX_ITERS) break;                       // alpha-skip re-traces are unbounded in the reference (Q7); hard stop
+        if (it >= nominal)
+        {
+            if (!alphaScene) break;                           // depth == maxDepth terminates every path (pathtrace.glsl:367)
+            CK(cudaMemcpyAsync(c->hCount, cn + CTR_NPATHS, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (*c->hCount == 0) break;
+        }
+    }
+    ptbk_accumulate(L, F, W, P, c->accum.p, previewOut);
+    CK(cudaGetLastError());
+    return PTB_OK;
+}
+
+int allocFrameBuffers(PtbCtx* c)
+{
+    size_t n = (size_t)c->opts.renderW * c->opts.renderH;
+    CK(c->accum.alloc(n)); CK(c->out8.alloc(n));
+    CK(cudaMemsetAsync(c->accum.p, 0, n * sizeof(float4), c->stream));
+    return PTB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t ptb_derive_features(const PtbSceneDesc* s, uint32_t ob)
+{
+    // Renderer.cpp:401-459
+    uint32_t m = 0;
+    if (!s) return 0;
+    if ((ob & 1u) && s->envImg && s->envW > 0) m |= PTB_OPT_ENVMAP;
+    if (s->numLights > 0) m |= PTB_OPT_LIGHTS;
+    if (ob & 2u) m |= PTB_OPT_RR;
+    if (ob & 4u) m |= PTB_OPT_UNIFORM_LIGHT;
+    if (ob & 8u) m |= PTB_OPT_OPENGL_NORMALMAP;
+    if (ob & 16u) m |= PTB_OPT_HIDE_EMITTERS;
+    if (ob & 32u) m |= PTB_OPT_BACKGROUND;
+    if (ob & 64u) m |= PTB_OPT_TRANSPARENT_BACKGROUND;
+    for (int i = 0; i < s->numMaterials; i++) if ((int)s->materials[(size_t)i * 32 + 29] != 0) { m |= PTB_OPT_ALPHA_TEST; break; }
+    if (ob & 128u) m |= PTB_OPT_ROUGHNESS_MOLLIFICATION;
+    for (int i = 0; i < s->numMaterials; i++) if ((int)s->materials[(size_t)i * 32 + 18] != 0) { m |= PTB_OPT_MEDIUM; break; }
+    if (ob & 256u) m |= PTB_OPT_VOL_MIS;
+    return m;
+}
+
+int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** out)
+{
+    REQUIRE(d && o && out, PTB_ERR_INVALID_ARGUMENT, "No Scene Found");     // Renderer.cpp:72-76
+    REQUIRE(d->nodes && d->numNodes > 0 && d->topLevelIndex >= 0 && d->topLevelIndex < d->numNodes, PTB_ERR_INVALID_ARGUMENT, "bad node array");
+    REQUIRE(d->numInstances > 0 && d->transforms && d->materials && d->numMaterials > 0, PTB_ERR_INVALID_ARGUMENT, "bad instance/material arrays");
+    REQUIRE(o->renderW > 0 && o->renderH > 0 && o->tileW > 0 && o->tileH > 0, PTB_ERR_INVALID_ARGUMENT, "bad resolution");
+    REQUIRE((uint32_t)d->numNodes < (1u << 24), PTB_ERR_UNSUPPORTED, "node indices are stored as floats in the reference layout (exact below 2^24)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    {
+        cudaGetLastError();
+        g_err = "no usable CUDA device (libptb200 has no CPU fallback)";
+        return PTB_ERR_NO_DEVICE;
+    }
+    CK(cudaSetDevice(device));
+    PtbCtx* c = new PtbCtx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->numSMs = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+    c->stream = c->ownStream;
+    CK(cudaEventCreate(&c->evStart)); CK(cudaEventCreate(&c->evStop));
+    CK(cudaMallocHost((void**)&c->hCount, sizeof(uint32_t)));
+
+    c->numNodes = d->numNodes; c->topLevelIndex = d->topLevelIndex;
+    c->hNodes.assign(d->nodes, d->nodes + (size_t)d->numNodes * 9);
+    c->hTransforms.assign(d->transforms, d->transforms + (size_t)d->numInstances * 16);
+    c->hMaterials.assign(d->materials, d->materials + (size_t)d->numMaterials * 32);
+
+    cudaStream_t s = c->stream;
+    CK(c->nodes.upload(d->nodes, (size_t)d->numNodes * 9, s));
+    CK(c->vertIndices.upload((const int*)d->vertIndices, (size_t)d->numIndices * 3, s));
+    CK(c->verticesUVX.upload((const float4*)d->verticesUVX, (size_t)d->numVertices, s));
+    CK(c->normalsUVY.upload((const float4*)d->normalsUVY, (size_t)d->numVertices, s));
+    CK(c->materials.upload((const float4*)d->materials, (size_t)d->numMaterials * 8, s));
+    CK(c->transforms.upload((const float4*)d->transforms, (size_t)d->numInstances * 4, s));
+    if (d->numLights > 0) CK(c->lights.upload(d->lights, (size_t)d->numLights * 15, s));
+    if (d->numTextures > 0) CK(c->textures.upload((const uchar4*)d->textures, (size_t)d->numTextures * d->texW * d->texH, s));
+    if (d->envImg && d->envW > 0)
+    {
+        CK(c->envImg.upload(d->envImg, (size_t)d->envW * d->envH * 3, s));
+        CK(c->envCdf.upload(d->envCdf, (size_t)d->envW * d->envH, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    DevScene& S = c->S;
+    S.nodes = c->nodes.p; S.vertIndices = c->vertIndices.p; S.verticesUVX = c->verticesUVX.p; S.normalsUVY = c->normalsUVY.p;
+    S.materials = c->materials.p; S.transforms = c->transforms.p; S.lights = c->lights.p; S.textures = c->textures.p;
+    S.envImg = c->envImg.p; S.envCdf = c->envCdf.p;
+    S.numNodes = d->numNodes; S.topLevelIndex = d->topLevelIndex; S.numIndices = d->numIndices; S.numVertices = d->numVertices;
+    S.numMaterials = d->numMaterials; S.numInstances = d->numInstances; S.numLights = d->numLights;
+    S.numTextures = d->numTextures; S.texW = d->texW; S.texH = d->texH;
+    S.envW = d->envImg ? d->envW : 0; S.envH = d->envImg ? d->envH : 0; S.envTotalSum = d->envTotalSum;
+
+    int rc;
+    if ((rc = buildTris(c, d)) != PTB_OK) { ptb_destroy(c); return rc; }
+    if ((rc = buildLightsPre(c, d->lights, d->numLights)) != PTB_OK) { ptb_destroy(c); return rc; }
+    if ((rc = deriveHierarchy(c, 0, c->numNodes, true)) != PTB_OK) { ptb_destroy(c); return rc; }
+
+    c->opts = *o;
+    // default camera: looking down -z from the origin (the caller sets the real one with ptb_set_camera)
+    c->cam = PtbCamera{{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, 1.0f, 1.0f, 0.0f};
+    refreshFrameParams(c);
+    c->F.cullBoxes = 0;
+    if ((rc = allocFrameBuffers(c)) != PTB_OK) { ptb_destroy(c); return rc; }
+    CK(c->dstats.alloc(1));
+    CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), s));
+    CK(cudaStreamSynchronize(s));
+    c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
+    *out = c;
+    return PTB_OK;
+}
+
+int ptb_destroy(PtbCtx* c)
+{
+    if (!c) return PTB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
+    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
+    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
+    c->rayO.release(); c->rayD.release(); c->thr.release(); c->rad.release(); c->hit.release(); c->med.release(); c->medCol.release();
+    for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
+    c->rng.release(); c->hitInst.release(); c->prevUV.release(); c->counters.release(); c->dstats.release();
+    for (auto e : c->traceEvents) cudaEventDestroy(e);
+    if (c->evStart) cudaEventDestroy(c->evStart);
+    if (c->evStop) cudaEventDestroy(c->evStop);
+    if (c->hCount) cudaFreeHost(c->hCount);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+    return PTB_OK;
+}
+
+int ptb_set_options(PtbCtx* c, const PtbOptions* o)
+{
+    REQUIRE(c && o, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    const bool resized = o->renderW != c->opts.renderW || o->renderH != c->opts.renderH;
+    REQUIRE(o->renderW > 0 && o->renderH > 0 && o->tileW > 0 && o->tileH > 0, PTB_ERR_INVALID_ARGUMENT, "bad resolution");
+    c->opts = *o;
+    int cull = c->F.cullBoxes;
+    refreshFrameParams(c);
+    c->F.cullBoxes = cull;
+    if (resized) return allocFrameBuffers(c);
+    return PTB_OK;
+}
+
+int ptb_resize(PtbCtx* c, int32_t w, int32_t h, int32_t tileW, int32_t tileH)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    PtbOptions o = c->opts; o.renderW = w; o.renderH = h; o.tileW = tileW; o.tileH = tileH;
+    int rc = ptb_set_options(c, &o);
+    if (rc) return rc;
+    c->samplesRendered = 0;
+    return ptb_reset_accum(c);
+}
+
+int ptb_set_camera(PtbCtx* c, const PtbCamera* cam)
+{
+    REQUIRE(c && cam, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    c->cam = *cam;
+    int cull = c->F.cullBoxes;
+    refreshFrameParams(c);
+    c->F.cullBoxes = cull;
+    return PTB_OK;
+}
+
+int ptb_update_instances(PtbCtx* c, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
+                         const float* tlasNodes, int32_t numTlasNodes)
+{
+    REQUIRE(c && transforms && materials && tlasNodes, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    REQUIRE(numInstances == c->S.numInstances, PTB_ERR_INVALID_ARGUMENT, "instance count changed (the reference re-uploads the same-sized arrays)");
+    REQUIRE(numTlasNodes == c->numNodes - c->topLevelIndex, PTB_ERR_INVALID_ARGUMENT, "TLAS slice size mismatch");
+    CK(cudaSetDevice(c->device));
+    c->hTransforms.assign(transforms, transforms + (size_t)numInstances * 16);
+    c->hMaterials.assign(materials, materials + (size_t)numMaterials * 32);
+    memcpy(&c->hNodes[(size_t)c->topLevelIndex * 9], tlasNodes, (size_t)numTlasNodes * 9 * sizeof(float));
+    CK(c->transforms.upload((const float4*)transforms, (size_t)numInstances * 4, c->stream));
+    CK(c->materials.upload((const float4*)materials, (size_t)numMaterials * 8, c->stream));
+    CK(cudaMemcpyAsync(c->nodes.p + (size_t)c->topLevelIndex * 9, tlasNodes, (size_t)numTlasNodes * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->S.materials = c->materials.p; c->S.transforms = c->transforms.p; c->S.numMaterials = numMaterials;
+    int rc = deriveHierarchy(c, c->topLevelIndex, c->numNodes, false);
+    if (rc) return rc;
+    refreshDerivedFlags(c);
+    return PTB_OK;
+}
+
+int ptb_update_envmap(PtbCtx* c, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum)
+{
+    REQUIRE(c && img && cdf && w > 0 && h > 0, PTB_ERR_INVALID_ARGUMENT, "bad environment map");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->envImg.release(); c->envCdf.release();
+    CK(c->envImg.upload(img, (size_t)w * h * 3, c->stream));
+    CK(c->envCdf.upload(cdf, (size_t)w * h, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->S.envImg = c->envImg.p; c->S.envCdf = c->envCdf.p; c->S.envW = w; c->S.envH = h; c->S.envTotalSum = totalSum;
+    int cull = c->F.cullBoxes;
+    refreshFrameParams(c);
+    c->F.cullBoxes = cull;
+    return PTB_OK;
+}
+
+int ptb_reset_accum(PtbCtx* c)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->accum.p, 0, (size_t)c->opts.renderW * c->opts.renderH * sizeof(float4), c->stream));
+    return PTB_OK;
+}
+
+static void beginTiming(PtbCtx* c) { c->traceEventsUsed = 0; cudaEventRecord(c->evStart, c->stream); }
+static void endTiming(PtbCtx* c) { cudaEventRecord(c->evStop, c->stream); c->timingValid = true; }
+
+int ptb_render_tile(PtbCtx* c, int32_t tx, int32_t ty, int32_t frameNum)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    const FrameParams& F = c->F;
+    REQUIRE(tx >= 0 && ty >= 0 && tx < F.numTilesX && ty < F.numTilesY, PTB_ERR_INVALID_ARGUMENT, "tile out of range");
+    CK(cudaSetDevice(c->device));
+    WaveParams W{};
+    W.x0 = tx * F.tileW; W.y0 = ty * F.tileH;
+    W.rw = std::min(F.tileW, F.renderW - W.x0); W.rh = std::min(F.tileH, F.renderH - W.y0);     // overhang clipped (Q15)
+    W.nSamples = 1; W.firstSample = 1; W.sampleStride = 1; W.fixedFrame = frameNum; W.previewMode = 0;
+    beginTiming(c);
+    int rc = renderWave(c, F, W, nullptr);
+    endTiming(c);
+    return rc;
+}
+
+int ptb_render_samples(PtbCtx* c, int32_t firstSample, int32_t nSamples, int32_t sampleStride)
+{
+    REQUIRE(c && firstSample >= 1 && nSamples >= 0 && sampleStride >= 1, PTB_ERR_INVALID_ARGUMENT, "bad sample range");
+    CK(cudaSetDevice(c->device));
+    const FrameParams& F = c->F;
+    int spw = c->opts.samplesPerWave;
+    if (spw <= 0)
+    {   // auto: keep ~8M paths in flight (fills 148 SMs many times over, bounds state to ~1.5 GB)
+        size_t px = (size_t)F.renderW * F.renderH;
+        spw = (int)std::max<size_t>(1, std::min<size_t>(16, (8u << 20) / std::max<size_t>(px, 1)));
+    }
+    beginTiming(c);
+    int done = 0;
+    while (done < nSamples)
+    {
+        int n = std::min(spw, nSamples - done);
+        WaveParams W{};
+        W.x0 = 0; W.y0 = 0; W.rw = F.renderW; W.rh = F.renderH;
+        W.nSamples = n; W.firstSample = firstSample + done * sampleStride; W.sampleStride = sampleStride; W.fixedFrame = -1; W.previewMode = 0;
+        int rc = renderWave(c, F, W, nullptr);
+        if (rc) return rc;
+        done += n;
+    }
+    endTiming(c);
+    c->samplesRendered += (uint64_t)nSamples;
+    return PTB_OK;
+}
+
+int ptb_render_preview(PtbCtx* c, int32_t w, int32_t h, float* outRgba)
+{
+    REQUIRE(c && outRgba && w > 0 && h > 0, PTB_ERR_INVALID_ARGUMENT, "bad preview target");
+    CK(cudaSetDevice(c->device));
+    CK(c->preview.alloc((size_t)w * h));
+    FrameParams F = c->F;
+    F.maxDepth = 2;                                           // Renderer.cpp:798 (scene->dirty ? 2 : maxDepth)
+    WaveParams W{};
+    W.x0 = 0; W.y0 = 0; W.rw = w; W.rh = h; W.nSamples = 1; W.firstSample = 1; W.sampleStride = 1; W.fixedFrame = 1; W.previewMode = 1;
+    int rc = renderWave(c, F, W, c->preview.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outRgba, c->preview.p, (size_t)w * h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_read_accum_f32(PtbCtx* c, float* out)
+{
+    REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->accum.p, (size_t)c->opts.renderW * c->opts.renderH * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_write_accum_f32(PtbCtx* c, const float* in)
+{
+    REQUIRE(c && in, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->accum.p, in, (size_t)c->opts.renderW * c->opts.renderH * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_accum_device_ptr(PtbCtx* c, void** p, uint64_t* nbytes)
+{
+    REQUIRE(c && p, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    *p = c->accum.p;
+    if (nbytes) *nbytes = (uint64_t)c->opts.renderW * c->opts.renderH * sizeof(float4);
+    return PTB_OK;
+}
+
+int ptb_read_output_rgba8(PtbCtx* c, float invSampleCounter, uint8_t* out)
+{
+    REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    const PtbOptions& o = c->opts;
+    ptbk_tonemap(cfg(c), c->accum.p, o.renderW, o.renderH, invSampleCounter, o.enableTonemap, o.enableAces, o.simpleAcesFit, o.backgroundCol, c->F.features, c->out8.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->out8.p, (size_t)o.renderW * o.renderH * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_get_stats(PtbCtx* c, PtbStats* out)
+{
+    REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    DevStats ds{};
+    CK(cudaMemcpy(&ds, c->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->pathSegments = ds.pathSegments; out->shadowRays = ds.shadowRays; out->samplesRendered = c->samplesRendered;
+    out->kernelLaunches = (uint64_t)ptbk_kernel_launch_count() - c->launchesAtCreate;
+    if (c->timingValid) cudaEventElapsedTime(&out->lastRenderMs, c->evStart, c->evStop);
+    if (c->profiling)
+    {
+        float tot = 0.f;
+        for (size_t i = 0; i + 1 < c->traceEventsUsed; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, c->traceEvents[i], c->traceEvents[i + 1]); tot += ms; }
+        out->lastTraceMs = tot;
+    }
+    return PTB_OK;
+}
+
+int ptb_reset_stats(PtbCtx* c)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), c->stream));
+    c->samplesRendered = 0;
+    return PTB_OK;
+}
+
+int ptb_set_profiling(PtbCtx* c, int32_t enable) { REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context"); c->profiling = enable != 0; return PTB_OK; }
+
+int ptb_set_stream(PtbCtx* c, void* s)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return PTB_OK;
+}
+
+int ptb_synchronize(PtbCtx* c)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+// internal knob used by tests/bench: conservative t-culling of child boxes (identical hits, fewer node fetches)
+int ptb_set_cull(PtbCtx* c, int32_t enable) { REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context"); c->F.cullBoxes = enable ? 1 : 0; return PTB_OK; }
+
+int ptb_trace_closest_device(PtbCtx* c, const void* devRays, int64_t n, int32_t depth, void* devHits)
+{
+    REQUIRE(c && devRays && devHits && n >= 0, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return PTB_OK;
+    ptbk_trace_closest_batch(cfg(c), c->S, c->F, (const float*)devRays, n, depth, devHits);
+    CK(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_trace_closest(PtbCtx* c, const float* rays, int64_t n, int32_t depth, PtbHit* out)
+{
+    REQUIRE(c && (n == 0 || (rays && out)) && n >= 0, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return PTB_OK;
+    CK(cudaSetDevice(c->device));
+    DevBuf<float> dr; DevBuf<PtbHit> dh;
+    CK(dr.upload(rays, (size_t)n * 6, c->stream));
+    CK(dh.alloc((size_t)n));
+    int rc = ptb_trace_closest_device(c, dr.p, n, depth, dh.p);
+    if (rc == PTB_OK)
+    {
+        cudaError_t e = cudaMemcpyAsync(out, dh.p, (size_t)n * sizeof(PtbHit), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { g_err = cudaGetErrorString(e); rc = PTB_ERR_CUDA; }
+    }
+    dr.release(); dh.release();
+    return rc;
+}
+
+int ptb_trace_any(PtbCtx* c, const float* rays, const float* maxDist, int64_t n, int32_t* out)
+{
+    REQUIRE(c && (n == 0 || (rays && maxDist && out)) && n >= 0, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return PTB_OK;
+    CK(cudaSetDevice(c->device));
+    DevBuf<float> dr, dm; DevBuf<int> dout;
+    CK(dr.upload(rays, (size_t)n * 6, c->stream));
+    CK(dm.upload(maxDist, (size_t)n, c->stream));
+    CK(dout.alloc((size_t)n));
+    ptbk_trace_any_batch(cfg(c), c->S, c->F, dr.p, dm.p, n, dout.p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dr.release(); dm.release(); dout.release();
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    return PTB_OK;
+}
+
+static int bsdfBatch(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out, int sample)
+{
+    REQUIRE(c && (n == 0 || (q && out)) && n >= 0, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return PTB_OK;
+    CK(cudaSetDevice(c->device));
+    DevBuf<PtbBsdfQuery> dq; DevBuf<PtbBsdfResult> dres;
+    CK(dq.upload(q, (size_t)n, c->stream));
+    CK(dres.alloc((size_t)n));
+    ptbk_bsdf_batch(cfg(c), dq.p, n, dres.p, sample);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dres.p, (size_t)n * sizeof(PtbBsdfResult), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dq.release(); dres.release();
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    return PTB_OK;
+}
+int ptb_bsdf_eval(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 0); }
+int ptb_bsdf_sample(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 1); }
+
+int ptb_camera_rays(PtbCtx* c, int32_t sample, float* outRays)
+{
+    REQUIRE(c && outRays && sample >= 1, PTB_ERR_INVALID_ARGUMENT, "bad argument");
+    CK(cudaSetDevice(c->device));
+    size_t n = (size_t)c->F.renderW * c->F.renderH;
+    DevBuf<float> d;
+    CK(d.alloc(n * 6));
+    WaveParams W{}; W.rw = c->F.renderW; W.rh = c->F.renderH; W.firstSample = sample; W.sampleStride = 1; W.fixedFrame = -1; W.nSamples = 1;
+    ptbk_camera_rays(cfg(c), c->F, W, d.p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(outRays, d.p, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.release();
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    return PTB_OK;
+}
+
+int ptb_read_nodes(PtbCtx* c, float* out, int32_t numNodes)
+{
+    REQUIRE(c && out && numNodes == c->numNodes, PTB_ERR_INVALID_ARGUMENT, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->nodes.p, (size_t)numNodes * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_stack_depth(PtbCtx* c, int32_t* out) { REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument"); *out = c->S.stackDepth; return PTB_OK; }
+
+} // extern "C"

@@ -1,0 +1,779 @@
+// ptb_device.cuh — device-side building blocks of the sm_100a wavefront path tracer: exact-arithmetic two-level BVH
+// traversal over the derived 64-byte node layout, analytic-light tests, Disney BSDF, light / env-map sampling.
+//
+// What each block computes is defined by the reference shaders (cited per function, paths relative to
+// /root/reference/src/shaders/common); how it is computed (wavefront stages, packed nodes, shared-memory stacks,
+// pre-inverted instance transforms) is specific to this implementation.
+#pragma once
+#include "ptb_internal.h"
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#define PTB_PI         3.14159265358979323f
+#define PTB_INV_PI     0.31830988618379067f
+#define PTB_TWO_PI     6.28318530717958648f
+#define PTB_INV_TWO_PI 0.15915494309189533f
+#define PTB_INV_4_PI   0.07957747154594766f
+#define PTB_EPS        0.0003f
+#define PTB_INF        1000000.0f
+
+namespace ptb {
+
+// ------------------------------------------------------------------ float3 helpers (contractable math) ----------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float a) { return make_float3(a, a, a); }
+__device__ __forceinline__ float3 f3(const float4& v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float3 operator+(float3 a, float s) { return f3(a.x + s, a.y + s, a.z + s); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3& operator+=(float3& a, float3 b) { a = a + b; return a; }
+__device__ __forceinline__ float3& operator*=(float3& a, float3 b) { a = a * b; return a; }
+__device__ __forceinline__ float3& operator*=(float3& a, float s) { a = a * s; return a; }
+__device__ __forceinline__ float3& operator/=(float3& a, float s) { a = a / s; return a; }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ float3 normalize(float3 a) { return a / sqrtf(dot(a, a)); }
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float3 mix(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float3 vpow(float3 a, float e) { return f3(powf(a.x, e), powf(a.y, e), powf(a.z, e)); }
+__device__ __forceinline__ float3 vexp(float3 a) { return f3(expf(a.x), expf(a.y), expf(a.z)); }
+__device__ __forceinline__ float3 reflect(float3 I, float3 N) { return I - N * (2.0f * dot(N, I)); }
+__device__ __forceinline__ float3 refract(float3 I, float3 N, float eta)
+{
+    float d = dot(N, I);
+    float k = 1.0f - eta * eta * (1.0f - d * d);
+    if (k < 0.0f) return f3(0.0f);
+    return I * eta - N * (eta * d + sqrtf(k));
+}
+__device__ __forceinline__ float Luminance(float3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; }   // globals.glsl:173
+
+// ------------------------------------------------------------------ exact (never contracted) arithmetic ---------
+// The hit decisions (which primitive / instance / light, and t) must agree bit-for-bit with a host traversal compiled
+// without FMA contraction, so the intersection math uses round-to-nearest intrinsics that ptxas never fuses.
+__device__ __forceinline__ float xm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xdot(float3 a, float3 b) { return xa(xa(xm(a.x, b.x), xm(a.y, b.y)), xm(a.z, b.z)); }
+__device__ __forceinline__ float3 xcross(float3 a, float3 b)
+{
+    return f3(xs(xm(a.y, b.z), xm(a.z, b.y)), xs(xm(a.z, b.x), xm(a.x, b.z)), xs(xm(a.x, b.y), xm(a.y, b.x)));
+}
+__device__ __forceinline__ float3 xsub(float3 a, float3 b) { return f3(xs(a.x, b.x), xs(a.y, b.y), xs(a.z, b.z)); }
+__device__ __forceinline__ float3 xmad(float3 o, float3 d, float t) { return f3(xa(o.x, xm(d.x, t)), xa(o.y, xm(d.y, t)), xa(o.z, xm(d.z, t))); }
+
+// ------------------------------------------------------------------ RNG: globals.glsl:144-166 -------------------
+struct Rng
+{
+    uint4 s;
+    __device__ __forceinline__ void init(uint32_t px, uint32_t py, uint32_t frame) { s = make_uint4(px, py, frame, px + py); }
+    __device__ __forceinline__ float rand()
+    {
+        uint32_t x = s.x * 1664525u + 1013904223u, y = s.y * 1664525u + 1013904223u, z = s.z * 1664525u + 1013904223u,
+                 w = s.w * 1664525u + 1013904223u;
+        x += y * w; y += z * x; z += x * y; w += y * z;
+        x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
+        x += y * w; y += z * x; z += x * y; w += y * z;
+        s = make_uint4(x, y, z, w);
+        return __fdiv_rn(__uint2float_rn(x), 4294967296.0f);   // float(seed.x) / float(0xffffffffu): in [0,1]
+    }
+};
+
+// ------------------------------------------------------------------ traversal -----------------------------------
+struct HitRec
+{
+    float t;        // PTB_INF on miss
+    float bu, bv;   // uvt.x, uvt.y of the winning triangle
+    int prim;       // leaf-ref slot or -1
+    int inst;       // instance (triangle hit) / -1
+    int light;      // analytic light index (light hit) / -1
+};
+
+// intersection.glsl:68-82 with the ray's reciprocal direction hoisted (1.0/dir is the same IEEE division the shader performs).
+__device__ __forceinline__ float aabbHit(float minx, float miny, float minz, float maxx, float maxy, float maxz, float3 o, float3 inv, float& entry)
+{
+    float fx = xm(xs(maxx, o.x), inv.x), fy = xm(xs(maxy, o.y), inv.y), fz = xm(xs(maxz, o.z), inv.z);
+    float nx = xm(xs(minx, o.x), inv.x), ny = xm(xs(miny, o.y), inv.y), nz = xm(xs(minz, o.z), inv.z);
+    float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+    float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+    entry = t0;
+    return (t1 >= t0) ? (t0 > 0.f ? t0 : t1) : -1.0f;
+}
+
+// intersection.glsl:47-66 (RectIntersect) on pre-scaled u,v and precomputed plane (closest_hit.glsl:49-53 hoisted to upload time)
+__device__ __forceinline__ float rectHit(float3 pos, float3 uS, float3 vS, float3 n, float planeW, float3 o, float3 d)
+{
+    float dt = xdot(d, n);
+    float t = xd(xs(planeW, xdot(n, o)), dt);
+    if (t > PTB_EPS)
+    {
+        float3 p = xmad(o, d, t);
+        float3 vi = xsub(p, pos);
+        float a1 = xdot(uS, vi);
+        if (a1 >= 0.0f && a1 <= 1.0f)
+        {
+            float a2 = xdot(vS, vi);
+            if (a2 >= 0.0f && a2 <= 1.0f) return t;
+        }
+    }
+    return PTB_INF;
+}
+// intersection.glsl:25-45
+__device__ __forceinline__ float sphereHit(float rad, float3 pos, float3 o, float3 d)
+{
+    float3 op = xsub(pos, o);
+    float b = xdot(op, d);
+    float det = xa(xs(xm(b, b), xdot(op, op)), xm(rad, rad));
+    if (det < 0.0f) return PTB_INF;
+    det = __fsqrt_rn(det);
+    float t1 = xs(b, det);
+    if (t1 > 0.001f) return t1;
+    float t2 = xa(b, det);
+    if (t2 > 0.001f) return t2;
+    return PTB_INF;
+}
+
+struct LightPre   // 8 float4, built at upload (ptb_api.cpp buildLightsPre)
+{
+    float3 position; float type; float3 emission; float area; float3 u; float radius; float3 v; float3 normal; float planeW;
+    float3 uS, vS;
+};
+__device__ __forceinline__ void loadLightGeom(const DevScene& S, int i, float3& pos, float& type, float& radius, float3& n, float& planeW, float3& uS, float3& vS)
+{
+    const float4* p = S.lightsPre + (size_t)i * 8;
+    float4 a = __ldg(p), c = __ldg(p + 2), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
+    pos = f3(a); type = a.w; radius = c.w; n = f3(e); planeW = e.w; uS = f3(f); vS = f3(g);
+}
+
+// Light loop of ClosestHit (closest_hit.glsl:28-86): nearest light, first index wins ties (strict <).
+__device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float3 d, float& t, int& light)
+{
+    for (int i = 0; i < S.numLights; i++)
+    {
+        float3 pos, n, uS, vS; float type, radius, planeW;
+        loadLightGeom(S, i, pos, type, radius, n, planeW, uS, vS);
+        float dist = PTB_INF;
+        if (type == 0.0f)
+        {
+            if (xdot(n, d) > 0.f) continue;
+            dist = rectHit(pos, uS, vS, n, planeW, o, d);
+        }
+        else if (type == 1.0f)
+            dist = sphereHit(radius, pos, o, d);
+        else
+            continue;
+        if (dist < 0.f) dist = PTB_INF;
+        if (dist < t) { t = dist; light = i; }
+    }
+}
+// Light loop of AnyHit (anyhit.glsl:28-63): two-sided quads.
+__device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d, float maxDist)
+{
+    for (int i = 0; i < S.numLights; i++)
+    {
+        float3 pos, n, uS, vS; float type, radius, planeW;
+        loadLightGeom(S, i, pos, type, radius, n, planeW, uS, vS);
+        float dist;
+        if (type == 0.0f) dist = rectHit(pos, uS, vS, n, planeW, o, d);
+        else if (type == 1.0f) dist = sphereHit(radius, pos, o, d);
+        else continue;
+        if (dist > 0.0f && dist < maxDist) return true;
+    }
+    return false;
+}
+
+// Stack policies: shared memory (one column per thread, conflict-free) for the wavefront trace kernels,
+// thread-local array for the rarely used inline traversal inside the shade kernel.
+struct SmemStack
+{
+    uint32_t* base; int stride;
+    __device__ __forceinline__ void set(int i, uint32_t v) { base[i * stride] = v; }
+    __device__ __forceinline__ uint32_t get(int i) const { return base[i * stride]; }
+};
+struct LocalStack
+{
+    uint32_t a[64];
+    __device__ __forceinline__ void set(int i, uint32_t v) { a[i] = v; }
+    __device__ __forceinline__ uint32_t get(int i) const { return a[i]; }
+};
+
+// Alpha test hook of AnyHit (anyhit.glsl:118-141), only in inline mode / MASK materials.
+struct NoAlpha { };
+
+// Two-level traversal (closest_hit.glsl:88-218 / anyhit.glsl:65-213) over the derived layout:
+//   inner[i]   = { lmin.xyz lmax.x | lmax.yz rmin.xy | rmin.z rmax.xyz | lmeta rmeta - - }   (one 64-byte fetch per step;
+//                the reference reads LRLeaf of the node and then both children's boxes from two other nodes)
+//   tris[slot] = { v0.xyz e0.x | e0.yz e1.xy | e1.z vertIndex.x - - }
+//   instTrav[k]= rows of inverse(transform) + {rootMeta, matID}
+// Visiting order, near/far rule (left first on ties), strict-< acceptance and the un-normalised transformed direction are the
+// reference's, so primitive/instance IDs and t are identical to a host traversal of the canonical array.
+// ANY: return true at the first accepted hit with t < tmax.  alphaFn(slot, inst, u, v) -> accept? (only when ALPHA)
+template <bool ANY, bool ALPHA, class Stack, class AlphaFn>
+__device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, float tmax, bool cull, Stack& stk, HitRec& h, AlphaFn alphaFn)
+{
+    float t = tmax;
+    int sp = 0;
+    stk.set(sp++, PTB_META_NONE);
+    uint32_t cur = S.rootMeta;
+    bool inBlas = false;
+    int curInst = -1;
+    float3 ro = o, rd = d;
+    float3 inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
+
+    while (true)
+    {
+        const uint32_t kind = cur >> 30;
+        if (kind == PTB_K_INNER)
+        {
+            const float4* n = S.inner + (size_t)cur * 4;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            float e0, e1;
+            float lh = aabbHit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ro, inv, e0);
+            float rh = aabbHit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ro, inv, e1);
+            if (cull) { if (e0 > t) lh = -1.0f; if (e1 > t) rh = -1.0f; }
+            const uint32_t lm = __float_as_uint(q3.x), rm = __float_as_uint(q3.y);
+            if (lh > 0.0f && rh > 0.0f)
+            {
+                uint32_t deferred;
+                if (lh > rh) { cur = rm; deferred = lm; } else { cur = lm; deferred = rm; }
+                stk.set(sp++, deferred);
+                continue;
+            }
+            else if (lh > 0.f) { cur = lm; continue; }
+            else if (rh > 0.f) { cur = rm; continue; }
+        }
+        else if (kind == PTB_K_LEAF)
+        {
+            const uint32_t first = cur & PTB_MAX_LEAF_SLOT, cnt = (cur >> 26) & 15u;
+            for (uint32_t i = 0; i < cnt; i++)
+            {
+                const float4* tp = S.tris + (size_t)(first + i) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                const float3 v0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x);
+                // closest_hit.glsl:127-141 (Moeller-Trumbore, three IEEE divisions by det, no det==0 guard)
+                float3 pv = xcross(rd, e1);
+                float det = xdot(e0, pv);
+                float3 tv = xsub(ro, v0);
+                float3 qv = xcross(tv, e0);
+                float ux = xd(xdot(tv, pv), det);
+                float uy = xd(xdot(rd, qv), det);
+                float uz = xd(xdot(e1, qv), det);
+                float uw = xs(xs(1.0f, ux), uy);
+                if (ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < t)
+                {
+                    if constexpr (ANY)
+                    {
+                        if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) return true; }
+                        else return true;
+                    }
+                    else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
+                }
+            }
+        }
+        else if (kind == PTB_K_INST)
+        {
+            curInst = (int)(cur & 0x3FFFFFFFu);
+            const float4* ip = S.instTrav + (size_t)curInst * 4;
+            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            // rTrans = inverse(transform) * (origin,1) / (direction,0)  (closest_hit.glsl:163-164); the inverse is precomputed at upload
+            ro = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
+                    xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
+                    xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
+            rd = f3(xa(xa(xa(xm(d.x, r0.x), xm(d.y, r1.x)), xm(d.z, r2.x)), xm(0.0f, r3.x)),
+                    xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
+                    xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
+            inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
+            stk.set(sp++, PTB_META_NONE);           // marker (closest_hit.glsl:166-167)
+            cur = __float_as_uint(r0.w);            // BLAS root meta
+            inBlas = true;
+            continue;
+        }
+        cur = stk.get(--sp);
+        if (inBlas && cur == PTB_META_NONE)         // closest_hit.glsl:208-216
+        {
+            inBlas = false;
+            cur = stk.get(--sp);
+            ro = o; rd = d;
+            inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
+        }
+        if (cur == PTB_META_NONE) break;
+    }
+    if (!ANY) h.t = t;
+    return false;
+}
+
+// ------------------------------------------------------------------ sampling.glsl -------------------------------
+__device__ __forceinline__ float GTR1(float NDotH, float a)   // :25-32
+{
+    if (a >= 1.0f) return PTB_INV_PI;
+    float a2 = a * a;
+    float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
+    return (a2 - 1.0f) / (PTB_PI * logf(a2) * t);
+}
+__device__ __forceinline__ float3 SampleGTR1(float rgh, float r1, float r2)   // :34-47
+{
+    float a = fmaxf(0.001f, rgh);
+    float a2 = a * a;
+    float phi = r1 * PTB_TWO_PI;
+    float cosTheta = sqrtf((1.0f - powf(a2, 1.0f - r2)) / (1.0f - a2));
+    float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
+    return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+}
+__device__ __forceinline__ float3 SampleGGXVNDF(float3 V, float ax, float ay, float r1, float r2)   // :70-88
+{
+    float3 Vh = normalize(f3(ax * V.x, ay * V.y, V.z));
+    float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * (1.0f / sqrtf(lensq)) : f3(1, 0, 0);
+    float3 T2 = cross(Vh, T1);
+    float r = sqrtf(r1);
+    float phi = 2.0f * PTB_PI * r2;
+    float sp, cp; sincosf(phi, &sp, &cp);
+    float t1 = r * cp;
+    float t2 = r * sp;
+    float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    float3 Nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+    return normalize(f3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
+}
+__device__ __forceinline__ float GTR2Aniso(float NDotH, float HDotX, float HDotY, float ax, float ay)   // :90-96
+{
+    float a = HDotX / ax;
+    float b = HDotY / ay;
+    float c = a * a + b * b + NDotH * NDotH;
+    return 1.0f / (PTB_PI * ax * ay * c * c);
+}
+__device__ __forceinline__ float SmithG(float NDotV, float alphaG)   // :109-114
+{
+    float a = alphaG * alphaG;
+    float b = NDotV * NDotV;
+    return (2.0f * NDotV) / (NDotV + sqrtf(a + b - a * b));
+}
+__device__ __forceinline__ float SmithGAniso(float NDotV, float VDotX, float VDotY, float ax, float ay)   // :116-122
+{
+    float a = VDotX * ax;
+    float b = VDotY * ay;
+    float c = NDotV;
+    return (2.0f * NDotV) / (NDotV + sqrtf(a * a + b * b + c * c));
+}
+__device__ __forceinline__ float SchlickWeight(float u)   // :124-129
+{
+    float m = clampf(1.0f - u, 0.0f, 1.0f);
+    float m2 = m * m;
+    return m2 * m2 * m;
+}
+__device__ __forceinline__ float DielectricFresnel(float cosThetaI, float eta)   // :131-145
+{
+    float sinThetaTSq = eta * eta * (1.0f - cosThetaI * cosThetaI);
+    if (sinThetaTSq > 1.0f) return 1.0f;
+    float cosThetaT = sqrtf(fmaxf(1.0f - sinThetaTSq, 0.0f));
+    float rs = (eta * cosThetaT - cosThetaI) / (eta * cosThetaT + cosThetaI);
+    float rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    return 0.5f * (rs * rs + rp * rp);
+}
+__device__ __forceinline__ float3 CosineSampleHemisphere(float r1, float r2)   // :147-156
+{
+    float3 dir;
+    float r = sqrtf(r1);
+    float phi = PTB_TWO_PI * r2;
+    float sp, cp; sincosf(phi, &sp, &cp);
+    dir.x = r * cp;
+    dir.y = r * sp;
+    dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+    return dir;
+}
+__device__ __forceinline__ float3 UniformSampleHemisphere(float r1, float r2)   // :158-163
+{
+    float r = sqrtf(fmaxf(0.0f, 1.0f - r1 * r1));
+    float phi = PTB_TWO_PI * r2;
+    float sp, cp; sincosf(phi, &sp, &cp);
+    return f3(r * cp, r * sp, r1);
+}
+__device__ __forceinline__ float PowerHeuristic(float a, float b)   // :173-177
+{
+    float t = a * a;
+    return t / (b * b + t);
+}
+__device__ __forceinline__ void Onb(float3 N, float3& T, float3& B)   // :179-184
+{
+    float3 up = fabsf(N.z) < 0.9999999f ? f3(0, 0, 1) : f3(1, 0, 0);
+    T = normalize(cross(up, N));
+    B = cross(N, T);
+}
+__device__ __forceinline__ float3 SampleHG(float3 V, float g, float r1, float r2)   // :250-270
+{
+    float cosTheta;
+    if (fabsf(g) < 0.001f) cosTheta = 1 - 2 * r2;
+    else
+    {
+        float sqrTerm = (1 - g * g) / (1 + g - 2 * g * r2);
+        cosTheta = -(1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+    }
+    float phi = r1 * PTB_TWO_PI;
+    float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
+    float3 v1, v2;
+    Onb(V, v1, v2);
+    return sinTheta * cosPhi * v1 + sinTheta * sinPhi * v2 + cosTheta * V;
+}
+__device__ __forceinline__ float PhaseHG(float cosTheta, float g)   // :272-276
+{
+    float denom = 1 + g * g + 2 * g * cosTheta;
+    return PTB_INV_4_PI * (1 - g * g) / (denom * sqrtf(denom));
+}
+
+// ------------------------------------------------------------------ material / surface state --------------------
+struct Material   // globals.glsl:60-83
+{
+    float3 baseColor; float opacity; int alphaMode; float alphaCutoff; float3 emission; float anisotropic, metallic, roughness,
+        subsurface, specularTint, sheen, sheenTint, clearcoat, clearcoatRoughness, specTrans, ior, ax, ay;
+    int medType; float medDensity; float3 medColor; float medAniso;
+};
+
+struct LightSample { float3 normal, emission, direction; float dist, pdf; };
+
+// sampling.glsl:186-248 (r1,r2 drawn by the caller in the reference order; distant lights draw none)
+__device__ __forceinline__ void SampleOneLight(const DevScene& S, int idx, float3 scatterPos, Rng& rng, LightSample& ls, float& area)
+{
+    const float4* p = S.lightsPre + (size_t)idx * 8;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), dd = __ldg(p + 3);
+    float3 position = f3(a), emission = f3(b), u = f3(c), v = f3(dd);
+    int type = (int)a.w; area = b.w; float radius = c.w;
+    float nl = (float)S.numLights;
+    if (type == 0)
+    {
+        float r1 = rng.rand(), r2 = rng.rand();
+        float3 lightSurfacePos = position + u * r1 + v * r2;
+        ls.direction = lightSurfacePos - scatterPos;
+        ls.dist = length(ls.direction);
+        float distSq = ls.dist * ls.dist;
+        ls.direction /= ls.dist;
+        ls.normal = normalize(cross(u, v));
+        ls.emission = emission * nl;
+        ls.pdf = distSq / (area * fabsf(dot(ls.normal, ls.direction)));
+    }
+    else if (type == 1)
+    {
+        float r1 = rng.rand(), r2 = rng.rand();
+        float3 c2s = scatterPos - position;
+        float distToCenter = length(c2s);
+        c2s /= distToCenter;
+        float3 sampledDir = UniformSampleHemisphere(r1, r2);
+        float3 T, B;
+        Onb(c2s, T, B);
+        sampledDir = T * sampledDir.x + B * sampledDir.y + c2s * sampledDir.z;
+        float3 lightSurfacePos = position + sampledDir * radius;
+        ls.direction = lightSurfacePos - scatterPos;
+        ls.dist = length(ls.direction);
+        float distSq = ls.dist * ls.dist;
+        ls.direction /= ls.dist;
+        ls.normal = normalize(lightSurfacePos - position);
+        ls.emission = emission * nl;
+        ls.pdf = distSq / (area * 0.5f * fabsf(dot(ls.normal, ls.direction)));
+    }
+    else
+    {
+        ls.direction = normalize(position);
+        ls.normal = normalize(scatterPos - position);
+        ls.emission = emission * nl;
+        ls.dist = PTB_INF;
+        ls.pdf = 1.0f;
+    }
+}
+
+// ------------------------------------------------------------------ disney.glsl ---------------------------------
+__device__ __forceinline__ float3 ToWorld(float3 X, float3 Y, float3 Z, float3 V) { return V.x * X + V.y * Y + V.z * Z; }
+__device__ __forceinline__ float3 ToLocal(float3 X, float3 Y, float3 Z, float3 V) { return f3(dot(V, X), dot(V, Y), dot(V, Z)); }
+
+struct Lobes { float diffPr, dielectricPr, metalPr, glassPr, clearCtPr, dielectricWt, metalWt, glassWt; float F0; float3 Csheen, Cspec0; };
+
+// TintColors (disney.glsl:49-59) + model weights / lobe probabilities (:155-179, :272-294)
+__device__ __forceinline__ void lobeSetup(const Material& m, float eta, float Vz, Lobes& p)
+{
+    float lum = Luminance(m.baseColor);
+    float3 ctint = lum > 0.0f ? m.baseColor / lum : f3(1.0f);
+    float F0 = (1.0f - eta) / (1.0f + eta);
+    F0 *= F0;
+    p.F0 = F0;
+    p.Cspec0 = F0 * mix(f3(1.0f), ctint, m.specularTint);
+    p.Csheen = mix(f3(1.0f), ctint, m.sheenTint);
+    p.dielectricWt = (1.0f - m.metallic) * (1.0f - m.specTrans);
+    p.metalWt = m.metallic;
+    p.glassWt = (1.0f - m.metallic) * m.specTrans;
+    float schlickWt = SchlickWeight(Vz);
+    p.diffPr = p.dielectricWt * Luminance(m.baseColor);
+    p.dielectricPr = p.dielectricWt * Luminance(mix(p.Cspec0, f3(1.0f), schlickWt));
+    p.metalPr = p.metalWt * Luminance(mix(m.baseColor, f3(1.0f), schlickWt));
+    p.glassPr = p.glassWt;
+    p.clearCtPr = 0.25f * m.clearcoat;
+    float invTotalWt = 1.0f / (p.diffPr + p.dielectricPr + p.metalPr + p.glassPr + p.clearCtPr);
+    p.diffPr *= invTotalWt; p.dielectricPr *= invTotalWt; p.metalPr *= invTotalWt; p.glassPr *= invTotalWt; p.clearCtPr *= invTotalWt;
+}
+
+__device__ __forceinline__ float3 EvalMicrofacetReflection(const Material& mat, float3 V, float3 L, float3 H, float3 F, float& pdf)   // :89-101
+{
+    pdf = 0.0f;
+    if (L.z <= 0.0f) return f3(0.0f);
+    float D = GTR2Aniso(H.z, H.x, H.y, mat.ax, mat.ay);
+    float G1 = SmithGAniso(fabsf(V.z), V.x, V.y, mat.ax, mat.ay);
+    float G2 = G1 * SmithGAniso(fabsf(L.z), L.x, L.y, mat.ax, mat.ay);
+    pdf = G1 * D / (4.0f * V.z);
+    return F * D * G2 / (4.0f * L.z * V.z);
+}
+
+// DisneyEval (disney.glsl:244-351) in the local frame (T,B,N); V,L already local.
+__device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, float3 V, float3 L, float& pdf)
+{
+    pdf = 0.0f;
+    float3 f = f3(0.0f);
+    float3 H;
+    if (L.z > 0.0f) H = normalize(L + V);
+    else H = normalize(L + V * eta);
+    if (H.z < 0.0f) H = -H;
+    Lobes p;
+    lobeSetup(mat, eta, V.z, p);
+    bool reflect = L.z * V.z > 0;
+    float tmpPdf = 0.0f;
+    float VDotH = fabsf(dot(V, H));
+
+    if (p.diffPr > 0.0f && reflect)   // EvalDisneyDiffuse :61-87
+    {
+        tmpPdf = 0.0f;
+        float3 fd = f3(0.0f);
+        if (L.z > 0.0f)
+        {
+            float LDotH = dot(L, H);
+            float Rr = 2.0f * mat.roughness * LDotH * LDotH;
+            float FL = SchlickWeight(L.z);
+            float FV = SchlickWeight(V.z);
+            float Fretro = Rr * (FL + FV + FL * FV * (Rr - 1.0f));
+            float Fd = (1.0f - 0.5f * FL) * (1.0f - 0.5f * FV);
+            float Fss90 = 0.5f * Rr;
+            float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
+            float ss = 1.25f * (Fss * (1.0f / (L.z + V.z) - 0.5f) + 0.5f);
+            float FH = SchlickWeight(LDotH);
+            float3 Fsheen = FH * mat.sheen * p.Csheen;
+            tmpPdf = L.z * PTB_INV_PI;
+            fd = PTB_INV_PI * mat.baseColor * mixf(Fd + Fretro, ss, mat.subsurface) + Fsheen;
+        }
+        f += fd * p.dielectricWt;
+        pdf += tmpPdf * p.diffPr;
+    }
+    if (p.dielectricPr > 0.0f && reflect)
+    {
+        float F = (DielectricFresnel(VDotH, 1.0f / mat.ior) - p.F0) / (1.0f - p.F0);
+        f += EvalMicrofacetReflection(mat, V, L, H, mix(p.Cspec0, f3(1.0f), F), tmpPdf) * p.dielectricWt;
+        pdf += tmpPdf * p.dielectricPr;
+    }
+    if (p.metalPr > 0.0f && reflect)
+    {
+        float3 F = mix(mat.baseColor, f3(1.0f), SchlickWeight(VDotH));
+        f += EvalMicrofacetReflection(mat, V, L, H, F, tmpPdf) * p.metalWt;
+        pdf += tmpPdf * p.metalPr;
+    }
+    if (p.glassPr > 0.0f)
+    {
+        float F = DielectricFresnel(VDotH, eta);
+        if (reflect)
+        {
+            f += EvalMicrofacetReflection(mat, V, L, H, f3(F), tmpPdf) * p.glassWt;
+            pdf += tmpPdf * p.glassPr * F;
+        }
+        else   // EvalMicrofacetRefraction :103-123
+        {
+            tmpPdf = 0.0f;
+            float3 fr = f3(0.0f);
+            if (!(L.z >= 0.0f))
+            {
+                float LDotH = dot(L, H);
+                float VDotH2 = dot(V, H);
+                float D = GTR2Aniso(H.z, H.x, H.y, mat.ax, mat.ay);
+                float G1 = SmithGAniso(fabsf(V.z), V.x, V.y, mat.ax, mat.ay);
+                float G2 = G1 * SmithGAniso(fabsf(L.z), L.x, L.y, mat.ax, mat.ay);
+                float denom = LDotH + VDotH2 * eta;
+                denom *= denom;
+                float eta2 = eta * eta;
+                float jacobian = fabsf(LDotH) / denom;
+                tmpPdf = G1 * fmaxf(0.0f, VDotH2) * D * jacobian / V.z;
+                fr = vpow(mat.baseColor, 0.5f) * (f3(1.0f) - f3(F)) * D * G2 * fabsf(VDotH2) * jacobian * eta2 / fabsf(L.z * V.z);
+            }
+            f += fr * p.glassWt;
+            pdf += tmpPdf * p.glassPr * (1.0f - F);
+        }
+    }
+    if (p.clearCtPr > 0.0f && reflect)   // EvalClearcoat :125-140
+    {
+        tmpPdf = 0.0f;
+        float3 fc = f3(0.0f);
+        if (L.z > 0.0f)
+        {
+            float VDotH2 = dot(V, H);
+            float F = mixf(0.04f, 1.0f, SchlickWeight(VDotH2));
+            float D = GTR1(H.z, mat.clearcoatRoughness);
+            float G = SmithG(L.z, 0.25f) * SmithG(V.z, 0.25f);
+            float jacobian = 1.0f / (4.0f * VDotH2);
+            tmpPdf = D * H.z * jacobian;
+            fc = f3(F) * D * G;
+        }
+        f += fc * 0.25f * mat.clearcoat;
+        pdf += tmpPdf * p.clearCtPr;
+    }
+    return f * fabsf(L.z);
+}
+
+__device__ __forceinline__ float3 DisneyEval(const Material& mat, float eta, float3 V, float3 N, float3 L, float& pdf)
+{
+    float3 T, B;
+    Onb(N, T, B);
+    return DisneyEvalLocal(mat, eta, ToLocal(T, B, N, V), ToLocal(T, B, N, L), pdf);
+}
+
+// DisneySample (disney.glsl:142-242) with the three draws passed in.
+__device__ __forceinline__ float3 DisneySample(const Material& mat, float eta, float3 V, float3 N, float3& Lw, float& pdf, float r1, float r2, float r3)
+{
+    pdf = 0.0f;
+    float3 T, B;
+    Onb(N, T, B);
+    V = ToLocal(T, B, N, V);
+    Lobes p;
+    lobeSetup(mat, eta, V.z, p);
+    float cdf0 = p.diffPr;
+    float cdf1 = cdf0 + p.dielectricPr;
+    float cdf2 = cdf1 + p.metalPr;
+    float cdf3 = cdf2 + p.glassPr;
+    float3 L;
+    if (r3 < cdf0) L = CosineSampleHemisphere(r1, r2);
+    else if (r3 < cdf2)
+    {
+        float3 H = SampleGGXVNDF(V, mat.ax, mat.ay, r1, r2);
+        if (H.z < 0.0f) H = -H;
+        L = normalize(reflect(-V, H));
+    }
+    else if (r3 < cdf3)
+    {
+        float3 H = SampleGGXVNDF(V, mat.ax, mat.ay, r1, r2);
+        float F = DielectricFresnel(fabsf(dot(V, H)), eta);
+        if (H.z < 0.0f) H = -H;
+        r3 = (r3 - cdf2) / (cdf3 - cdf2);
+        if (r3 < F) L = normalize(reflect(-V, H));
+        else L = normalize(refract(-V, H, eta));
+    }
+    else
+    {
+        float3 H = SampleGTR1(mat.clearcoatRoughness, r1, r2);
+        if (H.z < 0.0f) H = -H;
+        L = normalize(reflect(-V, H));
+    }
+    Lw = ToWorld(T, B, N, L);
+    // the reference converts V back to world and calls DisneyEval (disney.glsl:238-241), which re-derives the same frame
+    float3 Vw = ToWorld(T, B, N, V);
+    return DisneyEvalLocal(mat, eta, ToLocal(T, B, N, Vw), ToLocal(T, B, N, Lw), pdf);
+}
+
+// Material row -> Material (pathtrace.glsl:31-67 + :109-114), textures handled by the caller.
+__device__ __forceinline__ void materialFromRow(const float4* P, Material& mat, int4& texIDs)
+{
+    float4 p1 = __ldg(P), p2 = __ldg(P + 1), p3 = __ldg(P + 2), p4 = __ldg(P + 3), p5 = __ldg(P + 4), p6 = __ldg(P + 5), p7 = __ldg(P + 6), p8 = __ldg(P + 7);
+    mat.baseColor = f3(p1); mat.anisotropic = p1.w;
+    mat.emission = f3(p2);
+    mat.metallic = p3.x; mat.roughness = fmaxf(p3.y, 0.001f); mat.subsurface = p3.z; mat.specularTint = p3.w;
+    mat.sheen = p4.x; mat.sheenTint = p4.y; mat.clearcoat = p4.z; mat.clearcoatRoughness = mixf(0.1f, 0.001f, p4.w);
+    mat.specTrans = p5.x; mat.ior = p5.y; mat.medType = (int)p5.z; mat.medDensity = p5.w;
+    mat.medColor = f3(p6); mat.medAniso = clampf(p6.w, -0.9f, 0.9f);
+    texIDs = make_int4((int)p7.x, (int)p7.y, (int)p7.z, (int)p7.w);
+    mat.opacity = p8.x; mat.alphaMode = (int)p8.y; mat.alphaCutoff = p8.z;
+}
+__device__ __forceinline__ void materialFinish(Material& mat)
+{
+    float aspect = sqrtf(1.0f - mat.anisotropic * 0.9f);
+    mat.ax = fmaxf(0.001f, mat.roughness / aspect);
+    mat.ay = fmaxf(0.001f, mat.roughness * aspect);
+}
+
+// texture(textureMapsArrayTex, vec3(uv, layer)): RGBA8 unorm, LINEAR, REPEAT — manual fp32 bilinear
+__device__ __forceinline__ int wrapi(float f, int n) { int i = (int)fmodf(f, (float)n); if (i < 0) i += n; return i; }
+__device__ __forceinline__ float4 sampleTexArray(const DevScene& S, float2 uv, float layerf)
+{
+    int layer = (int)floorf(layerf + 0.5f); layer = max(0, min(layer, S.numTextures - 1));
+    int W = S.texW, H = S.texH;
+    float x = uv.x * (float)W - 0.5f, y = uv.y * (float)H - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float ax = x - fx0, ay = y - fy0;
+    int x0 = wrapi(fx0, W), x1 = wrapi(fx0 + 1.0f, W), y0 = wrapi(fy0, H), y1 = wrapi(fy0 + 1.0f, H);
+    const uchar4* base = S.textures + (size_t)layer * W * H;
+    uchar4 c00 = __ldg(base + (size_t)y0 * W + x0), c10 = __ldg(base + (size_t)y0 * W + x1), c01 = __ldg(base + (size_t)y1 * W + x0),
+           c11 = __ldg(base + (size_t)y1 * W + x1);
+    float4 o;
+    o.x = mixf(mixf(c00.x / 255.0f, c10.x / 255.0f, ax), mixf(c01.x / 255.0f, c11.x / 255.0f, ax), ay);
+    o.y = mixf(mixf(c00.y / 255.0f, c10.y / 255.0f, ax), mixf(c01.y / 255.0f, c11.y / 255.0f, ax), ay);
+    o.z = mixf(mixf(c00.z / 255.0f, c10.z / 255.0f, ax), mixf(c01.z / 255.0f, c11.z / 255.0f, ax), ay);
+    o.w = mixf(mixf(c00.w / 255.0f, c10.w / 255.0f, ax), mixf(c01.w / 255.0f, c11.w / 255.0f, ax), ay);
+    return o;
+}
+
+// ------------------------------------------------------------------ envmap.glsl ---------------------------------
+__device__ __forceinline__ float3 envTexel(const DevScene& S, int x, int y)
+{
+    const float* p = S.envImg + ((size_t)y * S.envW + x) * 3;
+    return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+__device__ __forceinline__ float3 sampleEnv(const DevScene& S, float2 uv)   // texture(envMapTex, uv): RGB32F LINEAR REPEAT
+{
+    int W = S.envW, H = S.envH;
+    float x = uv.x * (float)W - 0.5f, y = uv.y * (float)H - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float ax = x - fx0, ay = y - fy0;
+    int x0 = wrapi(fx0, W), x1 = wrapi(fx0 + 1.0f, W), y0 = wrapi(fy0, H), y1 = wrapi(fy0 + 1.0f, H);
+    return mix(mix(envTexel(S, x0, y0), envTexel(S, x1, y0), ax), mix(envTexel(S, x0, y1), envTexel(S, x1, y1), ax), ay);
+}
+__device__ __forceinline__ float2 envBinarySearch(const DevScene& S, float value)   // envmap.glsl:28-55
+{
+    int W = S.envW, H = S.envH;
+    int lower = 0, upper = H - 1;
+    while (lower < upper)
+    {
+        int mid = (lower + upper) >> 1;
+        if (value < __ldg(S.envCdf + (size_t)mid * W + (W - 1))) upper = mid;
+        else lower = mid + 1;
+    }
+    int y = max(0, min(lower, H - 1));
+    lower = 0; upper = W - 1;
+    while (lower < upper)
+    {
+        int mid = (lower + upper) >> 1;
+        if (value < __ldg(S.envCdf + (size_t)y * W + mid)) upper = mid;
+        else lower = mid + 1;
+    }
+    int x = max(0, min(lower, W - 1));
+    return make_float2((float)x / (float)W, (float)y / (float)H);
+}
+__device__ __forceinline__ float4 EvalEnvMap(const DevScene& S, const FrameParams& F, float3 dir)   // envmap.glsl:57-66
+{
+    float theta = acosf(clampf(dir.y, -1.0f, 1.0f));
+    float2 uv = make_float2((PTB_PI + atan2f(dir.z, dir.x)) * PTB_INV_TWO_PI + F.envMapRot, theta * PTB_INV_PI);
+    float3 color = sampleEnv(S, uv);
+    float pdf = Luminance(color) / S.envTotalSum;
+    return make_float4(color.x, color.y, color.z, (pdf * (float)S.envW * (float)S.envH) / (PTB_TWO_PI * PTB_PI * sinf(theta)));
+}
+__device__ __forceinline__ float4 SampleEnvMap(const DevScene& S, const FrameParams& F, Rng& rng, float3& color)   // envmap.glsl:68-83
+{
+    float2 uv = envBinarySearch(S, rng.rand() * S.envTotalSum);
+    color = sampleEnv(S, uv);
+    float pdf = Luminance(color) / S.envTotalSum;
+    uv.x -= F.envMapRot;
+    float phi = uv.x * PTB_TWO_PI;
+    float theta = uv.y * PTB_PI;
+    float st, ct, sp, cp; sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+    if (st == 0.0f) pdf = 0.0f;
+    return make_float4(-st * cp, ct, -st * sp, (pdf * (float)S.envW * (float)S.envH) / (PTB_TWO_PI * PTB_PI * st));
+}
+
+} // namespace ptb

@@ -1,0 +1,126 @@
+// ptb_internal.h — POD structures shared by the host side (ptb_api.cpp, g++) and the kernels (ptb_kernels.cu, nvcc).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+#include <vector_types.h>
+#include <vector_functions.h>
+#endif
+
+// ---- child / node "meta" word of the derived traversal layout -------------------------------------------------
+// bits 31..30 kind; INNER: canonical node index (30 bits); LEAF: count (4 bits, 29..26) | first leaf-ref slot (26 bits);
+// INST: instance index (30 bits); NONE: stack sentinel / BLAS marker (the reference's -1, closest_hit.glsl:91,166).
+enum : uint32_t { PTB_K_INNER = 0u, PTB_K_LEAF = 1u, PTB_K_INST = 2u, PTB_K_NONE = 3u };
+#define PTB_META_NONE 0xFFFFFFFFu
+#define PTB_MAX_LEAF_TRIS 15
+#define PTB_MAX_LEAF_SLOT ((1u << 26) - 1)
+
+// Device-resident scene.  Canonical arrays are byte-identical copies of what Renderer::InitGPUDataBuffers uploads
+// (reference Renderer.cpp:135-249); "derived" arrays are re-packings with identical content/indices for 128-bit fetches.
+struct DevScene
+{
+    // canonical (layout unchanged)
+    const float*  nodes;        // 9 floats / node
+    const int*    vertIndices;  // 3 ints / leaf-ref slot
+    const float4* verticesUVX;
+    const float4* normalsUVY;
+    const float4* materials;    // 8 float4 / material
+    const float4* transforms;   // 4 float4 / instance
+    const float*  lights;       // 15 floats / light
+    const uchar4* textures;     // RGBA8 [layer][y][x]
+    const float*  envImg;       // RGB32F
+    const float*  envCdf;       // R32F
+    // derived
+    const float4* inner;        // 4 float4 / canonical node index: child boxes + child metas (valid for internal nodes)
+    const float4* tris;         // 3 float4 / leaf-ref slot: v0, e0, e1, vertIndices.x
+    const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {rootMeta, matID, 0, 0} in .w
+    const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
+    const float4* lightsPre;    // 8 float4 / light (see LightPre in ptb_api.cpp)
+    uint32_t rootMeta;          // meta of the TLAS root
+    int numNodes, topLevelIndex, numIndices, numVertices, numMaterials, numInstances, numLights;
+    int numTextures, texW, texH, envW, envH;
+    float envTotalSum;
+    int stackDepth;             // traversal stack entries needed (bottom sentinel + TLAS path + marker + BLAS path)
+};
+
+struct FrameParams
+{
+    // options
+    uint32_t features;
+    int maxDepth, rrDepth;
+    float envMapIntensity, envMapRot /* already /360 */, roughnessMollificationAmt;
+    float uniformLightCol[3];
+    int renderW, renderH, tileW, tileH, numTilesX, numTilesY;
+    float invNumTilesX, invNumTilesY;
+    // camera
+    float camPos[3], camRight[3], camUp[3], camFwd[3];
+    float camScale /* tan(fov/2), computed on the host */, camFocalDist, camAperture;
+    // derived switches
+    int cullBoxes;       // cull child boxes whose entry distance exceeds the current hit distance
+    int inlineShadow;    // shadow rays consume path RNG draws (BLEND alpha in AnyHit / EvalTransmittance) -> traced inside shade
+    int general;         // 0: lights-only fast specialisation is valid
+};
+
+// One wavefront: S sample passes of a pixel rectangle.
+struct WaveParams
+{
+    int x0, y0, rw, rh;        // pixel rectangle
+    int vw, vh;                // rectangle padded to 8x4 pixel blocks
+    int nSamples;              // sample passes in this wave
+    int firstSample, sampleStride;
+    int fixedFrame;            // >= 0: use this frameNum for every pixel (ptb_render_tile); < 0: reference schedule
+    int previewMode;           // preview.glsl: InitRNG(gl_FragCoord, 1), TexCoords over the whole image, depth 2
+    uint32_t nSlots;           // vw*vh*nSamples
+};
+
+// Path state, SoA of 16-byte vectors indexed by path slot.
+struct PathState
+{
+    float4* rayO;     // origin.xyz, prev scatter pdf
+    float4* rayD;     // direction.xyz, bits: depth (low 16, signed) | flags (high 16)
+    float4* thr;      // throughput.xyz, previous roughness (mollification)
+    float4* rad;      // radiance.xyz, alpha
+    uint4*  rng;      // pcg4d state
+    float4* hit;      // t, bary u, bary v, bits(primSlot)
+    int*    hitInst;  // >=0 instance (triangle hit); -1 miss; <= -2: light -(idx+2)
+    float4* med;      // general: medium density, anisotropy, bits(type), bits(prevMatID)
+    float4* medCol;   // general: medium color.xyz, -
+    float2* prevUV;   // general: stale texCoord (Q2)
+    // shadow queues A (env NEE) and B (light NEE), dense by queue slot
+    float4* shO[2];   // origin.xyz, maxDist
+    float4* shD[2];   // direction.xyz, bits(path slot)
+    float4* shC[2];   // contribution.rgb (already multiplied by throughput)
+    uint32_t* queue[2];
+};
+
+#define PTB_FLAG_INMEDIUM   (1u << 16)
+#define PTB_FLAG_SURFSCAT   (1u << 17)
+
+#define PTB_MAX_ITERS 256
+#define PTB_CTR_STRIDE 8
+// counter slots per iteration
+enum { CTR_NPATHS = 0, CTR_NSHA = 1, CTR_NSHB = 2, CTR_FETCH_TRACE = 3, CTR_FETCH_SHADE = 4, CTR_FETCH_SHA = 5, CTR_FETCH_SHB = 6 };
+
+struct DevStats { unsigned long long pathSegments, shadowRays; };
+
+// ---- launchers implemented in ptb_kernels.cu ------------------------------------------------------------------
+struct LaunchCfg { int numSMs; void* stream; };
+
+void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
+void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats);
+void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats);
+void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
+                 uint32_t* fetchCtr, DevStats* stats);
+void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);
+void ptbk_tonemap(const LaunchCfg&, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
+                  int simpleAcesFit, const float* backgroundCol3, uint32_t features, uchar4* out);
+void ptbk_trace_closest_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, long long n, int depth, void* hitsOut);
+void ptbk_trace_any_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, const float* maxDist, long long n, int* out);
+void ptbk_bsdf_batch(const LaunchCfg&, const void* queries, long long n, void* results, int sample);
+void ptbk_camera_rays(const LaunchCfg&, const FrameParams&, const WaveParams&, float* outRays);
+int  ptbk_kernel_launch_count();   // kernels launched so far by this process through the launchers above

@@ -1,0 +1,958 @@
+// ptb_kernels.cu — sm_100a kernels of the wavefront path tracer and their launchers.
+//
+// Pipeline per wave (S sample passes of a pixel rectangle, all paths resident in HBM as SoA float4 state):
+//   k_camera      tile.glsl:41-68      camera rays + RNG seeding, initial queue
+//   loop over bounces:
+//     k_trace     closest_hit.glsl     persistent warps, dynamic 32-ray fetch, shared-memory stacks, 64-byte node fetches
+//     k_shade     pathtrace.glsl       hit attributes, GetMaterial, emission/MIS, media, alpha, NEE sample + DisneyEval,
+//                                      DisneySample, Russian roulette; warp-ballot compaction into next/shadow queues
+//     k_shadow    anyhit.glsl          any-hit for the queued NEE rays, adds the unoccluded contributions
+//   k_accumulate  tile.glsl:70-74      sum of the wave's samples into the running-sum buffer
+//   k_tonemap     tonemap.glsl         on readback
+#include "ptb_device.cuh"
+#include <cstdio>
+
+using namespace ptb;
+
+static int g_launches = 0;
+int ptbk_kernel_launch_count() { return g_launches; }
+
+#define OPT(F, bit) (((F).features & (bit)) != 0u)
+enum {
+    O_ENVMAP = 1 << 0, O_LIGHTS = 1 << 1, O_RR = 1 << 2, O_UNIFORM = 1 << 3, O_GLNORMAL = 1 << 4, O_HIDE = 1 << 5, O_BG = 1 << 6,
+    O_TRANSPBG = 1 << 7, O_ALPHA = 1 << 8, O_MOLLIFY = 1 << 9, O_MEDIUM = 1 << 10, O_VOLMIS = 1 << 11
+};
+
+constexpr int TRACE_THREADS = 256;
+constexpr int SHADE_THREADS = 128;
+
+// ------------------------------------------------------------------ slot <-> pixel mapping ----------------------
+// Path slots of one sample pass are ordered in 8x4 pixel blocks so that a warp's primary rays are spatially coherent.
+__device__ __forceinline__ bool slotToPixel(const WaveParams& W, uint32_t slot, int& s, int& px, int& py)
+{
+    const uint32_t perSample = (uint32_t)W.vw * (uint32_t)W.vh;
+    s = (int)(slot / perSample);
+    uint32_t idx = slot - (uint32_t)s * perSample;
+    uint32_t b = idx >> 5, l = idx & 31u;
+    uint32_t blocksX = (uint32_t)W.vw >> 3;
+    px = (int)((b % blocksX) * 8u + (l & 7u));
+    py = (int)((b / blocksX) * 4u + (l >> 3));
+    return px < W.rw && py < W.rh;
+}
+
+// tile.glsl:41-68 / preview.glsl:41-67.  (x,y) absolute pixel; returns the ray and leaves rng advanced by 4 draws.
+__device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass, Rng& rng, float3& ro, float3& rd)
+{
+    float cx, cy;
+    if (W.previewMode)
+    {
+        cx = ((float)x + 0.5f) / (float)W.rw; cy = ((float)y + 0.5f) / (float)W.rh;     // TexCoords over the whole low-res target
+        rng.init((uint32_t)x, (uint32_t)y, 1u);                                         // preview.glsl:43
+    }
+    else
+    {
+        int tx = x / F.tileW, ty = y / F.tileH, lx = x - tx * F.tileW, ly = y - ty * F.tileH;
+        float tcx = ((float)lx + 0.5f) / (float)F.tileW, tcy = ((float)ly + 0.5f) / (float)F.tileH;
+        float offx = (float)tx * F.invNumTilesX, offy = (float)ty * F.invNumTilesY;        // Renderer.cpp:780
+        // mix(tileOffset, tileOffset + invNumTiles, TexCoords)  (tile.glsl:43)
+        cx = __fadd_rn(__fmul_rn(offx, __fsub_rn(1.0f, tcx)), __fmul_rn(__fadd_rn(offx, F.invNumTilesX), tcx));
+        cy = __fadd_rn(__fmul_rn(offy, __fsub_rn(1.0f, tcy)), __fmul_rn(__fadd_rn(offy, F.invNumTilesY), tcy));
+        int frame;
+        if (W.fixedFrame >= 0) frame = W.fixedFrame;
+        else
+        {   // frameNum of pass s, tile j: first Update is the dirty one, tiles run x-fastest from the top row (Renderer.cpp:745-762)
+            int T = F.numTilesX * F.numTilesY;
+            int j = (F.numTilesY - 1 - ty) * F.numTilesX + tx;
+            frame = 2 + (samplePass - 1) * T + j;
+        }
+        rng.init((uint32_t)lx, (uint32_t)ly, (uint32_t)frame);                            // gl_FragCoord is tile-local (tile.glsl:45)
+    }
+    float r1 = __fmul_rn(2.0f, rng.rand());
+    float r2 = __fmul_rn(2.0f, rng.rand());
+    float jx = r1 < 1.0f ? __fsub_rn(__fsqrt_rn(r1), 1.0f) : __fsub_rn(1.0f, __fsqrt_rn(__fsub_rn(2.0f, r1)));
+    float jy = r2 < 1.0f ? __fsub_rn(__fsqrt_rn(r2), 1.0f) : __fsub_rn(1.0f, __fsqrt_rn(__fsub_rn(2.0f, r2)));
+    jx = __fdiv_rn(jx, __fmul_rn((float)F.renderW, 0.5f));
+    jy = __fdiv_rn(jy, __fmul_rn((float)F.renderH, 0.5f));
+    float dx = __fadd_rn(__fsub_rn(__fmul_rn(cx, 2.0f), 1.0f), jx);
+    float dy = __fadd_rn(__fsub_rn(__fmul_rn(cy, 2.0f), 1.0f), jy);
+    float scale = F.camScale;
+    dy = __fmul_rn(dy, __fmul_rn(__fdiv_rn((float)F.renderH, (float)F.renderW), scale));
+    dx = __fmul_rn(dx, scale);
+    float3 right = f3(F.camRight[0], F.camRight[1], F.camRight[2]), up = f3(F.camUp[0], F.camUp[1], F.camUp[2]),
+           fwd = f3(F.camFwd[0], F.camFwd[1], F.camFwd[2]), pos = f3(F.camPos[0], F.camPos[1], F.camPos[2]);
+    // exact-op evaluation keeps pinhole primary rays bit-identical to the oracle's (aperture 0 => no sin/cos influence)
+    float3 v = f3(xa(xa(xm(dx, right.x), xm(dy, up.x)), fwd.x), xa(xa(xm(dx, right.y), xm(dy, up.y)), fwd.y), xa(xa(xm(dx, right.z), xm(dy, up.z)), fwd.z));
+    float vl = __fsqrt_rn(xdot(v, v));
+    float3 rayDir = f3(xd(v.x, vl), xd(v.y, vl), xd(v.z, vl));
+    float3 focalPoint = f3(xm(F.camFocalDist, rayDir.x), xm(F.camFocalDist, rayDir.y), xm(F.camFocalDist, rayDir.z));
+    float cam_r1 = __fmul_rn(rng.rand(), PTB_TWO_PI);
+    float cam_r2 = __fmul_rn(rng.rand(), F.camAperture);
+    float sr = __fsqrt_rn(cam_r2);
+    float s1, c1; sincosf(cam_r1, &s1, &c1);
+    float3 ap = f3(xm(xa(xm(c1, right.x), xm(s1, up.x)), sr), xm(xa(xm(c1, right.y), xm(s1, up.y)), sr), xm(xa(xm(c1, right.z), xm(s1, up.z)), sr));
+    float3 fd = xsub(focalPoint, ap);
+    float fl = __fsqrt_rn(xdot(fd, fd));
+    rd = f3(xd(fd.x, fl), xd(fd.y, fl), xd(fd.z, fl));
+    ro = f3(xa(pos.x, ap.x), xa(pos.y, ap.y), xa(pos.z, ap.z));
+}
+
+__global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < W.nSlots; base += gridDim.x * blockDim.x)
+    {
+        uint32_t slot = base + lane;
+        bool live = false;
+        if (slot < W.nSlots)
+        {
+            int s, px, py;
+            live = slotToPixel(W, slot, s, px, py);
+            if (live)
+            {
+                Rng rng; float3 ro, rd;
+                cameraRay(F, W, W.x0 + px, W.y0 + py, W.firstSample + s * W.sampleStride, rng, ro, rd);
+                P.rayO[slot] = make_float4(ro.x, ro.y, ro.z, 0.0f);
+                P.rayD[slot] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(0u));
+                P.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                P.rad[slot] = make_float4(0.f, 0.f, 0.f, 1.f);
+                P.rng[slot] = rng.s;
+                if (F.general)
+                {
+                    P.med[slot] = make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(0));
+                    P.medCol[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    P.prevUV[slot] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m)
+        {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(&ctr0[CTR_NPATHS], (uint32_t)__popc(m));
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (live) P.queue[0][b + __popc(m & ((1u << lane) - 1u))] = slot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ closest-hit trace ---------------------------
+extern __shared__ uint32_t g_stackSmem[];
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
+                                                          const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats)
+{
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    const bool lights = OPT(F, O_LIGHTS);
+    const bool cull = F.cullBoxes != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->pathSegments, (unsigned long long)n);
+    while (true)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetchCtr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n)
+        {
+            const uint32_t p = queue[i];
+            const float4 o4 = P.rayO[p], d4 = P.rayD[p];
+            const float3 o = f3(o4), d = f3(d4);
+            HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
+            float t = PTB_INF;
+            if (lights)
+            {
+                int depth = (int)(short)(__float_as_uint(d4.w) & 0xffffu);
+                if (depth >= lightsFromDepth) closestLights(S, o, d, t, h.light);     // OPT_HIDE_EMITTERS: lights only at depth > 0
+            }
+            traverse<false, false>(S, o, d, t, cull, stk, h, NoAlpha());
+            P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
+            P.hitInst[p] = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ surface state -------------------------------
+struct Surf
+{
+    float3 fhp, normal, ffnormal, tangent, bitangent; float2 uv; int matID; float hitDist;
+};
+
+// closest_hit.glsl:220-263 for a triangle hit (slot = leaf-ref slot, inst = instance)
+__device__ __forceinline__ void triangleSurface(const DevScene& S, int slot, int inst, float bu, float bv, float3 ro, float3 rd, float t, bool needUV, bool needTangents, Surf& sf)
+{
+    const int i0 = __ldg(S.vertIndices + (size_t)slot * 3), i1 = __ldg(S.vertIndices + (size_t)slot * 3 + 1), i2 = __ldg(S.vertIndices + (size_t)slot * 3 + 2);
+    const float bw = 1.0f - bu - bv;       // uvt.w; bary = uvt.wxy
+    const float4 n0 = __ldg(S.normalsUVY + i0), n1 = __ldg(S.normalsUVY + i1), n2 = __ldg(S.normalsUVY + i2);
+    float3 normal = normalize(f3(n0) * bw + f3(n1) * bu + f3(n2) * bv);
+    const float4* is = S.instShade + (size_t)inst * 8;
+    const float4 m0 = __ldg(is + 4), m1 = __ldg(is + 5), m2 = __ldg(is + 6);       // inverse(mat3(transform)) rows
+    float3 nw = f3(m0.x * normal.x + m0.y * normal.y + m0.z * normal.z, m1.x * normal.x + m1.y * normal.y + m1.z * normal.z,
+                   m2.x * normal.x + m2.y * normal.y + m2.z * normal.z);
+    sf.normal = normalize(nw);
+    sf.ffnormal = dot(sf.normal, rd) <= 0.0f ? sf.normal : -sf.normal;
+    sf.hitDist = t;
+    sf.fhp = ro + rd * t;
+    sf.matID = __float_as_int(__ldg(S.instTrav + (size_t)inst * 4 + 1).w);
+    sf.uv = make_float2(0.f, 0.f);
+    sf.tangent = sf.bitangent = f3(0.f);
+    if (needUV)
+    {
+        const float4 v0 = __ldg(S.verticesUVX + i0), v1 = __ldg(S.verticesUVX + i1), v2 = __ldg(S.verticesUVX + i2);
+        float2 t0 = make_float2(v0.w, n0.w), t1 = make_float2(v1.w, n1.w), t2 = make_float2(v2.w, n2.w);
+        sf.uv = make_float2(t0.x * bw + t1.x * bu + t2.x * bv, t0.y * bw + t1.y * bu + t2.y * bv);
+        if (needTangents)
+        {
+            float3 dp1 = f3(v1) - f3(v0), dp2 = f3(v2) - f3(v0);
+            float2 duv1 = make_float2(t1.x - t0.x, t1.y - t0.y), duv2 = make_float2(t2.x - t0.x, t2.y - t0.y);
+            float invdet = 1.0f / (duv1.x * duv2.y - duv1.y * duv2.x);
+            float3 tg = (dp1 * duv2.y - dp2 * duv1.y) * invdet;
+            float3 bt = (dp2 * duv1.x - dp1 * duv2.x) * invdet;
+            const float4 d0 = __ldg(is), d1 = __ldg(is + 1), d2 = __ldg(is + 2);    // transform rows: mat3(transform) * v
+            sf.tangent = normalize(f3(tg.x * d0.x + tg.y * d1.x + tg.z * d2.x, tg.x * d0.y + tg.y * d1.y + tg.z * d2.y, tg.x * d0.z + tg.y * d1.z + tg.z * d2.z));
+            sf.bitangent = normalize(f3(bt.x * d0.x + bt.y * d1.x + bt.z * d2.x, bt.x * d0.y + bt.y * d1.y + bt.z * d2.y, bt.x * d0.z + bt.y * d1.z + bt.z * d2.z));
+        }
+    }
+}
+
+// GetMaterial (pathtrace.glsl:25-115).  prevRoughness = state.mat.roughness of the previous call (mollification).
+template <bool GEN>
+__device__ __forceinline__ void getMaterial(const DevScene& S, const FrameParams& F, Surf& sf, float3 rd, int depth, float prevRoughness, Material& mat, float& eta)
+{
+    int4 tex;
+    materialFromRow(S.materials + (size_t)sf.matID * 8, mat, tex);
+    if (GEN)
+    {
+        if (tex.x >= 0)
+        {
+            float4 col = sampleTexArray(S, sf.uv, (float)tex.x);
+            mat.baseColor *= vpow(f3(col), 2.2f);
+            mat.opacity *= col.w;
+        }
+        if (tex.y >= 0)
+        {
+            float4 mr = sampleTexArray(S, sf.uv, (float)tex.y);
+            mat.metallic = mr.z;
+            mat.roughness = fmaxf(mr.y * mr.y, 0.001f);
+        }
+        if (tex.z >= 0)
+        {
+            float4 tn = sampleTexArray(S, sf.uv, (float)tex.z);
+            float3 texNormal = f3(tn);
+            if (OPT(F, O_GLNORMAL)) texNormal.y = 1.0f - texNormal.y;
+            texNormal = normalize(texNormal * 2.0f - f3(1.0f));
+            float3 origNormal = sf.normal;
+            sf.normal = normalize(sf.tangent * texNormal.x + sf.bitangent * texNormal.y + sf.normal * texNormal.z);
+            sf.ffnormal = dot(origNormal, rd) <= 0.0f ? sf.normal : -sf.normal;
+        }
+        if (OPT(F, O_MOLLIFY) && depth > 0)
+            mat.roughness = fmaxf(mixf(0.0f, prevRoughness, F.roughnessMollificationAmt), mat.roughness);
+        if (tex.w >= 0)
+            mat.emission = vpow(f3(sampleTexArray(S, sf.uv, (float)tex.w)), 2.2f);
+    }
+    materialFinish(mat);
+    eta = dot(rd, sf.normal) < 0.0f ? (1.0f / mat.ior) : mat.ior;
+}
+
+__device__ __forceinline__ bool materialNeedsTangents(const DevScene& S, int matID) { return __ldg(S.materials + (size_t)matID * 8 + 6).z >= 0.f; }
+
+// lightSample.pdf / emission of a light hit (closest_hit.glsl:56-62, 72-83)
+__device__ __forceinline__ void lightHitInfo(const DevScene& S, int idx, float3 ro, float3 rd, float t, float& pdf, float3& emission)
+{
+    const float4* p = S.lightsPre + (size_t)idx * 8;
+    float4 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 4);
+    emission = f3(b);
+    float area = b.w;
+    if (a.w == 0.0f)
+    {
+        float cosTheta = dot(-rd, f3(e));
+        pdf = (t * t) / (area * cosTheta);
+    }
+    else
+    {
+        float3 hitPt = ro + t * rd;
+        float cosTheta = dot(-rd, normalize(hitPt - f3(a)));
+        pdf = (t * t) / (area * cosTheta * 0.5f);
+    }
+}
+
+// ------------------------------------------------------------------ inline traversal (RNG-consuming shadow rays) -
+struct InlineCounters { unsigned segs, shadows; };
+
+// ClosestHit + hit attributes for EvalTransmittance steps (pathtrace.glsl:128).  Returns hit kind: 0 miss, 1 tri, 2 light.
+__device__ __noinline__ int closestFull(const DevScene& S, const FrameParams& F, float3 ro, float3 rd, int depthForLights, Surf& sf, InlineCounters& ic)
+{
+    LocalStack stk;
+    HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
+    float t = PTB_INF;
+    ic.segs++;
+    if (OPT(F, O_LIGHTS) && (!OPT(F, O_HIDE) || depthForLights > 0)) closestLights(S, ro, rd, t, h.light);
+    traverse<false, false>(S, ro, rd, t, F.cullBoxes != 0, stk, h, NoAlpha());
+    if (h.t == PTB_INF) return 0;
+    if (h.inst < 0) { sf.hitDist = h.t; sf.fhp = ro + rd * h.t; return 2; }
+    int matID = __float_as_int(__ldg(S.instTrav + (size_t)h.inst * 4 + 1).w);
+    triangleSurface(S, h.prim, h.inst, h.bu, h.bv, ro, rd, h.t, true, materialNeedsTangents(S, matID), sf);
+    return 1;
+}
+
+struct AlphaRng   // AnyHit's alpha test (anyhit.glsl:118-141) with the path RNG
+{
+    const DevScene* S; Rng* rng;
+    __device__ __forceinline__ bool operator()(int slot, int inst, float ux, float uy) const
+    {
+        const DevScene& sc = *S;
+        int matID = __float_as_int(__ldg(sc.instTrav + (size_t)inst * 4 + 1).w);
+        const float4 texIDs = __ldg(sc.materials + (size_t)matID * 8 + 6), ap = __ldg(sc.materials + (size_t)matID * 8 + 7);
+        float alpha = 1.0f;
+        if (sc.numTextures > 0)
+        {
+            const int i0 = __ldg(sc.vertIndices + (size_t)slot * 3), i1 = __ldg(sc.vertIndices + (size_t)slot * 3 + 1), i2 = __ldg(sc.vertIndices + (size_t)slot * 3 + 2);
+            float uw = 1.0f - ux - uy;
+            float2 t0 = make_float2(__ldg(sc.verticesUVX + i0).w, __ldg(sc.normalsUVY + i0).w), t1 = make_float2(__ldg(sc.verticesUVX + i1).w, __ldg(sc.normalsUVY + i1).w),
+                   t2 = make_float2(__ldg(sc.verticesUVX + i2).w, __ldg(sc.normalsUVY + i2).w);
+            float2 uv = make_float2(t0.x * uw + t1.x * ux + t2.x * uy, t0.y * uw + t1.y * ux + t2.y * uy);
+            alpha = sampleTexArray(sc, uv, texIDs.x).w;
+        }
+        float opacity = ap.x * alpha;
+        int alphaMode = (int)ap.y;
+        float alphaCutoff = ap.z;
+        return !((alphaMode == 2 && opacity < alphaCutoff) || (alphaMode == 1 && rng->rand() > opacity));
+    }
+};
+
+__device__ __noinline__ bool anyHitInline(const DevScene& S, const FrameParams& F, float3 ro, float3 rd, float maxDist, Rng& rng, InlineCounters& ic)
+{
+    ic.shadows++;
+    if (OPT(F, O_LIGHTS) && anyLights(S, ro, rd, maxDist)) return true;
+    LocalStack stk; HitRec h;
+    if (OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM))
+        return traverse<true, true>(S, ro, rd, maxDist, F.cullBoxes != 0, stk, h, AlphaRng{&S, &rng});
+    return traverse<true, false>(S, ro, rd, maxDist, F.cullBoxes != 0, stk, h, NoAlpha());
+}
+
+// EvalTransmittance (pathtrace.glsl:119-155)
+__device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameParams& F, float3 ro, float3 rd, Rng& rng, InlineCounters& ic)
+{
+    float3 transmittance = f3(1.0f);
+    for (int depth = 0; depth < F.maxDepth; depth++)
+    {
+        Surf sf;
+        int kind = closestFull(S, F, ro, rd, 0, sf, ic);
+        if (kind != 1) break;                       // miss or emitter
+        Material mat; float eta;
+        getMaterial<true>(S, F, sf, rd, 0, 0.f, mat, eta);
+        bool alphatest = (mat.alphaMode == 2 && mat.opacity < mat.alphaCutoff) || (mat.alphaMode == 1 && rng.rand() > mat.opacity);
+        bool refractive = (1.0f - mat.metallic) * mat.specTrans > 0.0f;
+        if (!(alphatest || refractive)) return f3(0.0f);
+        if (dot(rd, sf.normal) > 0 && mat.medType != 0)
+        {
+            float3 color = mat.medType == 1 ? f3(1.0f) - mat.medColor : f3(1.0f);
+            transmittance *= vexp(-color * mat.medDensity * sf.hitDist);
+        }
+        ro = sf.fhp + rd * PTB_EPS;
+    }
+    return transmittance;
+}
+
+// ------------------------------------------------------------------ shade ----------------------------------------
+struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
+
+// DirectLight (pathtrace.glsl:158-283).  Deferred mode: fills sa (env) / sb (light) with contribution*throughput.
+// Inline mode (shadow rays draw from the path RNG): traces here and returns Ld.
+template <bool GEN>
+__device__ __forceinline__ float3 directLight(const DevScene& S, const FrameParams& F, float3 rd, const Surf& sf, const Material& mat, float eta, bool isSurface,
+                                              float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+{
+    float3 Ld = f3(0.0f);
+    const float3 scatterPos = sf.fhp + sf.normal * PTB_EPS;
+    const bool volMis = GEN && OPT(F, O_MEDIUM) && OPT(F, O_VOLMIS);
+    const bool inl = GEN && F.inlineShadow;
+
+    if (GEN && OPT(F, O_ENVMAP) && !OPT(F, O_UNIFORM))
+    {
+        float3 Li;
+        float4 dirPdf = SampleEnvMap(S, F, rng, Li);
+        float3 lightDir = f3(dirPdf);
+        float lightPdf = dirPdf.w;
+        if (volMis) Li *= evalTransmittance(S, F, scatterPos, lightDir, rng, ic);
+        bool visible = true;
+        if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, lightDir, PTB_INF - PTB_EPS, rng, ic);
+        if (visible)
+        {
+            float3 f; float pdf;
+            if (isSurface) f = DisneyEval(mat, eta, -rd, sf.ffnormal, lightDir, pdf);
+            else { float ph = PhaseHG(dot(-rd, lightDir), medAniso); f = f3(ph); pdf = ph; }
+            if (pdf > 0.0f)
+            {
+                float misWeight = PowerHeuristic(lightPdf, pdf);
+                if (misWeight > 0.0f)
+                {
+                    float3 c = misWeight * Li * f * F.envMapIntensity / lightPdf;
+                    if (volMis || inl) Ld += c;
+                    else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; }
+                }
+            }
+        }
+    }
+
+    if (OPT(F, O_LIGHTS))
+    {
+        int idx = (int)(rng.rand() * (float)S.numLights);      // pathtrace.glsl:223
+        if (idx >= S.numLights) idx = S.numLights - 1;          // Q6: rand()==1 would index past the end; clamp
+        LightSample ls; float area;
+        SampleOneLight(S, idx, scatterPos, rng, ls, area);
+        float3 Li = ls.emission;
+        if (dot(ls.direction, ls.normal) < 0.0f)
+        {
+            if (volMis) Li *= evalTransmittance(S, F, scatterPos, ls.direction, rng, ic);
+            bool visible = true;
+            if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, ls.direction, ls.dist - PTB_EPS, rng, ic);
+            if (visible)
+            {
+                float3 f; float pdf;
+                if (isSurface) f = DisneyEval(mat, eta, -rd, sf.ffnormal, ls.direction, pdf);
+                else { float ph = PhaseHG(dot(-rd, ls.direction), medAniso); f = f3(ph); pdf = ph; }
+                float misWeight = 1.0f;
+                if (area > 0.0f) misWeight = PowerHeuristic(ls.pdf, pdf);
+                if (pdf > 0.0f)
+                {
+                    float3 c = misWeight * Li * f / ls.pdf;
+                    if (volMis || inl) Ld += c;
+                    else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
+                }
+            }
+        }
+    }
+    return Ld;
+}
+
+// One iteration of the PathTrace loop body after ClosestHit (pathtrace.glsl:303-471) for path slot p.
+template <bool GEN>
+__device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+{
+    const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], thr4 = P.thr[p], rad4 = P.rad[p], hit4 = P.hit[p];
+    const int hitInst = P.hitInst[p];
+    Rng rng; rng.s = P.rng[p];
+    const uint32_t fl = __float_as_uint(rd4.w);
+    int depth = (int)(short)(fl & 0xffffu);
+    bool inMedium = (fl & PTB_FLAG_INMEDIUM) != 0u, surfaceScatter = (fl & PTB_FLAG_SURFSCAT) != 0u;
+    float3 ro = f3(ro4), rd = f3(rd4), thr = f3(thr4), rad = f3(rad4);
+    float alpha = rad4.w, prevPdf = ro4.w, prevRough = thr4.w;
+    cont = false;
+
+    if (hitInst == -1)      // miss: pathtrace.glsl:305-339
+    {
+        if (OPT(F, O_BG) || OPT(F, O_TRANSPBG)) { if (depth == 0) alpha = 0.0f; }
+        if (!OPT(F, O_HIDE) || depth > 0)
+        {
+            if (OPT(F, O_UNIFORM)) rad += f3(F.uniformLightCol[0], F.uniformLightCol[1], F.uniformLightCol[2]) * thr;
+            else if (GEN && OPT(F, O_ENVMAP))
+            {
+                float4 e = EvalEnvMap(S, F, rd);
+                float misWeight = 1.0f;
+                if (depth > 0) misWeight = PowerHeuristic(prevPdf, e.w);
+                if (OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
+                if (misWeight > 0) rad += misWeight * f3(e) * thr * F.envMapIntensity;
+            }
+        }
+        P.rad[p] = make_float4(rad.x, rad.y, rad.z, alpha);
+        return;
+    }
+
+    const float t = hit4.x;
+    Surf sf;
+    Material mat; float eta = 1.0f;
+    float4 med = make_float4(0.f, 0.f, 0.f, 0.f), medCol = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GEN) { med = P.med[p]; medCol = P.medCol[p]; }
+
+    if (hitInst <= -2)      // analytic light hit: pathtrace.glsl:341-364 with the stale matID/texCoord of SURVEY Q2
+    {
+        const int li = -(hitInst + 2);
+        if (GEN)
+        {
+            int prevMat = __float_as_int(med.w);
+            float3 em = f3(__ldg(S.materials + (size_t)prevMat * 8 + 1));
+            float etex = __ldg(S.materials + (size_t)prevMat * 8 + 6).w;
+            if (etex >= 0.f) em = vpow(f3(sampleTexArray(S, P.prevUV[p], (float)(int)etex)), 2.2f);
+            rad += em * thr;
+        }
+        float lpdf; float3 lem;
+        lightHitInfo(S, li, ro, rd, t, lpdf, lem);
+        float misWeight = 1.0f;
+        if (depth > 0) misWeight = PowerHeuristic(prevPdf, lpdf);
+        if (GEN && OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
+        rad += misWeight * lem * thr;
+        P.rad[p] = make_float4(rad.x, rad.y, rad.z, alpha);
+        return;
+    }
+
+    {
+        const int slot = __float_as_int(hit4.w);
+        int matID = __float_as_int(__ldg(S.instTrav + (size_t)hitInst * 4 + 1).w);
+        triangleSurface(S, slot, hitInst, hit4.y, hit4.z, ro, rd, t, GEN, GEN && materialNeedsTangents(S, matID), sf);
+        getMaterial<GEN>(S, F, sf, rd, depth, prevRough, mat, eta);
+    }
+    if (GEN) rad += mat.emission * thr;                      // pathtrace.glsl:344
+
+    bool terminated = (depth == F.maxDepth);                 // :367
+    bool mediumSampled = false;
+
+    if (!terminated)
+    {
+        if (GEN && OPT(F, O_MEDIUM))                          // :370-410
+        {
+            surfaceScatter = false;
+            if (inMedium)
+            {
+                const int mtype = __float_as_int(med.z);
+                const float density = med.x, aniso = med.y;
+                const float3 mcol = f3(medCol);
+                if (mtype == 1) thr *= vexp(-(f3(1.0f) - mcol) * sf.hitDist * density);
+                else if (mtype == 3) rad += mcol * sf.hitDist * density * thr;
+                else
+                {
+                    float scatterDist = fminf(-logf(rng.rand()) / density, sf.hitDist);
+                    mediumSampled = scatterDist < sf.hitDist;
+                    if (mediumSampled)
+                    {
+                        thr *= mcol;
+                        ro += rd * scatterDist;
+                        sf.fhp = ro;
+                        rad += directLight<GEN>(S, F, rd, sf, mat, eta, false, aniso, thr, rng, sa, sb, ic) * thr;
+                        float hr1 = rng.rand(), hr2 = rng.rand();
+                        float3 scatterDir = SampleHG(-rd, aniso, hr1, hr2);
+                        prevPdf = PhaseHG(dot(-rd, scatterDir), aniso);
+                        rd = scatterDir;
+                    }
+                }
+            }
+        }
+        if (!mediumSampled)
+        {
+            bool skipped = false;
+            float3 L = rd;
+            if (GEN && OPT(F, O_ALPHA))                       // :416-426
+            {
+                if ((mat.alphaMode == 2 && mat.opacity < mat.alphaCutoff) || (mat.alphaMode == 1 && rng.rand() > mat.opacity))
+                {
+                    depth--;
+                    skipped = true;
+                }
+            }
+            if (!skipped)
+            {
+                surfaceScatter = true;
+                rad += directLight<GEN>(S, F, rd, sf, mat, eta, true, 0.f, thr, rng, sa, sb, ic) * thr;     // :431
+                float r1 = rng.rand(), r2 = rng.rand(), r3 = rng.rand();
+                float pdf;
+                float3 f = DisneySample(mat, eta, -rd, sf.ffnormal, L, pdf, r1, r2, r3);                     // :434
+                if (pdf > 0.0f) { thr *= f / pdf; prevPdf = pdf; }
+                else terminated = true;
+            }
+            if (!terminated)
+            {
+                rd = L;
+                ro = sf.fhp + rd * PTB_EPS;                   // :442-443
+                if (GEN && OPT(F, O_MEDIUM))                  // :447-458
+                {
+                    if (dot(rd, sf.normal) < 0 && mat.medType != 0)
+                    {
+                        inMedium = true;
+                        med.x = mat.medDensity; med.y = mat.medAniso; med.z = __int_as_float(mat.medType);
+                        medCol = make_float4(mat.medColor.x, mat.medColor.y, mat.medColor.z, 0.f);
+                    }
+                    else if (mat.medType != 0) inMedium = false;
+                }
+            }
+        }
+        if (!terminated && OPT(F, O_RR))                     // :464-470
+        {
+            if (depth >= F.rrDepth)
+            {
+                float q = fminf(fmaxf(thr.x, fmaxf(thr.y, thr.z)) + 0.001f, 0.95f);
+                if (rng.rand() > q) terminated = true;
+                else thr /= q;
+            }
+        }
+    }
+
+    P.rad[p] = make_float4(rad.x, rad.y, rad.z, alpha);
+    if (!terminated)
+    {
+        depth++;
+        uint32_t nf = ((uint32_t)depth & 0xffffu) | (inMedium ? PTB_FLAG_INMEDIUM : 0u) | (surfaceScatter ? PTB_FLAG_SURFSCAT : 0u);
+        P.rayO[p] = make_float4(ro.x, ro.y, ro.z, prevPdf);
+        P.rayD[p] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(nf));
+        P.thr[p] = make_float4(thr.x, thr.y, thr.z, mat.roughness);
+        P.rng[p] = rng.s;
+        if (GEN)
+        {
+            med.w = __int_as_float(sf.matID);
+            P.med[p] = med; P.medCol[p] = medCol; P.prevUV[p] = sf.uv;
+        }
+        cont = true;
+    }
+}
+
+__device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32_t* ctr, uint32_t lane, const ShadowOut& s, uint32_t p)
+{
+    unsigned m = __ballot_sync(0xffffffffu, s.valid);
+    if (!m) return;
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(ctr, (uint32_t)__popc(m));
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (s.valid)
+    {
+        uint32_t k = b + __popc(m & ((1u << lane) - 1u));
+        P.shO[which][k] = make_float4(s.o.x, s.o.y, s.o.z, s.maxDist);
+        P.shD[which][k] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(p));
+        P.shC[which][k] = make_float4(s.c.x, s.c.y, s.c.z, 0.f);
+    }
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
+                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
+{
+    const uint32_t n = ctrThis[CTR_NPATHS];
+    const uint32_t lane = threadIdx.x & 31u;
+    InlineCounters ic{0u, 0u};
+    while (true)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        bool cont = false;
+        ShadowOut sa, sb; sa.valid = false; sb.valid = false;
+        uint32_t p = 0;
+        if (i < n)
+        {
+            p = queue[i];
+            shadePath<GEN>(S, F, P, p, cont, sa, sb, ic);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cont);
+        if (m)
+        {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(&ctrNext[CTR_NPATHS], (uint32_t)__popc(m));
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (cont) nextQueue[b + __popc(m & ((1u << lane) - 1u))] = p;
+        }
+        if (GEN) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
+        pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
+    }
+    if (GEN && (ic.segs | ic.shadows))
+    {
+        atomicAdd(&stats->pathSegments, (unsigned long long)ic.segs);
+        atomicAdd(&stats->shadowRays, (unsigned long long)ic.shadows);
+    }
+}
+
+// ------------------------------------------------------------------ shadow (any-hit) trace ----------------------
+struct AlphaMask   // deferred AnyHit alpha test: MASK only (BLEND needs the path RNG and runs inline in k_shade)
+{
+    const DevScene* S;
+    __device__ __forceinline__ bool operator()(int slot, int inst, float ux, float uy) const
+    {
+        Rng dummy; dummy.s = make_uint4(0, 0, 0, 0);
+        AlphaRng a{S, &dummy};
+        return a(slot, inst, ux, uy);
+    }
+};
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, FrameParams F, PathState P, int which, const uint32_t* __restrict__ countPtr,
+                                                           uint32_t* fetchCtr, DevStats* stats)
+{
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    const bool lights = OPT(F, O_LIGHTS);
+    const bool alpha = OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM);
+    const bool cull = F.cullBoxes != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->shadowRays, (unsigned long long)n);
+    while (true)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetchCtr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n)
+        {
+            const float4 o4 = P.shO[which][i], d4 = P.shD[which][i];
+            const float3 o = f3(o4), d = f3(d4);
+            const float maxDist = o4.w;
+            bool occluded = lights && anyLights(S, o, d, maxDist);
+            if (!occluded)
+            {
+                HitRec h;
+                if (alpha) occluded = traverse<true, true>(S, o, d, maxDist, cull, stk, h, AlphaMask{&S});
+                else occluded = traverse<true, false>(S, o, d, maxDist, cull, stk, h, NoAlpha());
+            }
+            if (!occluded)
+            {
+                const uint32_t p = __float_as_uint(d4.w);
+                const float4 c = P.shC[which][i];
+                float4 r = P.rad[p];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                P.rad[p] = r;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ accumulate / tonemap ------------------------
+// tile.glsl:70-74: color = pixelColor + accumColor, one sample pass after the other (deterministic order).
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W, PathState P, float4* accum, float4* previewOut)
+{
+    const uint32_t perSample = (uint32_t)W.vw * (uint32_t)W.vh;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < perSample; idx += gridDim.x * blockDim.x)
+    {
+        int s, px, py;
+        if (!slotToPixel(W, idx, s, px, py)) continue;
+        if (W.previewMode)
+        {
+            previewOut[(size_t)py * W.rw + px] = P.rad[idx];
+            continue;
+        }
+        float4* dst = accum + (size_t)(W.y0 + py) * F.renderW + (W.x0 + px);
+        float4 a = *dst;
+        for (int k = 0; k < W.nSamples; k++)
+        {
+            const float4 r = P.rad[idx + (uint32_t)k * perSample];
+            a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
+        }
+        *dst = a;
+    }
+}
+
+// tonemap.glsl:44-133 + float->unorm8 of glGetTexImage (Renderer.cpp:633)
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
+                                                  int simpleAcesFit, float bgr, float bgg, float bgb, uint32_t features, uchar4* __restrict__ out)
+{
+    const int n = w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 a = accum[i];
+        float3 color = f3(a.x * invSampleCounter, a.y * invSampleCounter, a.z * invSampleCounter);
+        float alpha = a.w * invSampleCounter;
+        if (enableTonemap)
+        {
+            if (enableAces)
+            {
+                if (simpleAcesFit)
+                {
+                    float3 num = color * (2.51f * color + 0.03f), den = color * (2.43f * color + 0.59f) + 0.14f;
+                    color = f3(clampf(num.x / den.x, 0.f, 1.f), clampf(num.y / den.y, 0.f, 1.f), clampf(num.z / den.z, 0.f, 1.f));
+                }
+                else
+                {
+                    float3 c = f3(color.x * 0.59719f + color.y * 0.35458f + color.z * 0.04823f, color.x * 0.07600f + color.y * 0.90834f + color.z * 0.01566f,
+                                  color.x * 0.02840f + color.y * 0.13383f + color.z * 0.83777f);
+                    float3 va = c * (c + 0.0245786f) + (-0.000090537f);
+                    float3 vb = c * (0.983729f * c + 0.4329510f) + 0.238081f;
+                    c = va / vb;
+                    c = f3(c.x * 1.60475f + c.y * -0.53108f + c.z * -0.07367f, c.x * -0.10208f + c.y * 1.10813f + c.z * -0.00605f,
+                           c.x * -0.00327f + c.y * -0.07276f + c.z * 1.07602f);
+                    color = f3(clampf(c.x, 0.f, 1.f), clampf(c.y, 0.f, 1.f), clampf(c.z, 0.f, 1.f));
+                }
+            }
+            else color = color * 1.0f / (1.0f + Luminance(color) / 1.5f);
+        }
+        color = vpow(color, 1.0f / 2.2f);
+        float outAlpha = 1.0f;
+        float3 bgCol = f3(bgr, bgg, bgb);
+        if (features & O_TRANSPBG)
+        {
+            outAlpha = alpha;
+            int x = i % w, y = i / w;
+            float mm = fmodf(floorf(((float)x + 0.5f) / 10.0f) + floorf(((float)y + 0.5f) / 10.0f), 2.0f);
+            float res = fmaxf(mm > 0.f ? 1.f : (mm < 0.f ? -1.f : 0.f), 0.0f);
+            bgCol = mix(f3(0.1f), f3(0.2f), res);
+        }
+        float4 o;
+        if (features & (O_BG | O_TRANSPBG)) { float3 m = mix(bgCol, color, alpha); o = make_float4(m.x, m.y, m.z, outAlpha); }
+        else o = make_float4(color.x, color.y, color.z, 1.0f);
+        float v[4] = {o.x, o.y, o.z, o.w};
+        unsigned char b[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            float f = v[k]; if (!(f == f)) f = 0.f;
+            f = clampf(f, 0.f, 1.f);
+            b[k] = (unsigned char)floorf(f * 255.0f + 0.5f);
+        }
+        out[i] = make_uchar4(b[0], b[1], b[2], b[3]);
+    }
+}
+
+// ------------------------------------------------------------------ parity / batch kernels ----------------------
+struct HitOut { float t; int kind, instance, matID, primSlot, triIDx; float bary[3]; int lightIdx; };
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(DevScene S, FrameParams F, const float* __restrict__ rays, long long n, int depth, HitOut* out)
+{
+    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    {
+        const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+        HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
+        float t = PTB_INF;
+        if (OPT(F, O_LIGHTS) && (!OPT(F, O_HIDE) || depth > 0)) closestLights(S, o, d, t, h.light);
+        traverse<false, false>(S, o, d, t, F.cullBoxes != 0, stk, h, NoAlpha());
+        HitOut r;
+        r.t = h.t;
+        if (h.t == PTB_INF) { r.kind = 0; r.instance = r.matID = r.primSlot = r.triIDx = r.lightIdx = -1; r.bary[0] = r.bary[1] = r.bary[2] = 0.f; }
+        else if (h.inst >= 0)
+        {
+            r.kind = 1; r.instance = h.inst; r.matID = __float_as_int(__ldg(S.instTrav + (size_t)h.inst * 4 + 1).w); r.primSlot = h.prim;
+            r.triIDx = __ldg(S.vertIndices + (size_t)h.prim * 3);
+            r.bary[0] = xs(xs(1.0f, h.bu), h.bv); r.bary[1] = h.bu; r.bary[2] = h.bv; r.lightIdx = -1;
+        }
+        else { r.kind = 2; r.instance = r.matID = r.primSlot = r.triIDx = -1; r.bary[0] = r.bary[1] = r.bary[2] = 0.f; r.lightIdx = h.light; }
+        out[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_any_batch(DevScene S, FrameParams F, const float* __restrict__ rays, const float* __restrict__ maxDist, long long n, int* out)
+{
+    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    {
+        const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+        bool occ = OPT(F, O_LIGHTS) && anyLights(S, o, d, maxDist[i]);
+        if (!occ) { HitRec h; occ = traverse<true, false>(S, o, d, maxDist[i], F.cullBoxes != 0, stk, h, NoAlpha()); }
+        out[i] = occ ? 1 : 0;
+    }
+}
+
+struct BsdfQuery { float mat[32]; float V[3], N[3], L[3]; float eta, r1, r2, r3; };
+struct BsdfResult { float f[3]; float pdf; float L[3]; };
+
+__global__ void k_bsdf_batch(const BsdfQuery* __restrict__ q, long long n, BsdfResult* out, int sample)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* P = q[i].mat;
+    Material mat;
+    mat.baseColor = f3(P[0], P[1], P[2]); mat.anisotropic = P[3]; mat.emission = f3(P[4], P[5], P[6]);
+    mat.metallic = P[8]; mat.roughness = fmaxf(P[9], 0.001f); mat.subsurface = P[10]; mat.specularTint = P[11];
+    mat.sheen = P[12]; mat.sheenTint = P[13]; mat.clearcoat = P[14]; mat.clearcoatRoughness = mixf(0.1f, 0.001f, P[15]);
+    mat.specTrans = P[16]; mat.ior = P[17]; mat.medType = 0; mat.medDensity = 0; mat.medColor = f3(0.f); mat.medAniso = 0;
+    mat.opacity = P[28]; mat.alphaMode = (int)P[29]; mat.alphaCutoff = P[30];
+    materialFinish(mat);
+    float3 V = f3(q[i].V[0], q[i].V[1], q[i].V[2]), N = f3(q[i].N[0], q[i].N[1], q[i].N[2]), L = f3(q[i].L[0], q[i].L[1], q[i].L[2]);
+    float pdf; float3 f;
+    if (sample) f = DisneySample(mat, q[i].eta, V, N, L, pdf, q[i].r1, q[i].r2, q[i].r3);
+    else f = DisneyEval(mat, q[i].eta, V, N, L, pdf);
+    out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf; out[i].L[0] = L.x; out[i].L[1] = L.y; out[i].L[2] = L.z;
+}
+
+__global__ void k_camera_rays(FrameParams F, WaveParams W, float* out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.renderW * F.renderH) return;
+    int x = i % F.renderW, y = i / F.renderW;
+    Rng rng; float3 ro, rd;
+    cameraRay(F, W, x, y, W.firstSample, rng, ro, rd);
+    out[i * 6 + 0] = ro.x; out[i * 6 + 1] = ro.y; out[i * 6 + 2] = ro.z; out[i * 6 + 3] = rd.x; out[i * 6 + 4] = rd.y; out[i * 6 + 5] = rd.z;
+}
+
+// ------------------------------------------------------------------ launchers -----------------------------------
+static inline cudaStream_t st(const LaunchCfg& c) { return (cudaStream_t)c.stream; }
+static inline size_t stackBytes(const DevScene& S, int threads) { return (size_t)S.stackDepth * threads * sizeof(uint32_t); }
+
+static int traceBlocksPerSM(const DevScene& S)
+{
+    static int cachedDepth = -1, cached = 0;
+    if (cachedDepth != S.stackDepth)
+    {
+        size_t smem = stackBytes(S, TRACE_THREADS);
+        cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace, TRACE_THREADS, smem);
+        cached = nb > 0 ? nb : 1; cachedDepth = S.stackDepth;
+    }
+    return cached;
+}
+
+void ptbk_camera(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, uint32_t* ctr0)
+{
+    int blocks = c.numSMs * 8;
+    k_camera<<<blocks, 256, 0, st(c)>>>(S, F, W, P, ctr0);
+    g_launches++;
+}
+
+void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats)
+{
+    int bps = traceBlocksPerSM(S);
+    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats);
+    g_launches++;
+}
+
+void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
+{
+    static int bpsGen = 0, bpsFast = 0;
+    if (!bpsGen)
+    {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsGen, k_shade<true>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false>, SHADE_THREADS, 0);
+        if (bpsGen < 1) bpsGen = 1; if (bpsFast < 1) bpsFast = 1;
+    }
+    if (F.general) k_shade<true><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    else k_shade<false><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    g_launches++;
+}
+
+void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
+                 uint32_t* fetchCtr, DevStats* stats)
+{
+    int bps = traceBlocksPerSM(S);
+    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
+    g_launches++;
+}
+
+void ptbk_accumulate(const LaunchCfg& c, const FrameParams& F, const WaveParams& W, const PathState& P, float4* accum, float4* previewOut)
+{
+    k_accumulate<<<c.numSMs * 8, 256, 0, st(c)>>>(F, W, P, accum, previewOut);
+    g_launches++;
+}
+
+void ptbk_tonemap(const LaunchCfg& c, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
+                  int simpleAcesFit, const float* bg, uint32_t features, uchar4* out)
+{
+    k_tonemap<<<c.numSMs * 8, 256, 0, st(c)>>>(accum, w, h, invSampleCounter, enableTonemap, enableAces, simpleAcesFit, bg[0], bg[1], bg[2], features, out);
+    g_launches++;
+}
+
+void ptbk_trace_closest_batch(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const float* rays, long long n, int depth, void* hitsOut)
+{
+    int bps = traceBlocksPerSM(S);
+    k_trace_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, rays, n, depth, (HitOut*)hitsOut);
+    g_launches++;
+}
+void ptbk_trace_any_batch(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const float* rays, const float* maxDist, long long n, int* out)
+{
+    int bps = traceBlocksPerSM(S);
+    k_any_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, rays, maxDist, n, out);
+    g_launches++;
+}
+void ptbk_bsdf_batch(const LaunchCfg& c, const void* queries, long long n, void* results, int sample)
+{
+    if (n <= 0) return;
+    k_bsdf_batch<<<(unsigned)((n + 127) / 128), 128, 0, st(c)>>>((const BsdfQuery*)queries, n, (BsdfResult*)results, sample);
+    g_launches++;
+}
+void ptbk_camera_rays(const LaunchCfg& c, const FrameParams& F, const WaveParams& W, float* outRays)
+{
+    int n = F.renderW * F.renderH;
+    k_camera_rays<<<(n + 255) / 256, 256, 0, st(c)>>>(F, W, outRays);
+    g_launches++;
+}

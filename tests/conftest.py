@@ -1,0 +1,47 @@
+import os, sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import glsl_pathtracer_b200  # noqa: F401  (import shim for the hyphenated package directory)
+from glsl_pathtracer_b200 import scene_io
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+_SCENES = {}
+
+
+def load_scene_cached(name):
+    if name not in _SCENES:
+        _SCENES[name] = scene_io.load_scene(name)
+    return _SCENES[name]
+
+
+def scene_at(name, w, h, tw=None, th=None, depth=None):
+    """Fresh copy of a fixture scene with the render size / tile size / depth overridden."""
+    import copy
+    sc = copy.deepcopy(load_scene_cached(name))
+    ro = sc.renderOptions
+    ro.renderResolution = (w, h); ro.windowResolution = (w, h)
+    if tw: ro.tileWidth = tw
+    if th: ro.tileHeight = th
+    if depth is not None: ro.maxDepth = depth
+    return sc
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    from oracle import binding
+    binding.lib()
+    return binding
+
+
+def rel_mse(a, b, eps=1e-2):
+    """relMSE of b against reference a over rgb: mean((a-b)^2 / (a^2 + eps))."""
+    a = np.asarray(a, np.float64)[..., :3]; b = np.asarray(b, np.float64)[..., :3]
+    return float(np.mean((a - b) ** 2 / (a * a + eps)))

@@ -1,0 +1,120 @@
+"""G1 gate: the CUDA traversal, called through the C ABI, returns bit-identical hit kind / instance /
+material / primitive slot / triangle id and t (tolerance 1e-5 relative, observed: bit-equal) versus the oracle's
+reference-faithful host traversal of the same flattened BVH, on primary, random and bounce-like rays."""
+import numpy as np
+import pytest
+from conftest import scene_at
+
+pytestmark = pytest.mark.gpu
+SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot"]
+
+
+def _ctx(sc):
+    from glsl_pathtracer_b200 import capi
+    return capi.Context(sc)
+
+
+def random_rays(sc, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array(sc.sceneBounds[0], np.float32), np.array(sc.sceneBounds[1], np.float32)
+    ext = hi - lo
+    o = (lo - 0.25 * ext + rng.random((n, 3), dtype=np.float32) * 1.5 * ext).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # a share of exactly axis-parallel rays: 0*inf NaNs in the slab test
+    k = n // 16
+    d[:k] = 0; d[np.arange(k), rng.integers(0, 3, k)] = rng.choice([-1.0, 1.0], k)
+    return np.concatenate([o, d.astype(np.float32)], axis=1)
+
+
+def assert_hits_equal(a, b):
+    for f in ("kind", "instance", "matID", "primSlot", "triIDx", "lightIdx"):
+        bad = np.nonzero(a[f] != b[f])[0]
+        assert bad.size == 0, f"{f}: {bad.size} mismatches, first ray {bad[:5]}: {a[f][bad[:5]]} vs {b[f][bad[:5]]}"
+    ta, tb = a["t"], b["t"]
+    assert np.all(np.abs(ta - tb) <= 1e-5 * np.abs(tb)), "t beyond 1e-5 relative"
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32)), "t not bit-identical"
+    hit = a["kind"] == 1
+    assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32)), "barycentrics not bit-identical"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_nodes_roundtrip_byte_exact(name, oracle_mod):
+    sc = scene_at(name, 64, 64, 32, 32)
+    ctx = _ctx(sc)
+    assert ctx.read_nodes().tobytes() == np.ascontiguousarray(sc.nodes, np.float32).tobytes()
+    assert ctx.stack_depth() <= 64
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_primary_rays_match_oracle(name, oracle_mod):
+    sc = scene_at(name, 480, 270, 128, 72)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    rays_o = orc.camera_rays(1)
+    rays_g = ctx.camera_rays(1)
+    assert np.array_equal(rays_o.view(np.uint32), rays_g.view(np.uint32)), "pinhole primary rays must be bit-identical"
+    for depth in (0, 1):
+        assert_hits_equal(ctx.trace_closest(rays_o, depth), orc.trace_closest(rays_o, depth))
+    ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_random_and_bounce_rays_match_oracle(name, oracle_mod):
+    sc = scene_at(name, 64, 64, 32, 32)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    rays = random_rays(sc, 200_000, 7)
+    h_o = orc.trace_closest(rays, 1)
+    assert_hits_equal(ctx.trace_closest(rays, 1), h_o)
+    # bounce-like rays: start on the surfaces found above, cosine-ish random directions
+    hit = h_o["kind"] == 1
+    p = rays[hit, :3] + rays[hit, 3:] * h_o["t"][hit, None]
+    rng = np.random.default_rng(11)
+    d = rng.normal(size=p.shape).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = np.concatenate([(p + d * np.float32(0.0003)).astype(np.float32), d], axis=1)
+    assert_hits_equal(ctx.trace_closest(b, 1), orc.trace_closest(b, 1))
+    ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_culled_traversal_identical(name, oracle_mod):
+    """ptb_set_cull(1) skips boxes entered beyond the current hit; IDs and t must not change."""
+    sc = scene_at(name, 320, 180, 80, 60)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    rays = np.concatenate([orc.camera_rays(1), random_rays(sc, 100_000, 3)])
+    ref = orc.trace_closest(rays, 1)
+    ctx.set_cull(True)
+    assert_hits_equal(ctx.trace_closest(rays, 1), ref)
+    ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_any_hit_matches_oracle(name, oracle_mod):
+    sc = scene_at(name, 64, 64, 32, 32)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    rays = random_rays(sc, 100_000, 5)
+    rng = np.random.default_rng(9)
+    ext = float(np.linalg.norm(np.array(sc.sceneBounds[1]) - np.array(sc.sceneBounds[0])))
+    md = (rng.random(len(rays), dtype=np.float32) * ext).astype(np.float32)
+    md[::3] = np.float32(1e6 - 0.0003)
+    a, b = ctx.trace_any(rays, md), orc.trace_any(rays, md)
+    assert np.array_equal(a, b), f"{np.count_nonzero(a != b)} occlusion mismatches"
+    ctx.set_cull(True)
+    assert np.array_equal(ctx.trace_any(rays, md), b)
+    ctx.close(); orc.close()
+
+
+def test_empty_and_invalid_inputs():
+    from glsl_pathtracer_b200 import capi
+    sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
+    ctx = _ctx(sc)
+    assert len(ctx.trace_closest(np.zeros((0, 6), np.float32))) == 0
+    with pytest.raises(capi.PtbError):
+        ctx.render_tile(99, 0, 2)
+    with pytest.raises(capi.PtbError):
+        ctx.render_samples(0, 1)
+    # degenerate rays: zero direction / NaN origin must not hang or crash and must agree with "miss or something" deterministically
+    rays = np.zeros((4, 6), np.float32); rays[1, 0] = np.nan; rays[2, 3:] = [0, 0, 1]; rays[3, 3:] = [1e-30, 1, 0]
+    h1, h2 = ctx.trace_closest(rays), ctx.trace_closest(rays)
+    assert h1.tobytes() == h2.tobytes()
+    ctx.close()
