@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -119,7 +120,8 @@ struct PtbCtx
     DevBuf<uint4> rng;
     DevBuf<int> hitInst;
     DevBuf<float2> prevUV;
-    DevBuf<uint32_t> queue[2], counters;
+    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist;
+    int sortMode = 1;          // 0 off, 1 sort bounces >= 1, 2 sort every bounce
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
 
@@ -289,7 +291,14 @@ int buildLightsPre(PtbCtx* c, const float* lights, int n)
         lp[i * 8 + 0] = make_float4(pos[0], pos[1], pos[2], type);
         lp[i * 8 + 1] = make_float4(em[0], em[1], em[2], area);
         lp[i * 8 + 2] = make_float4(u[0], u[1], u[2], radius);
-        lp[i * 8 + 3] = make_float4(v[0], v[1], v[2], 0.f);
+        // samePlaneAsPrevious: this quad's plane (normal, plane.w) is bit-identical to the previous light's plane
+        float same = 0.f;
+        if (i > 0 && type == 0.f && lp[(i - 1) * 8 + 0].w == 0.f)
+        {
+            const float4& pe = lp[(i - 1) * 8 + 4];
+            if (f2u(pe.x) == f2u(nx) && f2u(pe.y) == f2u(ny) && f2u(pe.z) == f2u(nz) && f2u(pe.w) == f2u(planeW)) same = 1.f;
+        }
+        lp[i * 8 + 3] = make_float4(v[0], v[1], v[2], same);
         lp[i * 8 + 4] = make_float4(nx, ny, nz, planeW);
         lp[i * 8 + 5] = make_float4(u[0] * su, u[1] * su, u[2] * su, 0.f);
         lp[i * 8 + 6] = make_float4(v[0] * sv, v[1] * sv, v[2] * sv, 0.f);
@@ -337,6 +346,7 @@ int ensureWaveState(PtbCtx* c, size_t slots)
         c->stateGeneral = true;
     }
     CK(c->counters.alloc((size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE));
+    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n));
     c->slotCap = n;
     return PTB_OK;
 }
@@ -370,6 +380,9 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
     LaunchCfg L = cfg(c);
     uint32_t* ctr = c->counters.p;
     CK(cudaMemsetAsync(ctr, 0, (size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE * sizeof(uint32_t), c->stream));
+    const int numKeys = c->S.numMaterials + 2;
+    CK(c->sortHist.alloc((size_t)numKeys * 2));
+    CK(cudaMemsetAsync(c->sortHist.p, 0, (size_t)numKeys * 2 * sizeof(uint32_t), c->stream));
     ptbk_camera(L, c->S, F, W, P, ctr);
     const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
     const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
@@ -380,9 +393,17 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
         uint32_t* ci = ctr + (size_t)it * PTB_CTR_STRIDE;
         uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
-        ptbk_trace(L, c->S, F, P, P.queue[it & 1], ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p);
+        const bool sortThis = c->sortMode == 2 || (c->sortMode == 1 && it >= 1);
+        ptbk_trace(L, c->S, F, P, P.queue[it & 1], ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
+                   sortThis ? c->sortKeys.p : nullptr, c->sortHist.p);
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
-        ptbk_shade(L, c->S, F, P, P.queue[it & 1], ci, cn, P.queue[(it + 1) & 1], c->dstats.p);
+        const uint32_t* shadeQueue = P.queue[it & 1];
+        if (sortThis)
+        {   // material-sorted shading: counting sort of the queue by (miss | light | material)
+            ptbk_sort(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
+            shadeQueue = c->sortedQueue.p;
+        }
+        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p);
         if (!F.inlineShadow)
         {
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
@@ -506,6 +527,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), s));
     CK(cudaStreamSynchronize(s));
     c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
+    if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
     *out = c;
     return PTB_OK;
 }
@@ -520,6 +542,7 @@ int ptb_destroy(PtbCtx* c)
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
     c->rayO.release(); c->rayD.release(); c->thr.release(); c->rad.release(); c->hit.release(); c->med.release(); c->medCol.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
+    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release();
     c->rng.release(); c->hitInst.release(); c->prevUV.release(); c->counters.release(); c->dstats.release();
     for (auto e : c->traceEvents) cudaEventDestroy(e);
     if (c->evStart) cudaEventDestroy(c->evStart);

@@ -108,20 +108,27 @@ __device__ __forceinline__ float aabbHit(float minx, float miny, float minz, flo
     return (t1 >= t0) ? (t0 > 0.f ? t0 : t1) : -1.0f;
 }
 
-// intersection.glsl:47-66 (RectIntersect) on pre-scaled u,v and precomputed plane (closest_hit.glsl:49-53 hoisted to upload time)
-__device__ __forceinline__ float rectHit(float3 pos, float3 uS, float3 vS, float3 n, float planeW, float3 o, float3 d)
+// intersection.glsl:47-66 (RectIntersect) split into its plane part and its rectangle part.  Lights that share a plane
+// bit-for-bit (same normal, same plane.w — e.g. the 17 ceiling strips of hyperion_rect_lights) reuse dt, t and p: the same
+// inputs give the same IEEE results, so the outcome per light is unchanged (closest_hit.glsl:49-53 hoisted to upload time).
+struct PlaneHit { float dt, t; float3 p; bool valid; };
+__device__ __forceinline__ void planeEval(float3 n, float planeW, float3 o, float3 d, PlaneHit& ph)
 {
-    float dt = xdot(d, n);
-    float t = xd(xs(planeW, xdot(n, o)), dt);
-    if (t > PTB_EPS)
+    ph.dt = xdot(d, n);
+    ph.t = xd(xs(planeW, xdot(n, o)), ph.dt);
+    ph.valid = ph.t > PTB_EPS;
+    ph.p = xmad(o, d, ph.t);
+}
+__device__ __forceinline__ float rectInside(const PlaneHit& ph, float3 pos, float3 uS, float3 vS)
+{
+    if (ph.valid)
     {
-        float3 p = xmad(o, d, t);
-        float3 vi = xsub(p, pos);
+        float3 vi = xsub(ph.p, pos);
         float a1 = xdot(uS, vi);
         if (a1 >= 0.0f && a1 <= 1.0f)
         {
             float a2 = xdot(vS, vi);
-            if (a2 >= 0.0f && a2 <= 1.0f) return t;
+            if (a2 >= 0.0f && a2 <= 1.0f) return ph.t;
         }
     }
     return PTB_INF;
@@ -141,33 +148,25 @@ __device__ __forceinline__ float sphereHit(float rad, float3 pos, float3 o, floa
     return PTB_INF;
 }
 
-struct LightPre   // 8 float4, built at upload (ptb_api.cpp buildLightsPre)
-{
-    float3 position; float type; float3 emission; float area; float3 u; float radius; float3 v; float3 normal; float planeW;
-    float3 uS, vS;
-};
-__device__ __forceinline__ void loadLightGeom(const DevScene& S, int i, float3& pos, float& type, float& radius, float3& n, float& planeW, float3& uS, float3& vS)
-{
-    const float4* p = S.lightsPre + (size_t)i * 8;
-    float4 a = __ldg(p), c = __ldg(p + 2), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
-    pos = f3(a); type = a.w; radius = c.w; n = f3(e); planeW = e.w; uS = f3(f); vS = f3(g);
-}
-
+// lightsPre rows (8 float4 per light, built at upload by buildLightsPre in ptb_api.cpp):
+//   0: position, type | 1: emission, area | 2: u, radius | 3: v, samePlaneAsPrevious | 4: normal, plane.w | 5: u/dot(u,u) | 6: v/dot(v,v)
 // Light loop of ClosestHit (closest_hit.glsl:28-86): nearest light, first index wins ties (strict <).
 __device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float3 d, float& t, int& light)
 {
+    PlaneHit ph; ph.dt = 0.f; ph.t = 0.f; ph.valid = false; ph.p = f3(0.f);
     for (int i = 0; i < S.numLights; i++)
     {
-        float3 pos, n, uS, vS; float type, radius, planeW;
-        loadLightGeom(S, i, pos, type, radius, n, planeW, uS, vS);
+        const float4* p = S.lightsPre + (size_t)i * 8;
+        const float4 a = __ldg(p);
         float dist = PTB_INF;
-        if (type == 0.0f)
+        if (a.w == 0.0f)
         {
-            if (xdot(n, d) > 0.f) continue;
-            dist = rectHit(pos, uS, vS, n, planeW, o, d);
+            if (__ldg(p + 3).w == 0.0f) { const float4 e = __ldg(p + 4); planeEval(f3(e), e.w, o, d, ph); }
+            if (ph.dt > 0.f) continue;                       // hide backfacing quad light (closest_hit.glsl:50)
+            dist = rectInside(ph, f3(a), f3(__ldg(p + 5)), f3(__ldg(p + 6)));
         }
-        else if (type == 1.0f)
-            dist = sphereHit(radius, pos, o, d);
+        else if (a.w == 1.0f)
+            dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
         else
             continue;
         if (dist < 0.f) dist = PTB_INF;
@@ -177,13 +176,19 @@ __device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float
 // Light loop of AnyHit (anyhit.glsl:28-63): two-sided quads.
 __device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d, float maxDist)
 {
+    PlaneHit ph; ph.dt = 0.f; ph.t = 0.f; ph.valid = false; ph.p = f3(0.f);
     for (int i = 0; i < S.numLights; i++)
     {
-        float3 pos, n, uS, vS; float type, radius, planeW;
-        loadLightGeom(S, i, pos, type, radius, n, planeW, uS, vS);
+        const float4* p = S.lightsPre + (size_t)i * 8;
+        const float4 a = __ldg(p);
         float dist;
-        if (type == 0.0f) dist = rectHit(pos, uS, vS, n, planeW, o, d);
-        else if (type == 1.0f) dist = sphereHit(radius, pos, o, d);
+        if (a.w == 0.0f)
+        {
+            if (__ldg(p + 3).w == 0.0f) { const float4 e = __ldg(p + 4); planeEval(f3(e), e.w, o, d, ph); }
+            // RectIntersect returns t or INF; the inside test only matters when t itself can pass `d < maxDist`
+            dist = (ph.valid && ph.t < maxDist) ? rectInside(ph, f3(a), f3(__ldg(p + 5)), f3(__ldg(p + 6))) : PTB_INF;
+        }
+        else if (a.w == 1.0f) dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
         else continue;
         if (dist > 0.0f && dist < maxDist) return true;
     }

@@ -111,7 +111,9 @@ struct LaunchCfg { int numSMs; void* stream; };
 
 void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
 void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats);
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist);
+void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
+               uint32_t* sorted);
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats);
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,

@@ -11,6 +11,7 @@
 //   k_tonemap     tonemap.glsl         on readback
 #include "ptb_device.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 using namespace ptb;
 
@@ -138,8 +139,17 @@ __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveP
 // ------------------------------------------------------------------ closest-hit trace ---------------------------
 extern __shared__ uint32_t g_stackSmem[];
 
+// Shading sort key: 0 = miss, 1 = analytic light, 2 + matID = triangle of that material (material-sorted shading).
+__device__ __forceinline__ uint32_t shadeKey(const DevScene& S, int hitInst)
+{
+    if (hitInst == -1) return 0u;
+    if (hitInst <= -2) return 1u;
+    return 2u + (uint32_t)__float_as_int(__ldg(S.instTrav + (size_t)hitInst * 4 + 1).w);
+}
+
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
-                                                          const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats)
+                                                          const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats,
+                                                          uint32_t* __restrict__ keys, uint32_t* hist)
 {
     const uint32_t n = *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
@@ -168,8 +178,49 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams
             }
             traverse<false, false>(S, o, d, t, cull, stk, h, NoAlpha());
             P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
-            P.hitInst[p] = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
+            const int hi = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
+            P.hitInst[p] = hi;
+            if (keys)
+            {   // histogram of shading keys, one atomic per distinct key per (converged part of the) warp
+                const uint32_t key = shadeKey(S, hi);
+                keys[i] = key;
+                const unsigned peers = __match_any_sync(__activemask(), key);
+                if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+            }
         }
+    }
+}
+
+// Exclusive scan of the key histogram into bucket cursors (one warp); clears the histogram for the next bounce.
+__global__ void k_sort_scan(uint32_t* hist, uint32_t* cursor, int numKeys)
+{
+    const int lane = threadIdx.x;
+    const int per = (numKeys + 31) / 32;
+    uint32_t sum = 0;
+    for (int k = lane * per; k < min(numKeys, (lane + 1) * per); k++) sum += hist[k];
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    uint32_t run = incl - sum;
+    for (int k = lane * per; k < min(numKeys, (lane + 1) * per); k++) { uint32_t h = hist[k]; cursor[k] = run; run += h; hist[k] = 0; }
+}
+
+// Counting-sort scatter: queue entries -> key buckets (order inside a bucket follows the input order chunk-wise).
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
+                                                       uint32_t* cursor, uint32_t* __restrict__ sorted)
+{
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = base + lane;
+        const bool live = i < n;
+        const uint32_t key = live ? keys[i] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        uint32_t b = 0;
+        const int leader = __ffs(peers) - 1;
+        if (live && (int)lane == leader) b = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        b = __shfl_sync(0xffffffffu, b, leader);
+        if (live) sorted[b + __popc(peers & ((1u << lane) - 1u))] = queue[i];
     }
 }
 
@@ -611,8 +662,8 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
     }
 }
 
-template <bool GEN>
-__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
+template <bool GEN, int MINB>
+__global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
                                                           uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
 {
     const uint32_t n = ctrThis[CTR_NPATHS];
@@ -889,25 +940,39 @@ void ptbk_camera(const LaunchCfg& c, const DevScene& S, const FrameParams& F, co
 }
 
 void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats)
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist)
 {
     int bps = traceBlocksPerSM(S);
-    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats);
+    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist);
     g_launches++;
+}
+
+void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
+               uint32_t* sorted)
+{
+    k_sort_scan<<<1, 32, 0, st(c)>>>(hist, cursor, numKeys);
+    k_sort_scatter<<<c.numSMs * 8, 256, 0, st(c)>>>(queue, keys, countPtr, cursor, sorted);
+    g_launches += 2;
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
 {
-    static int bpsGen = 0, bpsFast = 0;
+    static int bpsGen = 0, bpsFast = 0, occ = 0;
     if (!bpsGen)
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsGen, k_shade<true>, SHADE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false>, SHADE_THREADS, 0);
+        const char* e = getenv("PTB_SHADE_OCC");      // tuning knob: resident 128-thread blocks per SM the fast shade kernel is compiled for
+        occ = e ? atoi(e) : 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsGen, k_shade<true, 3>, SHADE_THREADS, 0);
+        if (occ >= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 8>, SHADE_THREADS, 0);
+        else if (occ >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 6>, SHADE_THREADS, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 4>, SHADE_THREADS, 0);
         if (bpsGen < 1) bpsGen = 1; if (bpsFast < 1) bpsFast = 1;
     }
-    if (F.general) k_shade<true><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
-    else k_shade<false><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    if (F.general) k_shade<true, 3><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    else if (occ >= 8) k_shade<false, 8><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    else if (occ >= 6) k_shade<false, 6><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    else k_shade<false, 4><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
     g_launches++;
 }
 

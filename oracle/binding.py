@@ -38,7 +38,8 @@ BSDF_RESULT_DTYPE = np.dtype([("f", "<f4", 3), ("pdf", "<f4"), ("L", "<f4", 3)])
 
 
 class OrcStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("closestRays", "anyRays", "nodeVisits", "internalSteps", "triTests", "tlasLeaves", "surfaceHits")]
+    _fields_ = [(n, C.c_uint64) for n in ("closestRays", "anyRays", "nodeVisits", "internalSteps", "triTests", "tlasLeaves", "surfaceHits",
+                                         "anyNodeVisits", "anyInternalSteps", "anyTriTests", "anyTlasLeaves")]
 
 
 def build(force: bool = False) -> str:

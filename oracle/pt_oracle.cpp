@@ -117,7 +117,8 @@ struct Rng
 inline float Luminance(vec3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; }   // globals.glsl:173
 
 // ---------------------------------------------------------------- context ----------------------------------------
-struct Counters { uint64_t closestRays = 0, anyRays = 0, nodeVisits = 0, internalSteps = 0, triTests = 0, tlasLeaves = 0, surfaceHits = 0; };
+struct Counters { uint64_t closestRays = 0, anyRays = 0, nodeVisits = 0, internalSteps = 0, triTests = 0, tlasLeaves = 0, surfaceHits = 0,
+                  anyNodeVisits = 0, anyInternalSteps = 0, anyTriTests = 0, anyTlasLeaves = 0; };
 
 } // namespace
 
@@ -558,13 +559,13 @@ bool AnyHit(Ctx& c, Ray r, float maxDist, bool allowAlpha = true)
 
     while (index != -1)
     {
-        if (c.cnt) c.cnt->nodeVisits++;
+        if (c.cnt) c.cnt->anyNodeVisits++;
         int leftIndex = (int)N[index * 9 + 6], rightIndex = (int)N[index * 9 + 7], leaf = (int)N[index * 9 + 8];
         if (leaf > 0)
         {
             for (int i = 0; i < rightIndex; i++)
             {
-                if (c.cnt) c.cnt->triTests++;
+                if (c.cnt) c.cnt->anyTriTests++;
                 const int32_t* vi = &s->vertIndices[(size_t)(leftIndex + i) * 3];
                 const float* p0 = &s->verticesUVX[(size_t)vi[0] * 4]; const float* p1 = &s->verticesUVX[(size_t)vi[1] * 4];
                 const float* p2 = &s->verticesUVX[(size_t)vi[2] * 4];
@@ -606,7 +607,7 @@ bool AnyHit(Ctx& c, Ray r, float maxDist, bool allowAlpha = true)
         }
         else if (leaf < 0)
         {
-            if (c.cnt) c.cnt->tlasLeaves++;
+            if (c.cnt) c.cnt->anyTlasLeaves++;
             inverse4(&s->transforms[(size_t)(-leaf - 1) * 16], invMat);
             rTrans.origin = xformPoint(invMat, r.origin, 1.0f);
             rTrans.direction = xformPoint(invMat, r.direction, 0.0f);
@@ -618,7 +619,7 @@ bool AnyHit(Ctx& c, Ray r, float maxDist, bool allowAlpha = true)
         }
         else
         {
-            if (c.cnt) c.cnt->internalSteps++;
+            if (c.cnt) c.cnt->anyInternalSteps++;
             float e0, e1;
             leftHit = AABBIntersect(texel3(s->nodes, leftIndex * 3 + 0), texel3(s->nodes, leftIndex * 3 + 1), rTrans, &e0);
             rightHit = AABBIntersect(texel3(s->nodes, rightIndex * 3 + 0), texel3(s->nodes, rightIndex * 3 + 1), rTrans, &e1);
@@ -1359,6 +1360,7 @@ void mergeCounters(Counters& dst, const Counters& a)
 {
     dst.closestRays += a.closestRays; dst.anyRays += a.anyRays; dst.nodeVisits += a.nodeVisits; dst.internalSteps += a.internalSteps;
     dst.triTests += a.triTests; dst.tlasLeaves += a.tlasLeaves; dst.surfaceHits += a.surfaceHits;
+    dst.anyNodeVisits += a.anyNodeVisits; dst.anyInternalSteps += a.anyInternalSteps; dst.anyTriTests += a.anyTriTests; dst.anyTlasLeaves += a.anyTlasLeaves;
 }
 
 void renderRect(OrcCtx* h, int firstSample, int nSamples, int x0, int y0, int x1, int y1, float* accum, int fixedFrame, int onlyTx, int onlyTy)
@@ -1690,6 +1692,8 @@ void orc_get_stats(OrcCtx* h, OrcStats* out)
     out->closestRays = h->total.closestRays; out->anyRays = h->total.anyRays; out->nodeVisits = h->total.nodeVisits;
     out->internalSteps = h->total.internalSteps; out->triTests = h->total.triTests; out->tlasLeaves = h->total.tlasLeaves;
     out->surfaceHits = h->total.surfaceHits;
+    out->anyNodeVisits = h->total.anyNodeVisits; out->anyInternalSteps = h->total.anyInternalSteps; out->anyTriTests = h->total.anyTriTests;
+    out->anyTlasLeaves = h->total.anyTlasLeaves;
 }
 void orc_reset_stats(OrcCtx* h) { h->total = Counters(); }
 

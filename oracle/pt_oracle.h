@@ -62,8 +62,9 @@ typedef struct OrcHit {
 
 typedef struct OrcStats {
     uint64_t closestRays, anyRays;            /* path segments / shadow rays */
-    uint64_t nodeVisits, internalSteps, triTests, tlasLeaves;   /* summed over closest+any */
+    uint64_t nodeVisits, internalSteps, triTests, tlasLeaves;   /* closest-hit traversals */
     uint64_t surfaceHits;
+    uint64_t anyNodeVisits, anyInternalSteps, anyTriTests, anyTlasLeaves;   /* any-hit traversals */
 } OrcStats;
 
 /* BSDF probe input: material row (32 floats as uploaded) + geometry. */
