@@ -521,7 +521,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     // default camera: looking down -z from the origin (the caller sets the real one with ptb_set_camera)
     c->cam = PtbCamera{{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, 1.0f, 1.0f, 0.0f};
     refreshFrameParams(c);
-    c->F.cullBoxes = 0;
+    c->F.cullBoxes = 1;      // identical hits, fewer node fetches (tests/test_gpu_trace.py::test_culled_traversal_identical)
     if ((rc = allocFrameBuffers(c)) != PTB_OK) { ptb_destroy(c); return rc; }
     CK(c->dstats.alloc(1));
     CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), s));

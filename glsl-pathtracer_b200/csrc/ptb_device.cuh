@@ -199,15 +199,18 @@ __device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d,
 // thread-local array for the rarely used inline traversal inside the shade kernel.
 struct SmemStack
 {
-    uint32_t* base; int stride;
-    __device__ __forceinline__ void set(int i, uint32_t v) { base[i * stride] = v; }
-    __device__ __forceinline__ uint32_t get(int i) const { return base[i * stride]; }
+    uint32_t* base; uint32_t* top; int stride;
+    __device__ __forceinline__ SmemStack(uint32_t* b, int strideWords) : base(b), top(b), stride(strideWords) {}
+    __device__ __forceinline__ void reset() { top = base; }
+    __device__ __forceinline__ void push(uint32_t v) { *top = v; top += stride; }
+    __device__ __forceinline__ uint32_t pop() { top -= stride; return *top; }
 };
 struct LocalStack
 {
-    uint32_t a[64];
-    __device__ __forceinline__ void set(int i, uint32_t v) { a[i] = v; }
-    __device__ __forceinline__ uint32_t get(int i) const { return a[i]; }
+    uint32_t a[64]; int sp = 0;
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(uint32_t v) { a[sp++] = v; }
+    __device__ __forceinline__ uint32_t pop() { return a[--sp]; }
 };
 
 // Alpha test hook of AnyHit (anyhit.glsl:118-141), only in inline mode / MASK materials.
@@ -220,42 +223,46 @@ struct NoAlpha { };
 //   instTrav[k]= rows of inverse(transform) + {rootMeta, matID}
 // Visiting order, near/far rule (left first on ties), strict-< acceptance and the un-normalised transformed direction are the
 // reference's, so primitive/instance IDs and t are identical to a host traversal of the canonical array.
+// Control flow is "while-while": every lane keeps descending internal nodes until it holds a leaf / instance / sentinel, then
+// the warp processes those together — incoherent warps spend fewer issue slots with most lanes masked off.
 // ANY: return true at the first accepted hit with t < tmax.  alphaFn(slot, inst, u, v) -> accept? (only when ALPHA)
-template <bool ANY, bool ALPHA, class Stack, class AlphaFn>
-__device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, float tmax, bool cull, Stack& stk, HitRec& h, AlphaFn alphaFn)
+template <bool ANY, bool ALPHA, bool CULL, class Stack, class AlphaFn>
+__device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, float tmax, Stack& stk, HitRec& h, AlphaFn alphaFn)
 {
     float t = tmax;
-    int sp = 0;
-    stk.set(sp++, PTB_META_NONE);
+    stk.reset();                                              // an any-hit early return leaves entries behind
+    stk.push(PTB_META_NONE);
     uint32_t cur = S.rootMeta;
     bool inBlas = false;
     int curInst = -1;
     float3 ro = o, rd = d;
     float3 inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
+    const float4* __restrict__ innerBase = S.inner;
 
     while (true)
     {
-        const uint32_t kind = cur >> 30;
-        if (kind == PTB_K_INNER)
+        while (cur < (1u << 30))                              // PTB_K_INNER: closest_hit.glsl:173-205
         {
-            const float4* n = S.inner + (size_t)cur * 4;
+            const float4* n = innerBase + (size_t)cur * 4;
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
             float e0, e1;
             float lh = aabbHit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ro, inv, e0);
             float rh = aabbHit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ro, inv, e1);
-            if (cull) { if (e0 > t) lh = -1.0f; if (e1 > t) rh = -1.0f; }
+            if (CULL) { if (e0 > t) lh = -1.0f; if (e1 > t) rh = -1.0f; }
             const uint32_t lm = __float_as_uint(q3.x), rm = __float_as_uint(q3.y);
-            if (lh > 0.0f && rh > 0.0f)
+            const bool hl = lh > 0.0f, hr = rh > 0.0f;
+            if (hl && hr)
             {
-                uint32_t deferred;
-                if (lh > rh) { cur = rm; deferred = lm; } else { cur = lm; deferred = rm; }
-                stk.set(sp++, deferred);
-                continue;
+                const bool rightFirst = lh > rh;              // near child first; left on ties (closest_hit.glsl:181-190)
+                stk.push(rightFirst ? lm : rm);
+                cur = rightFirst ? rm : lm;
             }
-            else if (lh > 0.f) { cur = lm; continue; }
-            else if (rh > 0.f) { cur = rm; continue; }
+            else if (hl) cur = lm;
+            else if (hr) cur = rm;
+            else cur = stk.pop();
         }
-        else if (kind == PTB_K_LEAF)
+        const uint32_t kind = cur >> 30;
+        if (kind == PTB_K_LEAF)                               // closest_hit.glsl:118-153
         {
             const uint32_t first = cur & PTB_MAX_LEAF_SLOT, cnt = (cur >> 26) & 15u;
             for (uint32_t i = 0; i < cnt; i++)
@@ -263,7 +270,7 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
                 const float4* tp = S.tris + (size_t)(first + i) * 3;
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 const float3 v0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x);
-                // closest_hit.glsl:127-141 (Moeller-Trumbore, three IEEE divisions by det, no det==0 guard)
+                // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard)
                 float3 pv = xcross(rd, e1);
                 float det = xdot(e0, pv);
                 float3 tv = xsub(ro, v0);
@@ -282,13 +289,14 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
                     else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
                 }
             }
+            cur = stk.pop();
         }
-        else if (kind == PTB_K_INST)
+        else if (kind == PTB_K_INST)                          // closest_hit.glsl:154-172
         {
             curInst = (int)(cur & 0x3FFFFFFFu);
             const float4* ip = S.instTrav + (size_t)curInst * 4;
             const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-            // rTrans = inverse(transform) * (origin,1) / (direction,0)  (closest_hit.glsl:163-164); the inverse is precomputed at upload
+            // rTrans = inverse(transform) * (origin,1) / (direction,0); the inverse is precomputed at upload
             ro = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
                     xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
                     xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
@@ -296,20 +304,18 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
                     xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
                     xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
             inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
-            stk.set(sp++, PTB_META_NONE);           // marker (closest_hit.glsl:166-167)
-            cur = __float_as_uint(r0.w);            // BLAS root meta
+            stk.push(PTB_META_NONE);                          // marker: back to the TLAS when it is popped
+            cur = __float_as_uint(r0.w);                      // BLAS root meta
             inBlas = true;
-            continue;
         }
-        cur = stk.get(--sp);
-        if (inBlas && cur == PTB_META_NONE)         // closest_hit.glsl:208-216
+        else                                                  // sentinel / marker (closest_hit.glsl:206-216)
         {
+            if (!inBlas) break;
             inBlas = false;
-            cur = stk.get(--sp);
+            cur = stk.pop();
             ro = o; rd = d;
             inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
         }
-        if (cur == PTB_META_NONE) break;
     }
     if (!ANY) h.t = t;
     return false;

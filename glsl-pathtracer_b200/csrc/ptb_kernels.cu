@@ -47,13 +47,13 @@ __device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams
     float cx, cy;
     if (W.previewMode)
     {
-        cx = ((float)x + 0.5f) / (float)W.rw; cy = ((float)y + 0.5f) / (float)W.rh;     // TexCoords over the whole low-res target
+        cx = __fdiv_rn((float)x + 0.5f, (float)W.rw); cy = __fdiv_rn((float)y + 0.5f, (float)W.rh);     // TexCoords over the whole low-res target
         rng.init((uint32_t)x, (uint32_t)y, 1u);                                         // preview.glsl:43
     }
     else
     {
         int tx = x / F.tileW, ty = y / F.tileH, lx = x - tx * F.tileW, ly = y - ty * F.tileH;
-        float tcx = ((float)lx + 0.5f) / (float)F.tileW, tcy = ((float)ly + 0.5f) / (float)F.tileH;
+        float tcx = __fdiv_rn((float)lx + 0.5f, (float)F.tileW), tcy = __fdiv_rn((float)ly + 0.5f, (float)F.tileH);
         float offx = (float)tx * F.invNumTilesX, offy = (float)ty * F.invNumTilesY;        // Renderer.cpp:780
         // mix(tileOffset, tileOffset + invNumTiles, TexCoords)  (tile.glsl:43)
         cx = __fadd_rn(__fmul_rn(offx, __fsub_rn(1.0f, tcx)), __fmul_rn(__fadd_rn(offx, F.invNumTilesX), tcx));
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams
 {
     const uint32_t n = *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
-    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     const bool lights = OPT(F, O_LIGHTS);
     const bool cull = F.cullBoxes != 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->pathSegments, (unsigned long long)n);
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams
                 int depth = (int)(short)(__float_as_uint(d4.w) & 0xffffu);
                 if (depth >= lightsFromDepth) closestLights(S, o, d, t, h.light);     // OPT_HIDE_EMITTERS: lights only at depth > 0
             }
-            traverse<false, false>(S, o, d, t, cull, stk, h, NoAlpha());
+            if (cull) traverse<false, false, true>(S, o, d, t, stk, h, NoAlpha());
+            else traverse<false, false, false>(S, o, d, t, stk, h, NoAlpha());
             P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
             const int hi = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
             P.hitInst[p] = hi;
@@ -204,15 +205,55 @@ __global__ void k_sort_scan(uint32_t* hist, uint32_t* cursor, int numKeys)
     for (int k = lane * per; k < min(numKeys, (lane + 1) * per); k++) { uint32_t h = hist[k]; cursor[k] = run; run += h; hist[k] = 0; }
 }
 
-// Counting-sort scatter: queue entries -> key buckets (order inside a bucket follows the input order chunk-wise).
+// Counting-sort scatter: queue entries -> key buckets.  Each 256-thread block ranks a tile of 2048 entries in shared memory
+// (warp match + shared atomics) and reserves its bucket ranges with ONE global atomic per key per tile, so the popular keys
+// ("miss", the floor material) do not serialise on a single L2 address.
+constexpr int SORT_ITEMS = 8;
 __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
-                                                       uint32_t* cursor, uint32_t* __restrict__ sorted)
+                                                       uint32_t* cursor, uint32_t* __restrict__ sorted, int numKeys)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t* hist = sm; uint32_t* base = sm + numKeys;
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tileSize = 256u * SORT_ITEMS;
+    for (uint32_t tile = blockIdx.x * tileSize; tile < n; tile += gridDim.x * tileSize)
+    {
+        for (int k = threadIdx.x; k < numKeys; k += 256) hist[k] = 0;
+        __syncthreads();
+        uint32_t key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++)
+        {
+            const uint32_t i = tile + j * 256u + threadIdx.x;
+            key[j] = i < n ? keys[i] : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t off = 0;
+            if ((int)lane == leader && key[j] != 0xffffffffu) off = atomicAdd(&hist[key[j]], (uint32_t)__popc(peers));
+            rank[j] = __shfl_sync(0xffffffffu, off, leader) + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < numKeys; k += 256) { uint32_t c = hist[k]; if (c) base[k] = atomicAdd(&cursor[k], c); }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++)
+        {
+            const uint32_t i = tile + j * 256u + threadIdx.x;
+            if (key[j] != 0xffffffffu) sorted[base[key[j]] + rank[j]] = queue[i];
+        }
+        __syncthreads();
+    }
+}
+// Fallback for very large key ranges (more materials than fit the shared histogram): direct global atomics.
+__global__ void __launch_bounds__(256) k_sort_scatter_global(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ countPtr, uint32_t* cursor, uint32_t* __restrict__ sorted)
 {
     const uint32_t n = *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x)
+    for (uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; b0 < n; b0 += gridDim.x * blockDim.x)
     {
-        const uint32_t i = base + lane;
+        const uint32_t i = b0 + lane;
         const bool live = i < n;
         const uint32_t key = live ? keys[i] : 0xffffffffu;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -339,7 +380,7 @@ __device__ __noinline__ int closestFull(const DevScene& S, const FrameParams& F,
     float t = PTB_INF;
     ic.segs++;
     if (OPT(F, O_LIGHTS) && (!OPT(F, O_HIDE) || depthForLights > 0)) closestLights(S, ro, rd, t, h.light);
-    traverse<false, false>(S, ro, rd, t, F.cullBoxes != 0, stk, h, NoAlpha());
+    traverse<false, false, true>(S, ro, rd, t, stk, h, NoAlpha());
     if (h.t == PTB_INF) return 0;
     if (h.inst < 0) { sf.hitDist = h.t; sf.fhp = ro + rd * h.t; return 2; }
     int matID = __float_as_int(__ldg(S.instTrav + (size_t)h.inst * 4 + 1).w);
@@ -378,8 +419,8 @@ __device__ __noinline__ bool anyHitInline(const DevScene& S, const FrameParams& 
     if (OPT(F, O_LIGHTS) && anyLights(S, ro, rd, maxDist)) return true;
     LocalStack stk; HitRec h;
     if (OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM))
-        return traverse<true, true>(S, ro, rd, maxDist, F.cullBoxes != 0, stk, h, AlphaRng{&S, &rng});
-    return traverse<true, false>(S, ro, rd, maxDist, F.cullBoxes != 0, stk, h, NoAlpha());
+        return traverse<true, true, true>(S, ro, rd, maxDist, stk, h, AlphaRng{&S, &rng});
+    return traverse<true, false, true>(S, ro, rd, maxDist, stk, h, NoAlpha());
 }
 
 // EvalTransmittance (pathtrace.glsl:119-155)
@@ -719,7 +760,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, FrameParam
 {
     const uint32_t n = *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
-    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     const bool lights = OPT(F, O_LIGHTS);
     const bool alpha = OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM);
     const bool cull = F.cullBoxes != 0;
@@ -740,8 +781,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, FrameParam
             if (!occluded)
             {
                 HitRec h;
-                if (alpha) occluded = traverse<true, true>(S, o, d, maxDist, cull, stk, h, AlphaMask{&S});
-                else occluded = traverse<true, false>(S, o, d, maxDist, cull, stk, h, NoAlpha());
+                if (alpha) occluded = traverse<true, true, true>(S, o, d, maxDist, stk, h, AlphaMask{&S});
+                else if (cull) occluded = traverse<true, false, true>(S, o, d, maxDist, stk, h, NoAlpha());
+                else occluded = traverse<true, false, false>(S, o, d, maxDist, stk, h, NoAlpha());
             }
             if (!occluded)
             {
@@ -845,14 +887,15 @@ struct HitOut { float t; int kind, instance, matID, primSlot, triIDx; float bary
 
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(DevScene S, FrameParams F, const float* __restrict__ rays, long long n, int depth, HitOut* out)
 {
-    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     {
         const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
         HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
         float t = PTB_INF;
         if (OPT(F, O_LIGHTS) && (!OPT(F, O_HIDE) || depth > 0)) closestLights(S, o, d, t, h.light);
-        traverse<false, false>(S, o, d, t, F.cullBoxes != 0, stk, h, NoAlpha());
+        if (F.cullBoxes) traverse<false, false, true>(S, o, d, t, stk, h, NoAlpha());
+        else traverse<false, false, false>(S, o, d, t, stk, h, NoAlpha());
         HitOut r;
         r.t = h.t;
         if (h.t == PTB_INF) { r.kind = 0; r.instance = r.matID = r.primSlot = r.triIDx = r.lightIdx = -1; r.bary[0] = r.bary[1] = r.bary[2] = 0.f; }
@@ -869,12 +912,16 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(DevScene S, Frame
 
 __global__ void __launch_bounds__(TRACE_THREADS) k_any_batch(DevScene S, FrameParams F, const float* __restrict__ rays, const float* __restrict__ maxDist, long long n, int* out)
 {
-    SmemStack stk{g_stackSmem + threadIdx.x, (int)blockDim.x};
+    SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     {
         const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
         bool occ = OPT(F, O_LIGHTS) && anyLights(S, o, d, maxDist[i]);
-        if (!occ) { HitRec h; occ = traverse<true, false>(S, o, d, maxDist[i], F.cullBoxes != 0, stk, h, NoAlpha()); }
+        if (!occ)
+        {
+            HitRec h;
+            occ = F.cullBoxes ? traverse<true, false, true>(S, o, d, maxDist[i], stk, h, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, h, NoAlpha());
+        }
         out[i] = occ ? 1 : 0;
     }
 }
@@ -951,7 +998,8 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
                uint32_t* sorted)
 {
     k_sort_scan<<<1, 32, 0, st(c)>>>(hist, cursor, numKeys);
-    k_sort_scatter<<<c.numSMs * 8, 256, 0, st(c)>>>(queue, keys, countPtr, cursor, sorted);
+    if (numKeys <= 4096) k_sort_scatter<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, cursor, sorted, numKeys);
+    else k_sort_scatter_global<<<c.numSMs * 8, 256, 0, st(c)>>>(queue, keys, countPtr, cursor, sorted);
     g_launches += 2;
 }
 

@@ -160,7 +160,7 @@ int  ptb_set_profiling(PtbCtx* ctx, int32_t enable);
 int  ptb_set_stream(PtbCtx* ctx, void* cudaStream);
 int  ptb_synchronize(PtbCtx* ctx);
 /* B200 tuning knob (no reference counterpart): skip child boxes whose entry distance exceeds the current hit distance.
- * Visiting order of the remaining nodes is unchanged, so hits are identical (checked by tests); default off. */
+ * Visiting order of the remaining nodes is unchanged, so hits are identical (checked by tests); default on. */
 int  ptb_set_cull(PtbCtx* ctx, int32_t enable);
 
 /* Parity entry points: run the production traversal / BSDF device code on caller-provided inputs.

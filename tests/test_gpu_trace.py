@@ -54,8 +54,10 @@ def test_primary_rays_match_oracle(name, oracle_mod):
     rays_o = orc.camera_rays(1)
     rays_g = ctx.camera_rays(1)
     assert np.array_equal(rays_o.view(np.uint32), rays_g.view(np.uint32)), "pinhole primary rays must be bit-identical"
-    for depth in (0, 1):
-        assert_hits_equal(ctx.trace_closest(rays_o, depth), orc.trace_closest(rays_o, depth))
+    for cull in (False, True):                       # reference-faithful traversal and the default culled one
+        ctx.set_cull(cull)
+        for depth in (0, 1):
+            assert_hits_equal(ctx.trace_closest(rays_o, depth), orc.trace_closest(rays_o, depth))
     ctx.close(); orc.close()
 
 
@@ -65,6 +67,9 @@ def test_random_and_bounce_rays_match_oracle(name, oracle_mod):
     ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
     rays = random_rays(sc, 200_000, 7)
     h_o = orc.trace_closest(rays, 1)
+    ctx.set_cull(False)
+    assert_hits_equal(ctx.trace_closest(rays, 1), h_o)
+    ctx.set_cull(True)
     assert_hits_equal(ctx.trace_closest(rays, 1), h_o)
     # bounce-like rays: start on the surfaces found above, cosine-ish random directions
     hit = h_o["kind"] == 1
