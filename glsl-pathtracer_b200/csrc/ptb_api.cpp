@@ -120,7 +120,8 @@ struct PtbCtx
     DevBuf<uint4> rng;
     DevBuf<int> hitInst;
     DevBuf<float2> prevUV;
-    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist;
+    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, shKey, shPerm, shHist;
+    int shadowSort = 0;        // (experiment, default off) sort light-NEE shadow rays by light index; measured slower, see DESIGN.md
     int sortMode = 1;          // 0 off, 1 sort bounces >= 1, 2 sort every bounce
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
@@ -346,7 +347,7 @@ int ensureWaveState(PtbCtx* c, size_t slots)
         c->stateGeneral = true;
     }
     CK(c->counters.alloc((size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE));
-    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n));
+    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n)); CK(c->shKey.alloc(n)); CK(c->shPerm.alloc(n));
     c->slotCap = n;
     return PTB_OK;
 }
@@ -357,6 +358,7 @@ PathState pathState(PtbCtx* c)
     P.rayO = c->rayO.p; P.rayD = c->rayD.p; P.thr = c->thr.p; P.rad = c->rad.p; P.rng = c->rng.p; P.hit = c->hit.p; P.hitInst = c->hitInst.p;
     P.med = c->med.p; P.medCol = c->medCol.p; P.prevUV = c->prevUV.p;
     for (int k = 0; k < 2; k++) { P.shO[k] = c->shO[k].p; P.shD[k] = c->shD[k].p; P.shC[k] = c->shC[k].p; P.queue[k] = c->queue[k].p; }
+    P.shKey = (c->shadowSort && c->S.numLights > 1 && c->S.numLights <= 4096) ? c->shKey.p : nullptr;
     return P;
 }
 
@@ -383,6 +385,11 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
     const int numKeys = c->S.numMaterials + 2;
     CK(c->sortHist.alloc((size_t)numKeys * 2));
     CK(cudaMemsetAsync(c->sortHist.p, 0, (size_t)numKeys * 2 * sizeof(uint32_t), c->stream));
+    if (P.shKey)
+    {
+        CK(c->shHist.alloc((size_t)c->S.numLights * 2));
+        CK(cudaMemsetAsync(c->shHist.p, 0, (size_t)c->S.numLights * 2 * sizeof(uint32_t), c->stream));
+    }
     ptbk_camera(L, c->S, F, W, P, ctr);
     const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
     const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
@@ -407,9 +414,17 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
         if (!F.inlineShadow)
         {
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
-                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
+                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p, nullptr);
             if (F.features & PTB_OPT_LIGHTS)
-                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p);
+            {
+                const uint32_t* perm = nullptr;
+                if (P.shKey && it <= c->shadowSort - 1 + 0)
+                {   // rays towards the same light from neighbouring pixels traverse the same nodes
+                    ptbk_sort_keys(L, P.shKey, ci + CTR_NSHB, c->shHist.p, c->shHist.p + c->S.numLights, c->S.numLights, c->shPerm.p);
+                    perm = c->shPerm.p;
+                }
+                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p, perm);
+            }
         }
         it++;
         if (it >= PTB_MAX_ITERS) break;                       // alpha-skip re-traces are unbounded in the reference (Q7); hard stop
@@ -528,6 +543,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     CK(cudaStreamSynchronize(s));
     c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
+    if (const char* e = getenv("PTB_SHADOW_SORT")) c->shadowSort = atoi(e);   // 0 off, k: sort the shadow rays of the first k bounces
     *out = c;
     return PTB_OK;
 }
@@ -542,7 +558,7 @@ int ptb_destroy(PtbCtx* c)
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
     c->rayO.release(); c->rayD.release(); c->thr.release(); c->rad.release(); c->hit.release(); c->med.release(); c->medCol.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
-    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release();
+    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->shKey.release(); c->shPerm.release(); c->shHist.release();
     c->rng.release(); c->hitInst.release(); c->prevUV.release(); c->counters.release(); c->dstats.release();
     for (auto e : c->traceEvents) cudaEventDestroy(e);
     if (c->evStart) cudaEventDestroy(c->evStart);

@@ -225,22 +225,35 @@ struct NoAlpha { };
 // reference's, so primitive/instance IDs and t are identical to a host traversal of the canonical array.
 // Control flow is "while-while": every lane keeps descending internal nodes until it holds a leaf / instance / sentinel, then
 // the warp processes those together — incoherent warps spend fewer issue slots with most lanes masked off.
-// ANY: return true at the first accepted hit with t < tmax.  alphaFn(slot, inst, u, v) -> accept? (only when ALPHA)
-template <bool ANY, bool ALPHA, bool CULL, class Stack, class AlphaFn>
-__device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, float tmax, Stack& stk, HitRec& h, AlphaFn alphaFn)
+// The traversal is a resumable per-lane state machine (Trav) so the wavefront kernels can hand a finished lane a new ray
+// while its neighbours are still traversing.
+// ANY: finish at the first accepted hit with t < tmax.  alphaFn(slot, inst, u, v) -> accept? (only when ALPHA)
+template <bool ANY, bool ALPHA, bool CULL>
+struct Trav
 {
-    float t = tmax;
-    stk.reset();                                              // an any-hit early return leaves entries behind
-    stk.push(PTB_META_NONE);
-    uint32_t cur = S.rootMeta;
-    bool inBlas = false;
-    int curInst = -1;
-    float3 ro = o, rd = d;
-    float3 inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
-    const float4* __restrict__ innerBase = S.inner;
+    float3 o, d, ro, rd, inv;
+    float t;
+    uint32_t cur;
+    int curInst;
+    bool inBlas;
+    bool occluded;      // ANY result
+    HitRec h;           // closest result (t filled by finish())
 
-    while (true)
+    template <class Stack>
+    __device__ __forceinline__ void begin(const DevScene& S, float3 o_, float3 d_, float tmax, Stack& stk)
     {
+        o = o_; d = d_; ro = o_; rd = d_;
+        inv = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z));
+        t = tmax; cur = S.rootMeta; curInst = -1; inBlas = false; occluded = false;
+        stk.reset();
+        stk.push(PTB_META_NONE);
+    }
+
+    // One round: descend to the next non-internal item and process it.  Returns true when the traversal is finished.
+    template <class Stack, class AlphaFn>
+    __device__ __forceinline__ bool round(const DevScene& S, Stack& stk, AlphaFn alphaFn)
+    {
+        const float4* __restrict__ innerBase = S.inner;
         while (cur < (1u << 30))                              // PTB_K_INNER: closest_hit.glsl:173-205
         {
             const float4* n = innerBase + (size_t)cur * 4;
@@ -283,8 +296,8 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
                 {
                     if constexpr (ANY)
                     {
-                        if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) return true; }
-                        else return true;
+                        if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) { occluded = true; return true; } }
+                        else { occluded = true; return true; }
                     }
                     else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
                 }
@@ -310,15 +323,25 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
         }
         else                                                  // sentinel / marker (closest_hit.glsl:206-216)
         {
-            if (!inBlas) break;
+            if (!inBlas) { h.t = t; return true; }
             inBlas = false;
             cur = stk.pop();
             ro = o; rd = d;
             inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
         }
+        return false;
     }
-    if (!ANY) h.t = t;
-    return false;
+};
+
+template <bool ANY, bool ALPHA, bool CULL, class Stack, class AlphaFn>
+__device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, float tmax, Stack& stk, HitRec& h, AlphaFn alphaFn)
+{
+    Trav<ANY, ALPHA, CULL> tr;
+    tr.h = h;
+    tr.begin(S, o, d, tmax, stk);
+    while (!tr.round(S, stk, alphaFn)) { }
+    if (!ANY) h = tr.h;
+    return tr.occluded;
 }
 
 // ------------------------------------------------------------------ sampling.glsl -------------------------------
