@@ -1,0 +1,160 @@
+"""The oracle itself is pinned where the reference offers something to pin it to: the flattened BVH (test_fixtures.py), a
+brute-force traversal, known-answer vectors of the RNG and the tone mapper computed independently in numpy, analytic
+properties of the BSDF/light sampling, and a committed golden render that guards against drift."""
+import os
+import numpy as np
+import pytest
+from conftest import scene_at, load_scene_cached, rel_mse
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def pcg4d_py(v):
+    M = 0xFFFFFFFF
+    v = [(x * 1664525 + 1013904223) & M for x in v]
+    v[0] = (v[0] + v[1] * v[3]) & M; v[1] = (v[1] + v[2] * v[0]) & M; v[2] = (v[2] + v[0] * v[1]) & M; v[3] = (v[3] + v[1] * v[2]) & M
+    v = [x ^ (x >> 16) for x in v]
+    v[0] = (v[0] + v[1] * v[3]) & M; v[1] = (v[1] + v[2] * v[0]) & M; v[2] = (v[2] + v[0] * v[1]) & M; v[3] = (v[3] + v[1] * v[2]) & M
+    return v
+
+
+def test_camera_rays_follow_tile_glsl(oracle_mod):
+    """tile.glsl:41-68 re-derived in numpy float32 for a few pixels, including the pcg4d seeding with tile-local coordinates."""
+    sc = scene_at("cornell_box_orig", 96, 64, 40, 24)        # over-hanging tiles
+    orc = oracle_mod.Oracle(sc)
+    rays = orc.camera_rays(3).reshape(64, 96, 6)
+    f32 = np.float32
+    cam = sc.camera
+    ntx, nty = 3, 3
+    for (x, y) in [(0, 0), (95, 63), (41, 25), (79, 47), (13, 60)]:
+        tx, ty, lx, ly = x // 40, y // 24, x % 40, y % 24
+        frame = 2 + (3 - 1) * ntx * nty + (nty - 1 - ty) * ntx + tx
+        seed = [lx, ly, frame, lx + ly]
+        rs = []
+        for _ in range(4):
+            seed = pcg4d_py(seed); rs.append(f32(seed[0]) / f32(4294967296.0))
+        inv = (f32(40) / f32(96), f32(24) / f32(64))
+        tc = ((f32(lx) + f32(0.5)) / f32(40), (f32(ly) + f32(0.5)) / f32(24))
+        off = (f32(tx) * inv[0], f32(ty) * inv[1])
+        c = [off[i] * (f32(1) - tc[i]) + (off[i] + inv[i]) * tc[i] for i in range(2)]
+        r = [f32(2) * rs[0], f32(2) * rs[1]]
+        j = [np.sqrt(v) - f32(1) if v < 1 else f32(1) - np.sqrt(f32(2) - v) for v in r]
+        j = [j[0] / (f32(96) * f32(0.5)), j[1] / (f32(64) * f32(0.5))]
+        d = [(c[i] * f32(2) - f32(1)) + j[i] for i in range(2)]
+        scale = f32(np.tan(np.float64(f32(cam.fov) * f32(0.5))))
+        d[1] = d[1] * (f32(64) / f32(96) * scale); d[0] = d[0] * scale
+        v = d[0] * cam.right + d[1] * cam.up + cam.forward
+        v = v / np.sqrt(np.dot(v, v))
+        np.testing.assert_allclose(rays[y, x, 3:], v, rtol=0, atol=2e-6)
+        np.testing.assert_array_equal(rays[y, x, :3], cam.position)
+    orc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_box_orig", "cornell_box_sphere", "volume_cube", "hyperion_sphere_light"])
+def test_bvh_traversal_equals_brute_force(name, oracle_mod):
+    """The restated stack traversal finds the same nearest hit as testing every instance x triangle (and light) directly."""
+    sc = scene_at(name, 48, 32, 24, 16)
+    orc = oracle_mod.Oracle(sc)
+    rays = orc.camera_rays(1)
+    if name.startswith("hyperion"):
+        rays = rays[::7]                     # brute force over 107k triangles per ray
+    a, b = orc.trace_closest(rays, 1), orc.trace_closest(rays, 1, brute=True)
+    assert np.array_equal(a["kind"], b["kind"])
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    same = a["primSlot"] == b["primSlot"]
+    assert same.mean() > 0.999          # exact ties between coincident triangles may resolve to another slot in brute-force order
+    orc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_box_sphere", "hyperion_rect_lights"])
+def test_culled_traversal_gives_identical_hits(name, oracle_mod):
+    sc = scene_at(name, 160, 90, 80, 45)
+    a = oracle_mod.Oracle(sc, cull=False); b = oracle_mod.Oracle(sc, cull=True)
+    rays = a.camera_rays(1)
+    ha, hb = a.trace_closest(rays, 1), b.trace_closest(rays, 1)
+    assert ha.tobytes() == hb.tobytes()
+    assert b.stats()["nodeVisits"] < a.stats()["nodeVisits"]
+    a.close(); b.close()
+
+
+def test_tonemap_matches_numpy(oracle_mod):
+    sc = load_scene_cached("cornell_box_orig")
+    rng = np.random.default_rng(3)
+    acc = (rng.random((16, 24, 4), dtype=np.float32) * 12).astype(np.float32); acc[..., 3] = 4
+    out = oracle_mod.tonemap(acc, np.float32(0.25), sc.renderOptions)
+    c = acc[..., :3].astype(np.float64) * 0.25
+    lum = 0.212671 * c[..., 0] + 0.715160 * c[..., 1] + 0.072169 * c[..., 2]
+    ref = np.clip(c / (1.0 + lum[..., None] / 1.5), 0, None) ** (1 / 2.2)
+    ref8 = np.floor(np.clip(ref, 0, 1) * 255 + 0.5)
+    assert np.abs(out[..., :3].astype(np.float64) - ref8).max() <= 1 and (out[..., 3] == 255).all()
+
+
+def bsdf_state(oracle_mod, mat, n, seed):
+    rng = np.random.default_rng(seed)
+    q = np.zeros(n, oracle_mod.BSDF_QUERY_DTYPE)
+    q["mat"] = mat; q["N"] = (0, 0, 1)
+    th = np.arccos(rng.random(n) * 0.98 + 0.01); ph = rng.random(n) * 2 * np.pi
+    q["V"] = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], 1)
+    q["eta"] = 1.0 / mat[17]
+    q["r1"], q["r2"], q["r3"] = rng.random(n), rng.random(n), rng.random(n)
+    return q
+
+
+def test_bsdf_sample_is_consistent_with_eval(oracle_mod):
+    """DisneySample returns DisneyEval of the sampled direction (disney.glsl:238-241)."""
+    orc = oracle_mod.Oracle(scene_at("cornell_box_orig", 16, 16, 8, 8))
+    for name in ("hyperion_rect_lights", "hyperion_sphere_light"):
+        for m in load_scene_cached(name).materials:
+            q = bsdf_state(oracle_mod, m, 300, 5)
+            s = orc.bsdf(q, sample=True)
+            q2 = q.copy(); q2["L"] = s["L"]
+            e = orc.bsdf(q2)
+            ok = np.isfinite(s["pdf"]) & (s["pdf"] > 0) & (s["pdf"] < 1e3)      # near-delta lobes amplify the world<->local round trip
+            np.testing.assert_allclose(e["pdf"][ok], s["pdf"][ok], rtol=5e-3)
+            np.testing.assert_allclose(e["f"][ok], s["f"][ok], rtol=5e-3, atol=1e-6)
+    orc.close()
+
+
+def test_diffuse_bsdf_is_energy_bounded_and_pdf_normalised(oracle_mod):
+    """White rough dielectric (the loader's default material, Material.h:50-85): E[f/pdf] ~ 1 and the mixture pdf integrates to its
+    lobe probability (Monte-Carlo over uniform directions)."""
+    orc = oracle_mod.Oracle(scene_at("cornell_box_orig", 16, 16, 8, 8))
+    m = load_scene_cached("cornell_box_orig").materials[0].copy()
+    q = bsdf_state(oracle_mod, m, 40000, 9)
+    q["V"] = (0.3, 0.1, np.sqrt(1 - 0.1))
+    s = orc.bsdf(q, sample=True)
+    ok = s["pdf"] > 0
+    w = np.where(ok[:, None], s["f"] / np.maximum(s["pdf"], 1e-20)[:, None], 0)
+    # the Disney diffuse + specular sum is known not to be strictly energy conserving (a few % above 1 for white base colour)
+    assert 0.9 < w.mean() <= 1.08
+    # integral of pdf over the sphere ~ 1
+    rng = np.random.default_rng(1)
+    z = rng.random(40000) * 2 - 1; ph = rng.random(40000) * 2 * np.pi; r = np.sqrt(1 - z * z)
+    q["L"] = np.stack([r * np.cos(ph), r * np.sin(ph), z], 1)
+    e = orc.bsdf(q)
+    assert abs(e["pdf"].mean() * 4 * np.pi - 1.0) < 0.05
+    orc.close()
+
+
+def test_render_matches_committed_golden(oracle_mod):
+    """Guards the oracle against drift: 48x32 renders of three scenes committed under tests/golden (tests/golden/make_golden.py)."""
+    for name, depth in (("cornell_box_orig", 3), ("hyperion_rect_lights", None), ("volume_cube", None)):
+        sc = scene_at(name, 48, 32, 24, 16, depth)
+        orc = oracle_mod.Oracle(sc)
+        acc = orc.render(1, 4)
+        ref = np.load(os.path.join(GOLDEN, f"oracle_{name}_48x32_4spp.npy"))
+        # libm differences between hosts may flip a handful of discrete decisions; the image must stay the same
+        assert rel_mse(ref, acc) < 1e-3
+        assert np.isclose(acc, ref, rtol=1e-3, atol=1e-4).all(axis=-1).mean() > 0.97
+        orc.close()
+
+
+def test_tile_schedule_equals_full_frame(oracle_mod):
+    sc = scene_at("volume_cube", 50, 34, 24, 16)
+    orc = oracle_mod.Oracle(sc)
+    acc = np.zeros((34, 50, 4), np.float32)
+    ntx, nty = 3, 3
+    for j in range(ntx * nty):
+        orc.render_tile(j % ntx, nty - 1 - j // ntx, 2 + j, acc)
+    assert acc.tobytes() == orc.render(1, 1).tobytes()
+    orc.close()
