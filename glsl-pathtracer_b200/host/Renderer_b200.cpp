@@ -1,0 +1,259 @@
+// Renderer_b200.cpp — drop-in replacement for the reference's src/core/Renderer.cpp.
+//
+// It implements the class `GLSLPT::Renderer` exactly as DECLARED by the reference's own, unmodified src/core/Renderer.h
+// (Renderer.h:104-185): same constructor, same public methods, same state machine.  Only the body changes: the OpenGL texture
+// uploads, FBOs, GLSL compilation and the three draws per tile are replaced by calls into libptb200.so (include/ptb200.h).
+// A maintainer swaps this file for Renderer.cpp and links -lptb200 instead of OpenGL/OIDN; Scene, the loaders, RadeonRays and
+// Main.cpp's call sites (Main.cpp:160,168,177,180,212,289,308,520) compile unchanged.
+//
+// The GL handle members of the class stay zero.  State the reference class has no member for (the PtbCtx, the tonemap uniform,
+// the completed image) lives in a side table keyed by `this`.
+#include "Config.h"
+#include "Renderer.h"
+#include "Scene.h"
+#include "Camera.h"
+#include "ptb200.h"
+#include "RendererB200Ext.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <vector>
+
+namespace GLSLPT
+{
+    namespace
+    {
+        struct Side
+        {
+            PtbCtx* ctx = nullptr;
+            float invSampleCounter = 1.0f;                 // tonemap uniform (Renderer.cpp:806)
+            std::vector<unsigned char> completed;          // tileOutputTexture[1 - currentBuffer]
+            std::vector<float> preview;                    // pathTraceTextureLowRes
+            int samplesPerWave = 0;
+        };
+        std::map<const Renderer*, Side>& table() { static std::map<const Renderer*, Side> t; return t; }
+
+        void check(int rc, const char* what)
+        {
+            if (rc != PTB_OK)
+            {   // the reference throws std::runtime_error on shader failures (Shader.cpp:54-55); same convention for device failures
+                printf("%s failed: %s\n", what, ptb_last_error());
+                throw std::runtime_error(std::string(what) + ": " + ptb_last_error());
+            }
+        }
+
+        PtbSceneDesc describe(Scene* s)
+        {   // the arrays InitGPUDataBuffers uploads (Renderer.cpp:135-249)
+            PtbSceneDesc d; memset(&d, 0, sizeof(d));
+            d.nodes = (const float*)s->bvhTranslator.nodes.data(); d.numNodes = (int)s->bvhTranslator.nodes.size();
+            d.topLevelIndex = s->bvhTranslator.topLevelIndex;
+            d.vertIndices = (const int32_t*)s->vertIndices.data(); d.numIndices = (int)s->vertIndices.size();
+            d.verticesUVX = (const float*)s->verticesUVX.data(); d.numVertices = (int)s->verticesUVX.size();
+            d.normalsUVY = (const float*)s->normalsUVY.data();
+            d.materials = (const float*)s->materials.data(); d.numMaterials = (int)s->materials.size();
+            d.transforms = (const float*)s->transforms.data(); d.numInstances = (int)s->transforms.size();
+            d.lights = s->lights.empty() ? nullptr : (const float*)s->lights.data(); d.numLights = (int)s->lights.size();
+            d.textures = s->textures.empty() ? nullptr : s->textureMapsArray.data(); d.numTextures = (int)s->textures.size();
+            d.texW = s->renderOptions.texArrayWidth; d.texH = s->renderOptions.texArrayHeight;
+            if (s->envMap) { d.envImg = s->envMap->img; d.envCdf = s->envMap->cdf; d.envW = s->envMap->width; d.envH = s->envMap->height; d.envTotalSum = s->envMap->totalSum; }
+            return d;
+        }
+
+        PtbOptions options(Scene* s, int samplesPerWave)
+        {   // the #defines of InitShaders (Renderer.cpp:401-459) and the uniforms of Update (Renderer.cpp:776-782, 806-810)
+            const RenderOptions& ro = s->renderOptions;
+            PtbOptions o; memset(&o, 0, sizeof(o));
+            o.renderW = ro.renderResolution.x; o.renderH = ro.renderResolution.y; o.tileW = ro.tileWidth; o.tileH = ro.tileHeight;
+            o.maxDepth = ro.maxDepth; o.rrDepth = ro.RRDepth;
+            uint32_t bools = (ro.enableEnvMap ? 1u : 0u) | (ro.enableRR ? 2u : 0u) | (ro.enableUniformLight ? 4u : 0u) | (ro.openglNormalMap ? 8u : 0u) |
+                             (ro.hideEmitters ? 16u : 0u) | (ro.enableBackground ? 32u : 0u) | (ro.transparentBackground ? 64u : 0u) |
+                             (ro.enableRoughnessMollification ? 128u : 0u) | (ro.enableVolumeMIS ? 256u : 0u);
+            PtbSceneDesc d = describe(s);
+            o.features = ptb_derive_features(&d, bools);
+            o.envMapIntensity = ro.envMapIntensity; o.envMapRot = ro.envMapRot; o.roughnessMollificationAmt = ro.roughnessMollificationAmt;
+            o.uniformLightCol[0] = ro.uniformLightCol.x; o.uniformLightCol[1] = ro.uniformLightCol.y; o.uniformLightCol[2] = ro.uniformLightCol.z;
+            o.backgroundCol[0] = ro.backgroundCol.x; o.backgroundCol[1] = ro.backgroundCol.y; o.backgroundCol[2] = ro.backgroundCol.z;
+            o.enableTonemap = ro.enableTonemap; o.enableAces = ro.enableAces; o.simpleAcesFit = ro.simpleAcesFit;
+            o.samplesPerWave = samplesPerWave;
+            return o;
+        }
+
+        PtbCamera camera(Scene* s)
+        {   // camera.* uniforms (Renderer.cpp:769-775)
+            Camera* c = s->camera;
+            PtbCamera p;
+            p.position[0] = c->position.x; p.position[1] = c->position.y; p.position[2] = c->position.z;
+            p.right[0] = c->right.x; p.right[1] = c->right.y; p.right[2] = c->right.z;
+            p.up[0] = c->up.x; p.up[1] = c->up.y; p.up[2] = c->up.z;
+            p.forward[0] = c->forward.x; p.forward[1] = c->forward.y; p.forward[2] = c->forward.z;
+            p.fov = c->fov; p.focalDist = c->focalDist; p.aperture = c->aperture;
+            return p;
+        }
+    }
+
+    Renderer::Renderer(Scene* scene, const std::string& shadersDirectory)
+        : scene(scene), quad(nullptr), BVHBuffer(0), BVHTex(0), vertexIndicesBuffer(0), vertexIndicesTex(0), verticesBuffer(0), verticesTex(0),
+          normalsBuffer(0), normalsTex(0), materialsTex(0), transformsTex(0), lightsTex(0), textureMapsArrayTex(0), envMapTex(0), envMapCDFTex(0),
+          pathTraceFBO(0), pathTraceFBOLowRes(0), accumFBO(0), outputFBO(0), shadersDirectory(shadersDirectory), pathTraceShader(nullptr),
+          pathTraceShaderLowRes(nullptr), outputShader(nullptr), tonemapShader(nullptr), pathTraceTextureLowRes(0), pathTraceTexture(0), accumTexture(0),
+          tileOutputTexture(), denoisedTexture(0), denoiserInputFramePtr(nullptr), frameOutputPtr(nullptr), denoised(false), initialized(false)
+    {
+        if (scene == nullptr)
+        {
+            printf("No Scene Found\n");                      // Renderer.cpp:72-76
+            return;
+        }
+        if (!scene->initialized)
+            scene->ProcessScene();                           // Renderer.cpp:78-79
+
+        Side& sd = table()[this];
+        PtbSceneDesc d = describe(scene);                    // InitGPUDataBuffers
+        PtbOptions o = options(scene, sd.samplesPerWave);    // InitShaders: feature selection instead of GLSL compilation
+        check(ptb_create(&d, &o, 0, &sd.ctx), "ptb_create");
+        pixelRatio = 0.25f;
+        InitFBOs();
+        initialized = true;
+    }
+
+    Renderer::~Renderer()
+    {
+        auto it = table().find(this);
+        if (it != table().end()) { ptb_destroy(it->second.ctx); table().erase(it); }
+    }
+
+    void Renderer::InitGPUDataBuffers() {}                   // done by ptb_create
+    void Renderer::InitShaders() { ReloadShaders(); }
+
+    void Renderer::InitFBOs()
+    {   // counters and tile grid of Renderer.cpp:281-300; the buffers themselves live in the PtbCtx
+        sampleCounter = 1; currentBuffer = 0; frameCounter = 1;
+        renderSize = scene->renderOptions.renderResolution; windowSize = scene->renderOptions.windowResolution;
+        tileWidth = scene->renderOptions.tileWidth; tileHeight = scene->renderOptions.tileHeight;
+        invNumTiles.x = (float)tileWidth / renderSize.x; invNumTiles.y = (float)tileHeight / renderSize.y;
+        numTiles.x = ceil((float)renderSize.x / tileWidth); numTiles.y = ceil((float)renderSize.y / tileHeight);
+        tile.x = -1; tile.y = numTiles.y - 1;
+        Side& sd = table()[this];
+        sd.completed.assign((size_t)renderSize.x * renderSize.y * 4, 0);
+        sd.invSampleCounter = 1.0f;
+        printf("Window Resolution : %d %d\n", windowSize.x, windowSize.y);
+        printf("Render Resolution : %d %d\n", renderSize.x, renderSize.y);
+        printf("Preview Resolution : %d %d\n", (int)((float)windowSize.x * pixelRatio), (int)((float)windowSize.y * pixelRatio));
+        printf("Tile Size : %d %d\n", tileWidth, tileHeight);
+    }
+
+    void Renderer::ResizeRenderer()
+    {   // Renderer.cpp:251-279
+        Side& sd = table()[this];
+        PtbOptions o = options(scene, sd.samplesPerWave);
+        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
+        check(ptb_resize(sd.ctx, o.renderW, o.renderH, o.tileW, o.tileH), "ptb_resize");
+        InitFBOs();
+    }
+
+    void Renderer::ReloadShaders()
+    {   // Renderer.cpp:381-390: re-derive the OPT_* set
+        Side& sd = table()[this];
+        PtbOptions o = options(scene, sd.samplesPerWave);
+        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
+    }
+
+    void Renderer::Render()
+    {   // Renderer.cpp:546-590
+        if (!scene->dirty && scene->renderOptions.maxSpp != -1 && sampleCounter >= scene->renderOptions.maxSpp)
+            return;
+        Side& sd = table()[this];
+        if (scene->dirty)
+        {
+            int w = (int)(windowSize.x * pixelRatio), h = (int)(windowSize.y * pixelRatio);
+            sd.preview.resize((size_t)w * h * 4);
+            check(ptb_render_preview(sd.ctx, w, h, sd.preview.data()), "ptb_render_preview");
+            scene->instancesModified = false;
+            scene->dirty = false;
+            scene->envMapModified = false;
+        }
+        else
+            check(ptb_render_tile(sd.ctx, tile.x, tile.y, frameCounter), "ptb_render_tile");
+    }
+
+    void Renderer::Present() {}                              // Renderer.cpp:592-611 draws to the window: nothing to do headless
+
+    float Renderer::GetProgress()
+    {
+        int maxSpp = scene->renderOptions.maxSpp;
+        return maxSpp <= 0 ? 0.0f : sampleCounter * 100.0f / maxSpp;
+    }
+
+    void Renderer::GetOutputBuffer(unsigned char** data, int& w, int& h)
+    {   // Renderer.cpp:619-634: caller delete[]s
+        w = renderSize.x; h = renderSize.y;
+        *data = new unsigned char[w * h * 4];
+        Side& sd = table()[this];
+        memcpy(*data, sd.completed.data(), (size_t)w * h * 4);
+    }
+
+    int Renderer::GetSampleCount() { return sampleCounter; }
+
+    void Renderer::Update(float secondsElapsed)
+    {   // Renderer.cpp:641-812
+        (void)secondsElapsed;
+        if (!scene->dirty && scene->renderOptions.maxSpp != -1 && sampleCounter >= scene->renderOptions.maxSpp)
+            return;
+        Side& sd = table()[this];
+        if (scene->instancesModified)
+        {
+            int top = scene->bvhTranslator.topLevelIndex;
+            check(ptb_update_instances(sd.ctx, (const float*)scene->transforms.data(), (int)scene->transforms.size(), (const float*)scene->materials.data(),
+                                       (int)scene->materials.size(), (const float*)&scene->bvhTranslator.nodes[top],
+                                       (int)scene->bvhTranslator.nodes.size() - top), "ptb_update_instances");
+        }
+        if (scene->envMapModified && scene->envMap != nullptr)
+            check(ptb_update_envmap(sd.ctx, scene->envMap->img, scene->envMap->cdf, scene->envMap->width, scene->envMap->height, scene->envMap->totalSum),
+                  "ptb_update_envmap");
+        denoised = false;                                    // OIDN (Renderer.cpp:695-730) stays out of the hot path
+        if (scene->dirty)
+        {
+            tile.x = -1; tile.y = numTiles.y - 1;
+            sampleCounter = 1; denoised = false; frameCounter = 1;
+            check(ptb_reset_accum(sd.ctx), "ptb_reset_accum");
+        }
+        else
+        {
+            frameCounter++;
+            tile.x++;
+            if (tile.x >= numTiles.x)
+            {
+                tile.x = 0;
+                tile.y--;
+                if (tile.y < 0)
+                {
+                    tile.x = 0;
+                    tile.y = numTiles.y - 1;
+                    // the buffer tonemapped with the finished pass's uniform becomes the displayed one (Renderer.cpp:584-588,758)
+                    check(ptb_read_output_rgba8(sd.ctx, sd.invSampleCounter, sd.completed.data()), "ptb_read_output_rgba8");
+                    sampleCounter++;
+                    currentBuffer = 1 - currentBuffer;
+                }
+            }
+        }
+        PtbCamera cam = camera(scene);
+        check(ptb_set_camera(sd.ctx, &cam), "ptb_set_camera");
+        PtbOptions o = options(scene, sd.samplesPerWave);
+        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
+        sd.invSampleCounter = 1.0f / (sampleCounter);
+    }
+
+    // ---- extension (RendererB200Ext.h): whole-frame passes with the seeds of the tile schedule -----------------------
+    void RenderSamplesB200(Renderer& r, Scene* scene, int n)
+    {
+        Side& sd = table()[&r];
+        PtbCamera cam = camera(scene);
+        check(ptb_set_camera(sd.ctx, &cam), "ptb_set_camera");
+        int first = r.GetSampleCount();
+        check(ptb_render_samples(sd.ctx, first, n, 1), "ptb_render_samples");
+        RendererB200Access::advance(r, n);
+        check(ptb_read_output_rgba8(sd.ctx, 1.0f / (float)(first + n - 1), sd.completed.data()), "ptb_read_output_rgba8");
+    }
+    PtbCtx* ContextOfB200(Renderer& r) { return table()[&r].ctx; }
+}
