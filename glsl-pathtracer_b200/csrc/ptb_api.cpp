@@ -103,7 +103,7 @@ struct PtbCtx
 
     DevBuf<float> nodes, lights, envImg, envCdf;
     DevBuf<int> vertIndices;
-    DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre;
+    DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
     DevScene S{};
 
@@ -305,9 +305,38 @@ int buildLightsPre(PtbCtx* c, const float* lights, int n)
         lp[i * 8 + 6] = make_float4(v[0] * sv, v[1] * sv, v[2] * sv, 0.f);
         lp[i * 8 + 7] = make_float4(0, 0, 0, 0);
     }
+    // groups of consecutive quads on one plane (+ singleton groups for everything else), with padded bounds of the member quads
+    std::vector<float4> groups;
+    for (int i = 0; i < n;)
+    {
+        int j = i + 1;
+        const bool quad = lp[i * 8 + 0].w == 0.f;
+        if (quad) while (j < n && lp[j * 8 + 3].w == 1.f) j++;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, mag = 1e-3;
+        for (int k = i; k < j && quad; k++)
+        {
+            const float* p = lights + (size_t)k * 15;
+            for (int cu = 0; cu < 2; cu++) for (int cv = 0; cv < 2; cv++) for (int a = 0; a < 3; a++)
+            {
+                double v = (double)p[a] + cu * (double)p[6 + a] + cv * (double)p[9 + a];
+                lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); mag = std::max(mag, fabs(v));
+            }
+        }
+        double ext = quad ? std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]}) : 0.0;
+        double pad = 1e-4 * (1.0 + mag + ext);
+        groups.push_back(make_float4(u2f((uint32_t)i), u2f((uint32_t)(j - i)), u2f(quad ? 0u : 1u), 0.f));
+        if (quad)
+        {
+            groups.push_back(make_float4((float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad), 0.f));
+            groups.push_back(make_float4((float)(hi[0] + pad), (float)(hi[1] + pad), (float)(hi[2] + pad), 0.f));
+        }
+        else { groups.push_back(make_float4(0, 0, 0, 0)); groups.push_back(make_float4(0, 0, 0, 0)); }
+        i = j;
+    }
     CK(c->lightsPre.upload(lp.data(), lp.size(), c->stream));
+    CK(c->lightGroups.upload(groups.data(), groups.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->S.lightsPre = c->lightsPre.p;
+    c->S.lightsPre = c->lightsPre.p; c->S.lightGroups = c->lightGroups.p; c->S.numLightGroups = (int)(groups.size() / 3);
     return PTB_OK;
 }
 
@@ -410,7 +439,7 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
             ptbk_sort(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
             shadeQueue = c->sortedQueue.p;
         }
-        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p);
+        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0);
         if (!F.inlineShadow)
         {
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
@@ -555,7 +584,7 @@ int ptb_destroy(PtbCtx* c)
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
-    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
+    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
     c->rayO.release(); c->rayD.release(); c->thr.release(); c->rad.release(); c->hit.release(); c->med.release(); c->medCol.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
     c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->shKey.release(); c->shPerm.release(); c->shHist.release();

@@ -150,47 +150,78 @@ __device__ __forceinline__ float sphereHit(float rad, float3 pos, float3 o, floa
 
 // lightsPre rows (8 float4 per light, built at upload by buildLightsPre in ptb_api.cpp):
 //   0: position, type | 1: emission, area | 2: u, radius | 3: v, samePlaneAsPrevious | 4: normal, plane.w | 5: u/dot(u,u) | 6: v/dot(v,v)
+// lightGroups rows (3 float4 per group of CONSECUTIVE lights): {first, count, kind (0 = quads sharing one plane, 1 = single other light)},
+//   boxMin, boxMax = padded bounds of the group's quads.  A plane hit outside the padded box cannot pass any member's inside test
+//   (the pad is ~1e3 x larger than the rounding of a1/a2), so skipping the members is exact; index order is preserved.
+__device__ __forceinline__ bool outsideBox(float3 p, float4 bmin, float4 bmax)
+{
+    return !(p.x >= bmin.x && p.x <= bmax.x && p.y >= bmin.y && p.y <= bmax.y && p.z >= bmin.z && p.z <= bmax.z);
+}
 // Light loop of ClosestHit (closest_hit.glsl:28-86): nearest light, first index wins ties (strict <).
 __device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float3 d, float& t, int& light)
 {
-    PlaneHit ph; ph.dt = 0.f; ph.t = 0.f; ph.valid = false; ph.p = f3(0.f);
-    for (int i = 0; i < S.numLights; i++)
+    for (int g = 0; g < S.numLightGroups; g++)
     {
-        const float4* p = S.lightsPre + (size_t)i * 8;
-        const float4 a = __ldg(p);
-        float dist = PTB_INF;
-        if (a.w == 0.0f)
+        const float4* gp = S.lightGroups + (size_t)g * 3;
+        const float4 g0 = __ldg(gp);
+        const int first = __float_as_int(g0.x), count = __float_as_int(g0.y);
+        const float4* p = S.lightsPre + (size_t)first * 8;
+        if (__float_as_int(g0.z) == 0)
         {
-            if (__ldg(p + 3).w == 0.0f) { const float4 e = __ldg(p + 4); planeEval(f3(e), e.w, o, d, ph); }
+            const float4 e = __ldg(p + 4);
+            PlaneHit ph;
+            planeEval(f3(e), e.w, o, d, ph);
             if (ph.dt > 0.f) continue;                       // hide backfacing quad light (closest_hit.glsl:50)
-            dist = rectInside(ph, f3(a), f3(__ldg(p + 5)), f3(__ldg(p + 6)));
+            if (!ph.valid) continue;                         // RectIntersect returns INF for every member
+            if (count > 1 && outsideBox(ph.p, __ldg(gp + 1), __ldg(gp + 2))) continue;
+            for (int i = 0; i < count; i++, p += 8)
+            {
+                float dist = rectInside(ph, f3(__ldg(p)), f3(__ldg(p + 5)), f3(__ldg(p + 6)));
+                if (dist < t) { t = dist; light = first + i; }
+            }
         }
-        else if (a.w == 1.0f)
-            dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
         else
-            continue;
-        if (dist < 0.f) dist = PTB_INF;
-        if (dist < t) { t = dist; light = i; }
+        {
+            const float4 a = __ldg(p);
+            if (a.w != 1.0f) continue;                       // distant lights are never intersected
+            float dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
+            if (dist < 0.f) dist = PTB_INF;
+            if (dist < t) { t = dist; light = first; }
+        }
     }
 }
-// Light loop of AnyHit (anyhit.glsl:28-63): two-sided quads.
+// Light loop of AnyHit (anyhit.glsl:28-63): two-sided quads.  (maxDist <= INF in every pipeline call; for larger values the
+// reference's `INF < maxDist` quirk makes any quad/sphere light an occluder.)
 __device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d, float maxDist)
 {
-    PlaneHit ph; ph.dt = 0.f; ph.t = 0.f; ph.valid = false; ph.p = f3(0.f);
-    for (int i = 0; i < S.numLights; i++)
+    if (maxDist > PTB_INF)
     {
-        const float4* p = S.lightsPre + (size_t)i * 8;
-        const float4 a = __ldg(p);
-        float dist;
-        if (a.w == 0.0f)
+        for (int i = 0; i < S.numLights; i++) { float ty = __ldg(S.lightsPre + (size_t)i * 8).w; if (ty == 0.0f || ty == 1.0f) return true; }
+        return false;
+    }
+    for (int g = 0; g < S.numLightGroups; g++)
+    {
+        const float4* gp = S.lightGroups + (size_t)g * 3;
+        const float4 g0 = __ldg(gp);
+        const int first = __float_as_int(g0.x), count = __float_as_int(g0.y);
+        const float4* p = S.lightsPre + (size_t)first * 8;
+        if (__float_as_int(g0.z) == 0)
         {
-            if (__ldg(p + 3).w == 0.0f) { const float4 e = __ldg(p + 4); planeEval(f3(e), e.w, o, d, ph); }
-            // RectIntersect returns t or INF; the inside test only matters when t itself can pass `d < maxDist`
-            dist = (ph.valid && ph.t < maxDist) ? rectInside(ph, f3(a), f3(__ldg(p + 5)), f3(__ldg(p + 6))) : PTB_INF;
+            const float4 e = __ldg(p + 4);
+            PlaneHit ph;
+            planeEval(f3(e), e.w, o, d, ph);
+            if (!(ph.valid && ph.t < maxDist)) continue;     // d > 0 && d < maxDist can only hold for d == t
+            if (count > 1 && outsideBox(ph.p, __ldg(gp + 1), __ldg(gp + 2))) continue;
+            for (int i = 0; i < count; i++, p += 8)
+                if (rectInside(ph, f3(__ldg(p)), f3(__ldg(p + 5)), f3(__ldg(p + 6))) < maxDist) return true;
         }
-        else if (a.w == 1.0f) dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
-        else continue;
-        if (dist > 0.0f && dist < maxDist) return true;
+        else
+        {
+            const float4 a = __ldg(p);
+            if (a.w != 1.0f) continue;
+            float dist = sphereHit(__ldg(p + 2).w, f3(a), o, d);
+            if (dist > 0.0f && dist < maxDist) return true;
+        }
     }
     return false;
 }
@@ -231,7 +262,7 @@ struct NoAlpha { };
 template <bool ANY, bool ALPHA, bool CULL>
 struct Trav
 {
-    float3 o, d, ro, rd, inv;
+    float3 o, d, ro, rd, inv, invW;
     float t;
     uint32_t cur;
     int curInst;
@@ -243,7 +274,7 @@ struct Trav
     __device__ __forceinline__ void begin(const DevScene& S, float3 o_, float3 d_, float tmax, Stack& stk)
     {
         o = o_; d = d_; ro = o_; rd = d_;
-        inv = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z));
+        inv = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z)); invW = inv;
         t = tmax; cur = S.rootMeta; curInst = -1; inBlas = false; occluded = false;
         stk.reset();
         stk.push(PTB_META_NONE);
@@ -327,7 +358,7 @@ struct Trav
             inBlas = false;
             cur = stk.pop();
             ro = o; rd = d;
-            inv = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
+            inv = invW;                                      // 1/direction of the world-space ray, computed once in begin()
         }
         return false;
     }

@@ -38,7 +38,9 @@ struct DevScene
     const float4* tris;         // 3 float4 / leaf-ref slot: v0, e0, e1, vertIndices.x
     const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {rootMeta, matID, 0, 0} in .w
     const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
-    const float4* lightsPre;    // 8 float4 / light (see LightPre in ptb_api.cpp)
+    const float4* lightsPre;    // 8 float4 / light (see buildLightsPre in ptb_api.cpp)
+    const float4* lightGroups;  // 3 float4 / group of consecutive lights (shared plane + padded bounds)
+    int numLightGroups;
     uint32_t rootMeta;          // meta of the TLAS root
     int numNodes, topLevelIndex, numIndices, numVertices, numMaterials, numInstances, numLights;
     int numTextures, texW, texH, envW, envH;
@@ -116,7 +118,7 @@ void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const Pat
 void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
                uint32_t* sorted);
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats);
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter);
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats, const uint32_t* perm);
 void ptbk_sort_keys(const LaunchCfg&, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys, uint32_t* perm);

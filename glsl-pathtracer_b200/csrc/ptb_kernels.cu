@@ -89,8 +89,12 @@ __device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams
     float cam_r1 = __fmul_rn(rng.rand(), PTB_TWO_PI);
     float cam_r2 = __fmul_rn(rng.rand(), F.camAperture);
     float sr = __fsqrt_rn(cam_r2);
-    float s1, c1; sincosf(cam_r1, &s1, &c1);
-    float3 ap = f3(xm(xa(xm(c1, right.x), xm(s1, up.x)), sr), xm(xa(xm(c1, right.y), xm(s1, up.y)), sr), xm(xa(xm(c1, right.z), xm(s1, up.z)), sr));
+    float3 ap = f3(0.f);
+    if (F.camAperture != 0.0f)       // pinhole: the lens offset is (cos,sin)*sqrt(0) = 0, skip the sincos (the two draws above are still consumed)
+    {
+        float s1, c1; sincosf(cam_r1, &s1, &c1);
+        ap = f3(xm(xa(xm(c1, right.x), xm(s1, up.x)), sr), xm(xa(xm(c1, right.y), xm(s1, up.y)), sr), xm(xa(xm(c1, right.z), xm(s1, up.z)), sr));
+    }
     float3 fd = xsub(focalPoint, ap);
     float fl = __fsqrt_rn(xdot(fd, fd));
     rd = f3(xd(fd.x, fl), xd(fd.y, fl), xd(fd.z, fl));
@@ -114,9 +118,7 @@ __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveP
                 cameraRay(F, W, W.x0 + px, W.y0 + py, W.firstSample + s * W.sampleStride, rng, ro, rd);
                 P.rayO[slot] = make_float4(ro.x, ro.y, ro.z, 0.0f);
                 P.rayD[slot] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(0u));
-                P.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-                P.rad[slot] = make_float4(0.f, 0.f, 0.f, 1.f);
-                P.rng[slot] = rng.s;
+                P.rng[slot] = rng.s;          // throughput (1) / radiance (0) / alpha (1) are implied in the first shade iteration
                 if (F.general)
                 {
                     P.med[slot] = make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(0));
@@ -549,9 +551,10 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
 
 // One iteration of the PathTrace loop body after ClosestHit (pathtrace.glsl:303-471) for path slot p.
 template <bool GEN>
-__device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+__device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool firstIter, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
 {
-    const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], thr4 = P.thr[p], rad4 = P.rad[p], hit4 = P.hit[p];
+    const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], hit4 = P.hit[p];
+    const float4 thr4 = firstIter ? make_float4(1.f, 1.f, 1.f, 0.f) : P.thr[p], rad4 = firstIter ? make_float4(0.f, 0.f, 0.f, 1.f) : P.rad[p];
     const int hitInst = P.hitInst[p];
     Rng rng; rng.s = P.rng[p];
     const uint32_t fl = __float_as_uint(rd4.w);
@@ -734,7 +737,7 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
 
 template <bool GEN, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
-                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
+                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
 {
     const uint32_t n = ctrThis[CTR_NPATHS];
     const uint32_t lane = threadIdx.x & 31u;
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
         if (i < n)
         {
             p = queue[i];
-            shadePath<GEN>(S, F, P, p, cont, sa, sb, ic);
+            shadePath<GEN>(S, F, P, p, firstIter != 0, cont, sa, sb, ic);
         }
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (m)
@@ -1040,7 +1043,7 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats)
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
 {
     static int bpsGen = 0, bpsFast = 0, occ = 0;
     if (!bpsGen)
@@ -1053,10 +1056,10 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 4>, SHADE_THREADS, 0);
         if (bpsGen < 1) bpsGen = 1; if (bpsFast < 1) bpsFast = 1;
     }
-    if (F.general) k_shade<true, 3><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
-    else if (occ >= 8) k_shade<false, 8><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
-    else if (occ >= 6) k_shade<false, 6><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
-    else k_shade<false, 4><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats);
+    if (F.general) k_shade<true, 3><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else if (occ >= 8) k_shade<false, 8><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else if (occ >= 6) k_shade<false, 6><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else k_shade<false, 4><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     g_launches++;
 }
 
