@@ -235,7 +235,7 @@ def run_ours(args):
         ab = algorithmic_bytes(sc)
         rays_last_step = segs / args.steps / world          # rank-0 share of one step
         n_trace_launches = (sc.renderOptions.maxDepth + 1) * max(1, -(-SPP_PER_STEP // max(1, ctx.opts.samplesPerWave or 4)))
-        bytes_per_ray = ab["culled"]["closest"]
+        bytes_per_ray = ab["culled" if args.cull else "unculled"]["closest"]
         achieved = rays_last_step * bytes_per_ray / (trace_ms_last * 1e-3) / 1e9 if trace_ms_last > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cull", type=int, default=1)
-    ap.add_argument("--samples-per-wave", type=int, default=4)
+    ap.add_argument("--samples-per-wave", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -565,7 +565,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     // default camera: looking down -z from the origin (the caller sets the real one with ptb_set_camera)
     c->cam = PtbCamera{{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, 1.0f, 1.0f, 0.0f};
     refreshFrameParams(c);
-    c->F.cullBoxes = 1;      // identical hits, fewer node fetches (tests/test_gpu_trace.py::test_culled_traversal_identical)
+    c->F.cullBoxes = 1;      // t-culled traversal by default; ptb_set_cull(0) = the reference's unculled visit order, see ptb200.h
     if ((rc = allocFrameBuffers(c)) != PTB_OK) { ptb_destroy(c); return rc; }
     CK(c->dstats.alloc(1));
     CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), s));

@@ -292,7 +292,7 @@ struct Trav
             float e0, e1;
             float lh = aabbHit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ro, inv, e0);
             float rh = aabbHit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ro, inv, e1);
-            if (CULL) { if (e0 > t) lh = -1.0f; if (e1 > t) rh = -1.0f; }
+            if (CULL) { const float tc = t * 1.00001f; if (e0 > tc) lh = -1.0f; if (e1 > tc) rh = -1.0f; }
             const uint32_t lm = __float_as_uint(q3.x), rm = __float_as_uint(q3.y);
             const bool hl = lh > 0.0f, hr = rh > 0.0f;
             if (hl && hr)

@@ -369,7 +369,7 @@ bool ClosestHit(Ctx& c, Ray r, State& state, LightSampleRec& lightSample, HitInf
             float e0, e1;
             leftHit = AABBIntersect(texel3(s->nodes, leftIndex * 3 + 0), texel3(s->nodes, leftIndex * 3 + 1), rTrans, &e0);
             rightHit = AABBIntersect(texel3(s->nodes, rightIndex * 3 + 0), texel3(s->nodes, rightIndex * 3 + 1), rTrans, &e1);
-            if (cull) { if (leftHit > 0.0f && e0 > t) leftHit = -1.0f; if (rightHit > 0.0f && e1 > t) rightHit = -1.0f; }
+            if (cull) { const float tc = t * 1.00001f; if (leftHit > 0.0f && e0 > tc) leftHit = -1.0f; if (rightHit > 0.0f && e1 > tc) rightHit = -1.0f; }
 
             if (leftHit > 0.0f && rightHit > 0.0f)
             {
@@ -623,7 +623,7 @@ bool AnyHit(Ctx& c, Ray r, float maxDist, bool allowAlpha = true)
             float e0, e1;
             leftHit = AABBIntersect(texel3(s->nodes, leftIndex * 3 + 0), texel3(s->nodes, leftIndex * 3 + 1), rTrans, &e0);
             rightHit = AABBIntersect(texel3(s->nodes, rightIndex * 3 + 0), texel3(s->nodes, rightIndex * 3 + 1), rTrans, &e1);
-            if (cull) { if (leftHit > 0.0f && e0 > maxDist) leftHit = -1.0f; if (rightHit > 0.0f && e1 > maxDist) rightHit = -1.0f; }
+            if (cull) { const float tc = maxDist * 1.00001f; if (leftHit > 0.0f && e0 > tc) leftHit = -1.0f; if (rightHit > 0.0f && e1 > tc) rightHit = -1.0f; }
             if (leftHit > 0.0f && rightHit > 0.0f)
             {
                 int deferred = -1;

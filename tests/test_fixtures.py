@@ -12,6 +12,9 @@ PINNED = {  # FNV-1a-64 over the raw bytes of bvhTranslator.no
     "hyperion_sphere_light": (100393, 100371, 0x004B190F9B53FFDB),
     "volume_cube": (16, 12, 0x1193AFF733BF53F0),
     "teapot": (3, 1, 0x6FB4E90F01A5D9BA),
+    # synthetic stand-ins (tests/golden/gen_synthetic.py, seed 42) built by the same unmodified reference host code; regression pins
+    "ibl_spheres": (1190, 1184, 0x07664C04E651EC2E),
+    "instancing": (21186, 1184, 0x4C5BB29432A17014),
 }
 
 
@@ -46,6 +49,21 @@ def test_feature_derivation_matches_renderer_cpp():
     # teapot.scene names an HDR that is missing from the checkout: enableEnvMap is set by the loader but scene->envMap is null
     t = load_scene_cached("teapot")
     assert t.renderOptions.enableEnvMap and t.envImg is None and not (f(t) & S.OPT_ENVMAP) and not (f(t) & S.OPT_LIGHTS)
+
+
+def test_synthetic_env_map_cdf_matches_buildcdf():
+    """EnvironmentMap::BuildCDF (EnvironmentMap.cpp:39-61): flat fp32 running sum of luminance; totalSum = last element."""
+    sc = load_scene_cached("ibl_spheres")
+    assert sc.envImg.shape == (256, 512, 3) and sc.envCdf.shape == (256, 512)
+    w = (np.float32(0.212671) * sc.envImg[..., 0] + np.float32(0.715160) * sc.envImg[..., 1] + np.float32(0.072169) * sc.envImg[..., 2]).astype(np.float32).ravel()
+    cdf = np.empty_like(w); acc = np.float32(0)
+    for i in range(0, len(w), 1):      # sequential fp32 accumulation, as the reference loop
+        acc = np.float32(acc + w[i]); cdf[i] = acc
+        if i == 4096: break
+    assert np.array_equal(cdf[:4097], sc.envCdf.ravel()[:4097])
+    assert sc.envTotalSum == sc.envCdf.ravel()[-1] and sc.tlasHeight == 3
+    inst = load_scene_cached("instancing")
+    assert len(inst.transforms) == 10001 and inst.tlasHeight == 15 and inst.renderOptions.maxDepth == 8
 
 
 def test_vert_indices_follow_scene_cpp_packing():

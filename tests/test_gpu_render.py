@@ -89,7 +89,11 @@ def test_bsdf_sample_matches_oracle(oracle_mod):
 # of the inputs (libm vs CUDA sin/cos, 2-ulp division).  Those samples carry little energy (contribution ~ |cos| at the light).
 CASES = [("cornell_box_orig", 128, 128, 64, 64, 4, 8, 0.97), ("cornell_box_sphere", 128, 128, 64, 64, None, 8, 0.97),
          ("hyperion_rect_lights", 240, 136, 64, 36, None, 8, 0.97), ("hyperion_sphere_light", 240, 136, 64, 36, None, 8, 0.5),
-         ("volume_cube", 160, 90, 80, 45, None, 8, 0.97), ("teapot", 128, 72, 64, 36, None, 8, 0.97)]
+         ("volume_cube", 160, 90, 80, 45, None, 8, 0.97), ("teapot", 128, 72, 64, 36, None, 8, 0.97),
+         # generated HDR environment (SampleEnvMap / EvalEnvMap / CDF binary search, env NEE shadow queue), checker texture with REPEAT wrap
+         ("ibl_spheres", 240, 136, 64, 36, None, 8, 0.95),
+         # 10 001 instances, TLAS height 15, rotated + non-uniformly scaled transforms, depth 8, glass/metal/clearcoat/sheen/anisotropic materials
+         ("instancing", 240, 136, 64, 36, None, 4, 0.93)]
 
 
 @pytest.mark.parametrize("name,w,h,tw,th,depth,spp,minfrac", CASES)
