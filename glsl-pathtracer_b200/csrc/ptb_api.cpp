@@ -116,10 +116,8 @@ struct PtbCtx
 
     // wave state
     size_t slotCap = 0; bool stateGeneral = false;
-    DevBuf<float4> rayO, rayD, thr, rad, hit, med, medCol, shO[2], shD[2], shC[2];
-    DevBuf<uint4> rng;
-    DevBuf<int> hitInst;
-    DevBuf<float2> prevUV;
+    DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
+    int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, shKey, shPerm, shHist;
     int shadowSort = 0;        // (experiment, default off) sort light-NEE shadow rays by light index; measured slower, see DESIGN.md
     int sortMode = 1;          // 0 off, 1 sort bounces >= 1, 2 sort every bounce
@@ -366,12 +364,12 @@ int ensureWaveState(PtbCtx* c, size_t slots)
     const bool gen = c->F.general != 0;
     if (slots <= c->slotCap && (!gen || c->stateGeneral)) return PTB_OK;
     size_t n = std::max(slots, c->slotCap);
-    CK(c->rayO.alloc(n)); CK(c->rayD.alloc(n)); CK(c->thr.alloc(n)); CK(c->rad.alloc(n)); CK(c->hit.alloc(n)); CK(c->rng.alloc(n)); CK(c->hitInst.alloc(n));
+    c->stateStrideF4 = (gen || c->stateGeneral) ? 12 : 8;            // float4 per path: 7 used (+3 general), padded to 128 / 192 bytes
+    CK(c->state.alloc(n * c->stateStrideF4));
     CK(c->queue[0].alloc(n)); CK(c->queue[1].alloc(n));
     CK(c->shO[1].alloc(n)); CK(c->shD[1].alloc(n)); CK(c->shC[1].alloc(n));
     if (gen || c->stateGeneral)
     {
-        CK(c->med.alloc(n)); CK(c->medCol.alloc(n)); CK(c->prevUV.alloc(n));
         CK(c->shO[0].alloc(n)); CK(c->shD[0].alloc(n)); CK(c->shC[0].alloc(n));
         c->stateGeneral = true;
     }
@@ -384,8 +382,20 @@ int ensureWaveState(PtbCtx* c, size_t slots)
 PathState pathState(PtbCtx* c)
 {
     PathState P{};
-    P.rayO = c->rayO.p; P.rayD = c->rayD.p; P.thr = c->thr.p; P.rad = c->rad.p; P.rng = c->rng.p; P.hit = c->hit.p; P.hitInst = c->hitInst.p;
-    P.med = c->med.p; P.medCol = c->medCol.p; P.prevUV = c->prevUV.p;
+    char* b = (char*)c->state.p;
+    const size_t n = c->slotCap;
+    if (c->aos)
+    {   // field k of path i at b + i*stride + 16*k
+        const uint32_t st = (uint32_t)(c->stateStrideF4 * 16);
+        P.rayO = {b, st}; P.rayD = {b + 16, st}; P.thr = {b + 32, st}; P.rad = {b + 48, st}; P.rng = {b + 64, st}; P.hit = {b + 80, st};
+        P.hitInst = {b + 96, st}; P.med = {b + 112, st}; P.medCol = {b + 128, st}; P.prevUV = {b + 144, st};
+    }
+    else
+    {   // SoA: array k at b + k*n*16
+        auto arr = [&](int k) { return b + (size_t)k * n * 16; };
+        P.rayO = {arr(0), 16}; P.rayD = {arr(1), 16}; P.thr = {arr(2), 16}; P.rad = {arr(3), 16}; P.rng = {arr(4), 16}; P.hit = {arr(5), 16};
+        P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
+    }
     for (int k = 0; k < 2; k++) { P.shO[k] = c->shO[k].p; P.shD[k] = c->shD[k].p; P.shC[k] = c->shC[k].p; P.queue[k] = c->queue[k].p; }
     P.shKey = (c->shadowSort && c->S.numLights > 1 && c->S.numLights <= 4096) ? c->shKey.p : nullptr;
     return P;
@@ -572,6 +582,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     CK(cudaStreamSynchronize(s));
     c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
+    if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
     if (const char* e = getenv("PTB_SHADOW_SORT")) c->shadowSort = atoi(e);   // 0 off, k: sort the shadow rays of the first k bounces
     *out = c;
     return PTB_OK;
@@ -585,10 +596,10 @@ int ptb_destroy(PtbCtx* c)
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
-    c->rayO.release(); c->rayD.release(); c->thr.release(); c->rad.release(); c->hit.release(); c->med.release(); c->medCol.release();
+    c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
     c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->shKey.release(); c->shPerm.release(); c->shHist.release();
-    c->rng.release(); c->hitInst.release(); c->prevUV.release(); c->counters.release(); c->dstats.release();
+    c->counters.release(); c->dstats.release();
     for (auto e : c->traceEvents) cudaEventDestroy(e);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);

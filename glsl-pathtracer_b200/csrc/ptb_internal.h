@@ -78,19 +78,31 @@ struct WaveParams
     uint32_t nSlots;           // vw*vh*nSamples
 };
 
-// Path state, SoA of 16-byte vectors indexed by path slot.
+// Path state fields are addressed as base + slot * stride.  stride = sizeof(T) gives SoA arrays; a common 128-byte (lights-only)
+// or 192-byte (general) stride interleaves all fields of one path in one or two cache lines, so that the material-sorted (scattered)
+// shade passes touch whole sectors instead of 16 bytes out of every 32-byte sector.
+#if defined(__CUDACC__)
+#define PTB_HD __host__ __device__ __forceinline__
+#else
+#define PTB_HD inline
+#endif
+template <class T> struct StateField
+{
+    char* base; uint32_t stride;
+    PTB_HD T& operator[](size_t i) const { return *reinterpret_cast<T*>(base + i * stride); }
+};
 struct PathState
 {
-    float4* rayO;     // origin.xyz, prev scatter pdf
-    float4* rayD;     // direction.xyz, bits: depth (low 16, signed) | flags (high 16)
-    float4* thr;      // throughput.xyz, previous roughness (mollification)
-    float4* rad;      // radiance.xyz, alpha
-    uint4*  rng;      // pcg4d state
-    float4* hit;      // t, bary u, bary v, bits(primSlot)
-    int*    hitInst;  // >=0 instance (triangle hit); -1 miss; <= -2: light -(idx+2)
-    float4* med;      // general: medium density, anisotropy, bits(type), bits(prevMatID)
-    float4* medCol;   // general: medium color.xyz, -
-    float2* prevUV;   // general: stale texCoord (Q2)
+    StateField<float4> rayO;     // origin.xyz, prev scatter pdf
+    StateField<float4> rayD;     // direction.xyz, bits: depth (low 16, signed) | flags (high 16)
+    StateField<float4> thr;      // throughput.xyz, previous roughness (mollification)
+    StateField<float4> rad;      // radiance.xyz, alpha
+    StateField<uint4>  rng;      // pcg4d state
+    StateField<float4> hit;      // t, bary u, bary v, bits(primSlot)
+    StateField<int>    hitInst;  // >=0 instance (triangle hit); -1 miss; <= -2: light -(idx+2)
+    StateField<float4> med;      // general: medium density, anisotropy, bits(type), bits(prevMatID)
+    StateField<float4> medCol;   // general: medium color.xyz, -
+    StateField<float2> prevUV;   // general: stale texCoord (Q2)
     // shadow queues A (env NEE) and B (light NEE), dense by queue slot
     float4* shO[2];   // origin.xyz, maxDist
     float4* shD[2];   // direction.xyz, bits(path slot)
