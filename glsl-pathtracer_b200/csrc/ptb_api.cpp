@@ -118,8 +118,7 @@ struct PtbCtx
     size_t slotCap = 0; bool stateGeneral = false;
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
-    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, shKey, shPerm, shHist;
-    int shadowSort = 0;        // (experiment, default off) sort light-NEE shadow rays by light index; measured slower, see DESIGN.md
+    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist;
     int sortMode = 1;          // 0 off, 1 sort bounces >= 1, 2 sort every bounce
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
@@ -374,7 +373,7 @@ int ensureWaveState(PtbCtx* c, size_t slots)
         c->stateGeneral = true;
     }
     CK(c->counters.alloc((size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE));
-    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n)); CK(c->shKey.alloc(n)); CK(c->shPerm.alloc(n));
+    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n));
     c->slotCap = n;
     return PTB_OK;
 }
@@ -397,7 +396,6 @@ PathState pathState(PtbCtx* c)
         P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
     }
     for (int k = 0; k < 2; k++) { P.shO[k] = c->shO[k].p; P.shD[k] = c->shD[k].p; P.shC[k] = c->shC[k].p; P.queue[k] = c->queue[k].p; }
-    P.shKey = (c->shadowSort && c->S.numLights > 1 && c->S.numLights <= 4096) ? c->shKey.p : nullptr;
     return P;
 }
 
@@ -424,11 +422,6 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
     const int numKeys = c->S.numMaterials + 2;
     CK(c->sortHist.alloc((size_t)numKeys * 2));
     CK(cudaMemsetAsync(c->sortHist.p, 0, (size_t)numKeys * 2 * sizeof(uint32_t), c->stream));
-    if (P.shKey)
-    {
-        CK(c->shHist.alloc((size_t)c->S.numLights * 2));
-        CK(cudaMemsetAsync(c->shHist.p, 0, (size_t)c->S.numLights * 2 * sizeof(uint32_t), c->stream));
-    }
     ptbk_camera(L, c->S, F, W, P, ctr);
     const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
     const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
@@ -453,17 +446,9 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
         if (!F.inlineShadow)
         {
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
-                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p, nullptr);
+                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
             if (F.features & PTB_OPT_LIGHTS)
-            {
-                const uint32_t* perm = nullptr;
-                if (P.shKey && it <= c->shadowSort - 1 + 0)
-                {   // rays towards the same light from neighbouring pixels traverse the same nodes
-                    ptbk_sort_keys(L, P.shKey, ci + CTR_NSHB, c->shHist.p, c->shHist.p + c->S.numLights, c->S.numLights, c->shPerm.p);
-                    perm = c->shPerm.p;
-                }
-                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p, perm);
-            }
+                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p);
         }
         it++;
         if (it >= PTB_MAX_ITERS) break;                       // alpha-skip re-traces are unbounded in the reference (Q7); hard stop
@@ -583,7 +568,6 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
-    if (const char* e = getenv("PTB_SHADOW_SORT")) c->shadowSort = atoi(e);   // 0 off, k: sort the shadow rays of the first k bounces
     *out = c;
     return PTB_OK;
 }
@@ -598,7 +582,7 @@ int ptb_destroy(PtbCtx* c)
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
-    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->shKey.release(); c->shPerm.release(); c->shHist.release();
+    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release();
     c->counters.release(); c->dstats.release();
     for (auto e : c->traceEvents) cudaEventDestroy(e);
     if (c->evStart) cudaEventDestroy(c->evStart);

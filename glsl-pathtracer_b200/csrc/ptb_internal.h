@@ -108,7 +108,6 @@ struct PathState
     float4* shD[2];   // direction.xyz, bits(path slot)
     float4* shC[2];   // contribution.rgb (already multiplied by throughput)
     uint32_t* queue[2];
-    uint32_t* shKey;  // light index of each queue-B shadow ray (sort key), or null
 };
 
 #define PTB_FLAG_INMEDIUM   (1u << 16)
@@ -132,8 +131,7 @@ void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, co
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter);
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
-                 uint32_t* fetchCtr, DevStats* stats, const uint32_t* perm);
-void ptbk_sort_keys(const LaunchCfg&, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys, uint32_t* perm);
+                 uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);
 void ptbk_tonemap(const LaunchCfg&, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
                   int simpleAcesFit, const float* backgroundCol3, uint32_t features, uchar4* out);

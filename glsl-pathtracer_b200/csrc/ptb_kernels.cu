@@ -25,6 +25,7 @@ enum {
 };
 
 constexpr int TRACE_THREADS = 256;
+constexpr int TRACE_MIN_BLOCKS = 5;     // 48 registers: measured 772 spp/s vs 720 (3 blocks, 72 regs), 767 (4), 753 (6)
 constexpr int SHADE_THREADS = 128;
 
 // ------------------------------------------------------------------ slot <-> pixel mapping ----------------------
@@ -193,7 +194,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
     }
 }
 
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
                                                           const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats,
                                                           uint32_t* __restrict__ keys, uint32_t* hist)
 {
@@ -214,25 +215,6 @@ __global__ void k_sort_scan(uint32_t* hist, uint32_t* cursor, int numKeys)
     for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     uint32_t run = incl - sum;
     for (int k = lane * per; k < min(numKeys, (lane + 1) * per); k++) { uint32_t h = hist[k]; cursor[k] = run; run += h; hist[k] = 0; }
-}
-
-// Tile-aggregated key histogram for queues whose keys are produced by another kernel (shadow rays keyed by light index).
-__global__ void __launch_bounds__(256) k_sort_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr, uint32_t* hist, int numKeys)
-{
-    extern __shared__ uint32_t sm[];
-    const uint32_t n = *countPtr;
-    for (int k = threadIdx.x; k < numKeys; k += 256) sm[k] = 0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; b0 < n; b0 += gridDim.x * blockDim.x)
-    {
-        const uint32_t i = b0 + lane;
-        const uint32_t key = i < n ? keys[i] : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (key != 0xffffffffu && (int)lane == __ffs(peers) - 1) atomicAdd(&sm[key], (uint32_t)__popc(peers));
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < numKeys; k += 256) { uint32_t c = sm[k]; if (c) atomicAdd(&hist[k], c); }
 }
 
 // Counting-sort scatter: queue entries -> key buckets.  Each 256-thread block ranks a tile of 2048 entries in shared memory
@@ -270,7 +252,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
         for (int j = 0; j < SORT_ITEMS; j++)
         {
             const uint32_t i = tile + j * 256u + threadIdx.x;
-            if (key[j] != 0xffffffffu) sorted[base[key[j]] + rank[j]] = queue ? queue[i] : i;
+            if (key[j] != 0xffffffffu) sorted[base[key[j]] + rank[j]] = queue[i];
         }
         __syncthreads();
     }
@@ -478,7 +460,7 @@ __device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameP
 }
 
 // ------------------------------------------------------------------ shade ----------------------------------------
-struct ShadowOut { bool valid; float3 o, d, c; float maxDist; uint32_t key; };
+struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 
 // DirectLight (pathtrace.glsl:158-283).  Deferred mode: fills sa (env) / sb (light) with contribution*throughput.
 // Inline mode (shadow rays draw from the path RNG): traces here and returns Ld.
@@ -541,7 +523,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f / ls.pdf;
                     if (volMis || inl) Ld += c;
-                    else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; sb.key = (uint32_t)idx; }
+                    else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
                 }
             }
         }
@@ -731,7 +713,6 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
         P.shO[which][k] = make_float4(s.o.x, s.o.y, s.o.z, s.maxDist);
         P.shD[which][k] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(p));
         P.shC[which][k] = make_float4(s.c.x, s.c.y, s.c.z, 0.f);
-        if (which == 1 && P.shKey) P.shKey[k] = s.key;
     }
 }
 
@@ -789,7 +770,7 @@ struct AlphaMask   // deferred AnyHit alpha test: MASK only (BLEND needs the pat
 
 template <bool ALPHA, bool CULL, class AlphaFn>
 __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams& F, const PathState& P, int which, uint32_t n, uint32_t* fetchCtr,
-                                           const uint32_t* __restrict__ perm, AlphaFn alphaFn)
+                                           AlphaFn alphaFn)
 {
     const uint32_t lane = threadIdx.x & 31u;
     SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
@@ -800,10 +781,9 @@ __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams&
         if (lane == 0) base = atomicAdd(fetchCtr, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        uint32_t i = base + lane;
+        const uint32_t i = base + lane;
         if (i < n)
         {
-            if (perm) i = perm[i];                      // light-sorted order
             const float4 o4 = P.shO[which][i], d4 = P.shD[which][i];
             const float3 o = f3(o4), d = f3(d4);
             const float maxDist = o4.w;
@@ -825,15 +805,15 @@ __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams&
     }
 }
 
-__global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, FrameParams F, PathState P, int which, const uint32_t* __restrict__ countPtr,
-                                                           uint32_t* fetchCtr, DevStats* stats, const uint32_t* __restrict__ perm)
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, FrameParams F, PathState P, int which, const uint32_t* __restrict__ countPtr,
+                                                           uint32_t* fetchCtr, DevStats* stats)
 {
     const uint32_t n = *countPtr;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->shadowRays, (unsigned long long)n);
     const bool alpha = OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM);
-    if (alpha) shadowLoop<true, true>(S, F, P, which, n, fetchCtr, perm, AlphaMask{&S});
-    else if (F.cullBoxes) shadowLoop<false, true>(S, F, P, which, n, fetchCtr, perm, NoAlpha());
-    else shadowLoop<false, false>(S, F, P, which, n, fetchCtr, perm, NoAlpha());
+    if (alpha) shadowLoop<true, true>(S, F, P, which, n, fetchCtr, AlphaMask{&S});
+    else if (F.cullBoxes) shadowLoop<false, true>(S, F, P, which, n, fetchCtr, NoAlpha());
+    else shadowLoop<false, false>(S, F, P, which, n, fetchCtr, NoAlpha());
 }
 
 // ------------------------------------------------------------------ accumulate / tonemap ------------------------
@@ -1064,20 +1044,11 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
 }
 
 void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
-                 uint32_t* fetchCtr, DevStats* stats, const uint32_t* perm)
+                 uint32_t* fetchCtr, DevStats* stats)
 {
     int bps = traceBlocksPerSM(S);
-    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats, perm);
+    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
     g_launches++;
-}
-
-// keys[0..n) -> perm (indices sorted by key); only for numKeys <= 4096 (shared-memory histograms)
-void ptbk_sort_keys(const LaunchCfg& c, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys, uint32_t* perm)
-{
-    k_sort_count<<<c.numSMs * 4, 256, (size_t)numKeys * sizeof(uint32_t), st(c)>>>(keys, countPtr, hist, numKeys);
-    k_sort_scan<<<1, 32, 0, st(c)>>>(hist, cursor, numKeys);
-    k_sort_scatter<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(nullptr, keys, countPtr, cursor, perm, numKeys);
-    g_launches += 3;
 }
 
 void ptbk_accumulate(const LaunchCfg& c, const FrameParams& F, const WaveParams& W, const PathState& P, float4* accum, float4* previewOut)
