@@ -119,7 +119,7 @@ struct PtbCtx
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist;
-    int sortMode = 1;          // 0 off, 1 sort bounces >= 1, 2 sort every bounce
+    int sortMode = 3;          // 0 off, 1 global sort of bounces >= 1, 2 global sort of every bounce, 3 tile-local sort of bounces >= 1 (default: +3 % over 1)
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
 
@@ -432,14 +432,15 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
         uint32_t* ci = ctr + (size_t)it * PTB_CTR_STRIDE;
         uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
-        const bool sortThis = c->sortMode == 2 || (c->sortMode == 1 && it >= 1);
+        const bool sortThis = c->sortMode == 2 || ((c->sortMode == 1 || c->sortMode == 3) && it >= 1);
         ptbk_trace(L, c->S, F, P, P.queue[it & 1], ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
                    sortThis ? c->sortKeys.p : nullptr, c->sortHist.p);
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
         const uint32_t* shadeQueue = P.queue[it & 1];
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)
-            ptbk_sort(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
+            if (c->sortMode == 3 && numKeys <= 4096) ptbk_sort_tile_local(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, numKeys, c->sortedQueue.p);
+            else ptbk_sort(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
             shadeQueue = c->sortedQueue.p;
         }
         ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0);

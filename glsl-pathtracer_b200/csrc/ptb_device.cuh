@@ -594,8 +594,9 @@ __device__ __forceinline__ float3 EvalMicrofacetReflection(const Material& mat, 
     return F * D * G2 / (4.0f * L.z * V.z);
 }
 
-// DisneyEval (disney.glsl:244-351) in the local frame (T,B,N); V,L already local.
-__device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, float3 V, float3 L, float& pdf)
+// DisneyEval (disney.glsl:244-351) in the local frame (T,B,N); V,L already local; p = lobeSetup(mat, eta, V.z) (depends on V only,
+// so the NEE evaluation and the evaluation of the sampled direction of one hit share it).
+__device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, const Lobes& p, float3 V, float3 L, float& pdf)
 {
     pdf = 0.0f;
     float3 f = f3(0.0f);
@@ -603,8 +604,6 @@ __device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, f
     if (L.z > 0.0f) H = normalize(L + V);
     else H = normalize(L + V * eta);
     if (H.z < 0.0f) H = -H;
-    Lobes p;
-    lobeSetup(mat, eta, V.z, p);
     bool reflect = L.z * V.z > 0;
     float tmpPdf = 0.0f;
     float VDotH = fabsf(dot(V, H));
@@ -694,22 +693,32 @@ __device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, f
     return f * fabsf(L.z);
 }
 
+// Shading frame of one hit: Onb(N), V in that frame, lobe weights — computed once per hit, used by the NEE evaluations and the sample.
+struct ShadeFrame { float3 T, B, N, Vl; Lobes lobes; };
+__device__ __forceinline__ void frameSetup(const Material& mat, float eta, float3 V, float3 N, ShadeFrame& fr)
+{
+    fr.N = N;
+    Onb(N, fr.T, fr.B);
+    fr.Vl = ToLocal(fr.T, fr.B, N, V);
+    lobeSetup(mat, eta, fr.Vl.z, fr.lobes);
+}
+__device__ __forceinline__ float3 DisneyEvalFr(const Material& mat, float eta, const ShadeFrame& fr, float3 L, float& pdf)
+{
+    return DisneyEvalLocal(mat, eta, fr.lobes, fr.Vl, ToLocal(fr.T, fr.B, fr.N, L), pdf);
+}
 __device__ __forceinline__ float3 DisneyEval(const Material& mat, float eta, float3 V, float3 N, float3 L, float& pdf)
 {
-    float3 T, B;
-    Onb(N, T, B);
-    return DisneyEvalLocal(mat, eta, ToLocal(T, B, N, V), ToLocal(T, B, N, L), pdf);
+    ShadeFrame fr;
+    frameSetup(mat, eta, V, N, fr);
+    return DisneyEvalFr(mat, eta, fr, L, pdf);
 }
 
-// DisneySample (disney.glsl:142-242) with the three draws passed in.
-__device__ __forceinline__ float3 DisneySample(const Material& mat, float eta, float3 V, float3 N, float3& Lw, float& pdf, float r1, float r2, float r3)
+// DisneySample (disney.glsl:142-242) with the three draws passed in and the hit's frame / lobe weights precomputed.
+__device__ __forceinline__ float3 DisneySampleFr(const Material& mat, float eta, const ShadeFrame& fr, float3& Lw, float& pdf, float r1, float r2, float r3)
 {
     pdf = 0.0f;
-    float3 T, B;
-    Onb(N, T, B);
-    V = ToLocal(T, B, N, V);
-    Lobes p;
-    lobeSetup(mat, eta, V.z, p);
+    const float3 V = fr.Vl;
+    const Lobes& p = fr.lobes;
     float cdf0 = p.diffPr;
     float cdf1 = cdf0 + p.dielectricPr;
     float cdf2 = cdf1 + p.metalPr;
@@ -737,10 +746,16 @@ __device__ __forceinline__ float3 DisneySample(const Material& mat, float eta, f
         if (H.z < 0.0f) H = -H;
         L = normalize(reflect(-V, H));
     }
-    Lw = ToWorld(T, B, N, L);
-    // the reference converts V back to world and calls DisneyEval (disney.glsl:238-241), which re-derives the same frame
-    float3 Vw = ToWorld(T, B, N, V);
-    return DisneyEvalLocal(mat, eta, ToLocal(T, B, N, Vw), ToLocal(T, B, N, Lw), pdf);
+    Lw = ToWorld(fr.T, fr.B, fr.N, L);
+    // the reference converts V and L back to world space and calls DisneyEval (disney.glsl:238-241), which re-derives the same frame
+    // and takes both to local space again; L makes that round trip here, V (and with it the lobe weights) is reused.
+    return DisneyEvalLocal(mat, eta, p, V, ToLocal(fr.T, fr.B, fr.N, Lw), pdf);
+}
+__device__ __forceinline__ float3 DisneySample(const Material& mat, float eta, float3 V, float3 N, float3& Lw, float& pdf, float r1, float r2, float r3)
+{
+    ShadeFrame fr;
+    frameSetup(mat, eta, V, N, fr);
+    return DisneySampleFr(mat, eta, fr, Lw, pdf, r1, r2, r3);
 }
 
 // Material row -> Material (pathtrace.glsl:31-67 + :109-114), textures handled by the caller.

@@ -257,6 +257,53 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
         __syncthreads();
     }
 }
+// Tile-local variant: entries are grouped by key only inside their own tile of 2048 queue entries.  Warps become material-coherent
+// while every warp still touches path slots from one 2048-entry window, so the scattered state fetches stay sector/page local.
+__global__ void __launch_bounds__(256) k_sort_tile_local(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
+                                                          uint32_t* __restrict__ sorted, int numKeys)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t* hist = sm; uint32_t* base = sm + numKeys;
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tileSize = 256u * SORT_ITEMS;
+    for (uint32_t tile = blockIdx.x * tileSize; tile < n; tile += gridDim.x * tileSize)
+    {
+        for (int k = threadIdx.x; k < numKeys; k += 256) hist[k] = 0;
+        __syncthreads();
+        uint32_t key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++)
+        {
+            const uint32_t i = tile + j * 256u + threadIdx.x;
+            key[j] = i < n ? keys[i] : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t off = 0;
+            if ((int)lane == leader && key[j] != 0xffffffffu) off = atomicAdd(&hist[key[j]], (uint32_t)__popc(peers));
+            rank[j] = __shfl_sync(0xffffffffu, off, leader) + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {   // exclusive scan of the tile histogram by one warp
+            const int per = (numKeys + 31) / 32;
+            uint32_t sum = 0;
+            for (int k = lane * per; k < min(numKeys, (int)(lane + 1) * per); k++) sum += hist[k];
+            uint32_t incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            uint32_t run = incl - sum;
+            for (int k = lane * per; k < min(numKeys, (int)(lane + 1) * per); k++) { base[k] = run; run += hist[k]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++)
+        {
+            const uint32_t i = tile + j * 256u + threadIdx.x;
+            if (key[j] != 0xffffffffu) sorted[tile + base[key[j]] + rank[j]] = queue[i];
+        }
+        __syncthreads();
+    }
+}
 // Fallback for very large key ranges (more materials than fit the shared histogram): direct global atomics.
 __global__ void __launch_bounds__(256) k_sort_scatter_global(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ countPtr, uint32_t* cursor, uint32_t* __restrict__ sorted)
@@ -465,8 +512,8 @@ struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 // DirectLight (pathtrace.glsl:158-283).  Deferred mode: fills sa (env) / sb (light) with contribution*throughput.
 // Inline mode (shadow rays draw from the path RNG): traces here and returns Ld.
 template <bool GEN>
-__device__ __forceinline__ float3 directLight(const DevScene& S, const FrameParams& F, float3 rd, const Surf& sf, const Material& mat, float eta, bool isSurface,
-                                              float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+__device__ __forceinline__ float3 directLight(const DevScene& S, const FrameParams& F, float3 rd, const Surf& sf, const Material& mat, float eta, const ShadeFrame& fr,
+                                              bool isSurface, float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
 {
     float3 Ld = f3(0.0f);
     const float3 scatterPos = sf.fhp + sf.normal * PTB_EPS;
@@ -485,7 +532,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
         if (visible)
         {
             float3 f; float pdf;
-            if (isSurface) f = DisneyEval(mat, eta, -rd, sf.ffnormal, lightDir, pdf);
+            if (isSurface) f = DisneyEvalFr(mat, eta, fr, lightDir, pdf);
             else { float ph = PhaseHG(dot(-rd, lightDir), medAniso); f = f3(ph); pdf = ph; }
             if (pdf > 0.0f)
             {
@@ -515,7 +562,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
             if (visible)
             {
                 float3 f; float pdf;
-                if (isSurface) f = DisneyEval(mat, eta, -rd, sf.ffnormal, ls.direction, pdf);
+                if (isSurface) f = DisneyEvalFr(mat, eta, fr, ls.direction, pdf);
                 else { float ph = PhaseHG(dot(-rd, ls.direction), medAniso); f = f3(ph); pdf = ph; }
                 float misWeight = 1.0f;
                 if (area > 0.0f) misWeight = PowerHeuristic(ls.pdf, pdf);
@@ -624,7 +671,8 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                         thr *= mcol;
                         ro += rd * scatterDist;
                         sf.fhp = ro;
-                        rad += directLight<GEN>(S, F, rd, sf, mat, eta, false, aniso, thr, rng, sa, sb, ic) * thr;
+                        ShadeFrame noFrame;
+                        rad += directLight<GEN>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic) * thr;
                         float hr1 = rng.rand(), hr2 = rng.rand();
                         float3 scatterDir = SampleHG(-rd, aniso, hr1, hr2);
                         prevPdf = PhaseHG(dot(-rd, scatterDir), aniso);
@@ -648,10 +696,12 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
             if (!skipped)
             {
                 surfaceScatter = true;
-                rad += directLight<GEN>(S, F, rd, sf, mat, eta, true, 0.f, thr, rng, sa, sb, ic) * thr;     // :431
+                ShadeFrame fr;
+                frameSetup(mat, eta, -rd, sf.ffnormal, fr);
+                rad += directLight<GEN>(S, F, rd, sf, mat, eta, fr, true, 0.f, thr, rng, sa, sb, ic) * thr;  // :431
                 float r1 = rng.rand(), r2 = rng.rand(), r3 = rng.rand();
                 float pdf;
-                float3 f = DisneySample(mat, eta, -rd, sf.ffnormal, L, pdf, r1, r2, r3);                     // :434
+                float3 f = DisneySampleFr(mat, eta, fr, L, pdf, r1, r2, r3);                                 // :434
                 if (pdf > 0.0f) { thr *= f / pdf; prevPdf = pdf; }
                 else terminated = true;
             }
@@ -1010,6 +1060,12 @@ void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
 {
     int bps = traceBlocksPerSM(S);
     k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist);
+    g_launches++;
+}
+
+void ptbk_sort_tile_local(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted)
+{
+    k_sort_tile_local<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys);
     g_launches++;
 }
 
