@@ -596,7 +596,7 @@ __device__ __forceinline__ float3 EvalMicrofacetReflection(const Material& mat, 
 
 // DisneyEval (disney.glsl:244-351) in the local frame (T,B,N); V,L already local; p = lobeSetup(mat, eta, V.z) (depends on V only,
 // so the NEE evaluation and the evaluation of the sampled direction of one hit share it).
-__device__ __noinline__ float3 DisneyEvalLocal(const Material& mat, float eta, const Lobes& p, float3 V, float3 L, float& pdf)
+__device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta, const Lobes& p, float3 V, float3 L, float& pdf)
 {
     pdf = 0.0f;
     float3 f = f3(0.0f);
