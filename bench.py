@@ -19,18 +19,31 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 SCENE = "hyperion_rect_lights"
-W, H, TILE_W, TILE_H = 1920, 1080, 256, 144
+W, H = 1920, 1080
 SPP_PER_STEP = 32
 METRIC = "Mpath-segments/s"
+# BASELINE.json configs -> (scene blob, width, height, maxdepth override).  Tile sizes / depth come from the .scene files.
+WORKLOADS = {
+    "hyperion_rect_lights": ("hyperion_rect_lights", 1920, 1080, None),     # configs[2] — the headline (default)
+    "hyperion_sphere_light": ("hyperion_sphere_light", 1920, 1080, None),   # configs[2]
+    "cornell_box_orig": ("cornell_box_orig", 512, 512, 4),                  # configs[0]
+    "ibl_spheres": ("ibl_spheres", 1920, 1080, None),                       # configs[1] stand-in (teapot meshes + HDR are missing from the checkout)
+    "volume_cube": ("volume_cube", 1920, 1080, None),                       # configs[3]
+    "instancing": ("instancing", 3840, 2160, None),                         # configs[4]: 10 001 instances, depth 8, 4K
+}
 
 
-def load_workload(scene_name=SCENE, w=W, h=H):
+def load_workload(scene_name=SCENE, w=None, h=None):
     import glsl_pathtracer_b200  # noqa: F401
     from glsl_pathtracer_b200 import scene_io
-    sc = copy.deepcopy(scene_io.load_scene(scene_name))
+    blob, ww, hh, depth = WORKLOADS[scene_name]
+    global W, H
+    W, H = (w or ww), (h or hh)
+    sc = copy.deepcopy(scene_io.load_scene(blob))
     ro = sc.renderOptions
-    ro.renderResolution = (w, h); ro.windowResolution = (w, h)
-    ro.tileWidth, ro.tileHeight = TILE_W, TILE_H          # the hyperion file's tiles (hyperion_rect_lights.scene:5-6)
+    ro.renderResolution = (W, H); ro.windowResolution = (W, H)     # tiles stay the .scene file's (hyperion: 256x144)
+    if depth is not None:
+        ro.maxDepth = depth
     return sc
 
 
@@ -109,7 +122,7 @@ def cpu_baseline(sc, spp=2):
     dt = time.time() - t0
     st = o.stats(); o.close()
     return {"value": st["closestRays"] / dt / 1e6, "unit": METRIC, "spp_per_s": spp / dt, "cores": ob.lib().orc_num_threads(), "kind": "port",
-            "sample": f"{spp} full-frame sample passes of the same 1920x1080 workload ({dt:.1f} s wall)",
+            "sample": f"{spp} full-frame sample passes of the same {W}x{H} workload ({dt:.1f} s wall)",
             "note": "reference GLSL under Mesa llvmpipe is not runnable in this image (no GL/Mesa/Xvfb); the oracle is a compiled C++ restatement, "
                     "expected to be faster than llvmpipe-JIT GLSL"}
 
@@ -126,7 +139,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sc = load_workload()
+    sc = load_workload(args.workload)
     from oracle import binding as ob
     o = ob.Oracle(sc)
     spp_step = 1                       # bounded sample per step: one full-frame pass
@@ -142,10 +155,10 @@ def run_reference(args):
     cores = ob.lib().orc_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "spp_per_s": args.steps * spp_step / dt, "n_gpus": 0,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "in-repo scene fixture (hyperion_rect_lights)",
+            "vs_baseline": None, "dtype": "f32", "data": f"scene fixture built by the reference host code ({sc.name})",
             "config": workload_config(sc, {"reference_step": "1 full-frame sample pass per step (bounded sample of the same workload)"}),
             "cpu_baseline": {"value": val, "unit": METRIC, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} x 1 full-frame 1080p sample pass on {cores} host threads"},
+                             "sample": f"{args.steps} x 1 full-frame {W}x{H} sample pass on {cores} host threads"},
             "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -161,7 +174,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sc = load_workload()
+    sc = load_workload(args.workload)
     ctx = capi.Context(sc, device=local, samples_per_wave=args.samples_per_wave)
     ctx.set_cull(args.cull)
     stream = torch.cuda.Stream(device=local)
@@ -234,13 +247,12 @@ def run_ours(args):
         peak, peak_src = peaks()
         ab = algorithmic_bytes(sc)
         rays_last_step = segs / args.steps / world          # rank-0 share of one step
-        n_trace_launches = (sc.renderOptions.maxDepth + 1) * max(1, -(-SPP_PER_STEP // max(1, ctx.opts.samplesPerWave or 4)))
         bytes_per_ray = ab["culled" if args.cull else "unculled"]["closest"]
         achieved = rays_last_step * bytes_per_ray / (trace_ms_last * 1e-3) / 1e9 if trace_ms_last > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "in-repo scene fixture (hyperion_rect_lights), reference RNG/frame schedule",
+            "data": f"scene fixture built by the reference host code ({sc.name}), reference RNG/frame schedule",
             "config": workload_config(sc, {"parallelism": f"sample-range sharding x{world}, NCCL reduce per readback", "cull_boxes": bool(args.cull)}),
             "spp_per_s": total_spp / (ms * 1e-3), "mshadow_rays_per_s": shadows / (ms * 1e-3) / 1e6, "mrays_per_s": (segs + shadows) / (ms * 1e-3) / 1e6,
             "e2e": {"value": e2e_segs / (e2e_ms * 1e-3) / 1e6, "unit": METRIC, "spp_per_s": e2e_steps * SPP_PER_STEP * world / (e2e_ms * 1e-3),
@@ -272,8 +284,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cull", type=int, default=1)
-    ap.add_argument("--samples-per-wave", type=int, default=8)
+    ap.add_argument("--samples-per-wave", type=int, default=0, help="0 = library default (~16 M paths in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default=SCENE, choices=sorted(WORKLOADS))
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

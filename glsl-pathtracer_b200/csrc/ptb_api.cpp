@@ -699,9 +699,9 @@ int ptb_render_samples(PtbCtx* c, int32_t firstSample, int32_t nSamples, int32_t
     const FrameParams& F = c->F;
     int spw = c->opts.samplesPerWave;
     if (spw <= 0)
-    {   // auto: keep ~8M paths in flight (fills 148 SMs many times over, bounds state to ~1.5 GB)
+    {   // auto: keep ~16 M paths in flight (amortises the launch tails of the deep bounces; ~3 GB of path state)
         size_t px = (size_t)F.renderW * F.renderH;
-        spw = (int)std::max<size_t>(1, std::min<size_t>(16, (8u << 20) / std::max<size_t>(px, 1)));
+        spw = (int)std::max<size_t>(1, std::min<size_t>(16, ((16u << 20) + px / 2) / std::max<size_t>(px, 1)));
     }
     beginTiming(c);
     int done = 0;
