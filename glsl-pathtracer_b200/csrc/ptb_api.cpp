@@ -268,6 +268,7 @@ void refreshFrameParams(PtbCtx* c)
     F.invNumTilesX = (float)o.tileW / o.renderW; F.invNumTilesY = (float)o.tileH / o.renderH;           // Renderer.cpp:293-294
     F.numTilesX = (int)ceilf((float)o.renderW / o.tileW); F.numTilesY = (int)ceilf((float)o.renderH / o.tileH);   // :296-297
     memcpy(F.camPos, cam.position, 12); memcpy(F.camRight, cam.right, 12); memcpy(F.camUp, cam.up, 12); memcpy(F.camFwd, cam.forward, 12);
+    F.aspect = (float)o.renderH / (float)o.renderW;
     F.camScale = tanf(cam.fov * 0.5f); F.camFocalDist = cam.focalDist; F.camAperture = cam.aperture;
     refreshDerivedFlags(c);
 }

@@ -83,7 +83,9 @@ struct Rng
         x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
         x += y * w; y += z * x; z += x * y; w += y * z;
         s = make_uint4(x, y, z, w);
-        return __fdiv_rn(__uint2float_rn(x), 4294967296.0f);   // float(seed.x) / float(0xffffffffu): in [0,1]
+        // float(seed.x) / float(0xffffffffu), in [0,1]: float(0xffffffff) rounds to 2^32 and dividing by a power of two is the
+        // same IEEE result as multiplying by 2^-32
+        return __fmul_rn(__uint2float_rn(x), 2.3283064365386963e-10f);
     }
 };
 
@@ -511,6 +513,7 @@ __device__ __forceinline__ void SampleOneLight(const DevScene& S, int idx, float
     const float4* p = S.lightsPre + (size_t)idx * 8;
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), dd = __ldg(p + 3);
     float3 position = f3(a), emission = f3(b), u = f3(c), v = f3(dd);
+    (void)v;
     int type = (int)a.w; area = b.w; float radius = c.w;
     float nl = (float)S.numLights;
     if (type == 0)
@@ -521,7 +524,7 @@ __device__ __forceinline__ void SampleOneLight(const DevScene& S, int idx, float
         ls.dist = length(ls.direction);
         float distSq = ls.dist * ls.dist;
         ls.direction /= ls.dist;
-        ls.normal = normalize(cross(u, v));
+        ls.normal = f3(__ldg(p + 4));                 // normalize(cross(u, v)), evaluated once at upload
         ls.emission = emission * nl;
         ls.pdf = distSq / (area * fabsf(dot(ls.normal, ls.direction)));
     }

@@ -60,6 +60,7 @@ struct FrameParams
     // camera
     float camPos[3], camRight[3], camUp[3], camFwd[3];
     float camScale /* tan(fov/2), computed on the host */, camFocalDist, camAperture;
+    float aspect;        // float(renderH) / float(renderW)
     // derived switches
     int cullBoxes;       // cull child boxes whose entry distance exceeds the current hit distance
     int inlineShadow;    // shadow rays consume path RNG draws (BLEND alpha in AnyHit / EvalTransmittance) -> traced inside shade

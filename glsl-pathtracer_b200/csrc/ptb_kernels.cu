@@ -78,7 +78,7 @@ __device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams
     float dx = __fadd_rn(__fsub_rn(__fmul_rn(cx, 2.0f), 1.0f), jx);
     float dy = __fadd_rn(__fsub_rn(__fmul_rn(cy, 2.0f), 1.0f), jy);
     float scale = F.camScale;
-    dy = __fmul_rn(dy, __fmul_rn(__fdiv_rn((float)F.renderH, (float)F.renderW), scale));
+    dy = __fmul_rn(dy, __fmul_rn(F.aspect, scale));     // aspect = float(renderH) / float(renderW), one IEEE division on the host
     dx = __fmul_rn(dx, scale);
     float3 right = f3(F.camRight[0], F.camRight[1], F.camRight[2]), up = f3(F.camUp[0], F.camUp[1], F.camUp[2]),
            fwd = f3(F.camFwd[0], F.camFwd[1], F.camFwd[2]), pos = f3(F.camPos[0], F.camPos[1], F.camPos[2]);
