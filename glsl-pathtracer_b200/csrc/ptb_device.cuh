@@ -26,10 +26,13 @@ __device__ __forceinline__ float3 f3(const float4& v) { return make_float3(v.x, 
 __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+// Shading-math division: div.approx (MUFU.RCP + FMUL, 2 ulp) instead of the ~8-instruction full-range sequence; operands here are
+// BSDF terms far from the 2^126 range limit.  Hit-deciding code never uses these (it uses the x* exact intrinsics below).
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(fdiv(a.x, b.x), fdiv(a.y, b.y), fdiv(a.z, b.z)); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { const float r = fdiv(1.0f, s); return f3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float3 operator+(float3 a, float s) { return f3(a.x + s, a.y + s, a.z + s); }
 __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float3& operator+=(float3& a, float3 b) { a = a + b; return a; }
@@ -39,7 +42,7 @@ __device__ __forceinline__ float3& operator/=(float3& a, float s) { a = a / s; r
 __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ float3 normalize(float3 a) { return a / sqrtf(dot(a, a)); }
+__device__ __forceinline__ float3 normalize(float3 a) { const float r = rsqrtf(dot(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float3 mix(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -383,14 +386,14 @@ __device__ __forceinline__ float GTR1(float NDotH, float a)   // :25-32
     if (a >= 1.0f) return PTB_INV_PI;
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (PTB_PI * logf(a2) * t);
+    return fdiv(a2 - 1.0f, PTB_PI * logf(a2) * t);
 }
 __device__ __forceinline__ float3 SampleGTR1(float rgh, float r1, float r2)   // :34-47
 {
     float a = fmaxf(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * PTB_TWO_PI;
-    float cosTheta = sqrtf((1.0f - powf(a2, 1.0f - r2)) / (1.0f - a2));
+    float cosTheta = sqrtf(fdiv(1.0f - powf(a2, 1.0f - r2), 1.0f - a2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
     return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
@@ -399,7 +402,7 @@ __device__ __forceinline__ float3 SampleGGXVNDF(float3 V, float ax, float ay, fl
 {
     float3 Vh = normalize(f3(ax * V.x, ay * V.y, V.z));
     float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
-    float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * (1.0f / sqrtf(lensq)) : f3(1, 0, 0);
+    float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * rsqrtf(lensq) : f3(1, 0, 0);
     float3 T2 = cross(Vh, T1);
     float r = sqrtf(r1);
     float phi = 2.0f * PTB_PI * r2;
@@ -413,23 +416,23 @@ __device__ __forceinline__ float3 SampleGGXVNDF(float3 V, float ax, float ay, fl
 }
 __device__ __forceinline__ float GTR2Aniso(float NDotH, float HDotX, float HDotY, float ax, float ay)   // :90-96
 {
-    float a = HDotX / ax;
-    float b = HDotY / ay;
+    float a = fdiv(HDotX, ax);
+    float b = fdiv(HDotY, ay);
     float c = a * a + b * b + NDotH * NDotH;
-    return 1.0f / (PTB_PI * ax * ay * c * c);
+    return fdiv(1.0f, PTB_PI * ax * ay * c * c);
 }
 __device__ __forceinline__ float SmithG(float NDotV, float alphaG)   // :109-114
 {
     float a = alphaG * alphaG;
     float b = NDotV * NDotV;
-    return (2.0f * NDotV) / (NDotV + sqrtf(a + b - a * b));
+    return fdiv(2.0f * NDotV, NDotV + sqrtf(a + b - a * b));
 }
 __device__ __forceinline__ float SmithGAniso(float NDotV, float VDotX, float VDotY, float ax, float ay)   // :116-122
 {
     float a = VDotX * ax;
     float b = VDotY * ay;
     float c = NDotV;
-    return (2.0f * NDotV) / (NDotV + sqrtf(a * a + b * b + c * c));
+    return fdiv(2.0f * NDotV, NDotV + sqrtf(a * a + b * b + c * c));
 }
 __device__ __forceinline__ float SchlickWeight(float u)   // :124-129
 {
@@ -442,8 +445,8 @@ __device__ __forceinline__ float DielectricFresnel(float cosThetaI, float eta)  
     float sinThetaTSq = eta * eta * (1.0f - cosThetaI * cosThetaI);
     if (sinThetaTSq > 1.0f) return 1.0f;
     float cosThetaT = sqrtf(fmaxf(1.0f - sinThetaTSq, 0.0f));
-    float rs = (eta * cosThetaT - cosThetaI) / (eta * cosThetaT + cosThetaI);
-    float rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    float rs = fdiv(eta * cosThetaT - cosThetaI, eta * cosThetaT + cosThetaI);
+    float rp = fdiv(eta * cosThetaI - cosThetaT, eta * cosThetaI + cosThetaT);
     return 0.5f * (rs * rs + rp * rp);
 }
 __device__ __forceinline__ float3 CosineSampleHemisphere(float r1, float r2)   // :147-156
@@ -467,7 +470,7 @@ __device__ __forceinline__ float3 UniformSampleHemisphere(float r1, float r2)   
 __device__ __forceinline__ float PowerHeuristic(float a, float b)   // :173-177
 {
     float t = a * a;
-    return t / (b * b + t);
+    return fdiv(t, b * b + t);
 }
 __device__ __forceinline__ void Onb(float3 N, float3& T, float3& B)   // :179-184
 {
@@ -526,7 +529,7 @@ __device__ __forceinline__ void SampleOneLight(const DevScene& S, int idx, float
         ls.direction /= ls.dist;
         ls.normal = f3(__ldg(p + 4));                 // normalize(cross(u, v)), evaluated once at upload
         ls.emission = emission * nl;
-        ls.pdf = distSq / (area * fabsf(dot(ls.normal, ls.direction)));
+        ls.pdf = fdiv(distSq, area * fabsf(dot(ls.normal, ls.direction)));
     }
     else if (type == 1)
     {
@@ -545,7 +548,7 @@ __device__ __forceinline__ void SampleOneLight(const DevScene& S, int idx, float
         ls.direction /= ls.dist;
         ls.normal = normalize(lightSurfacePos - position);
         ls.emission = emission * nl;
-        ls.pdf = distSq / (area * 0.5f * fabsf(dot(ls.normal, ls.direction)));
+        ls.pdf = fdiv(distSq, area * 0.5f * fabsf(dot(ls.normal, ls.direction)));
     }
     else
     {
@@ -568,7 +571,7 @@ __device__ __forceinline__ void lobeSetup(const Material& m, float eta, float Vz
 {
     float lum = Luminance(m.baseColor);
     float3 ctint = lum > 0.0f ? m.baseColor / lum : f3(1.0f);
-    float F0 = (1.0f - eta) / (1.0f + eta);
+    float F0 = fdiv(1.0f - eta, 1.0f + eta);
     F0 *= F0;
     p.F0 = F0;
     p.Cspec0 = F0 * mix(f3(1.0f), ctint, m.specularTint);
@@ -582,7 +585,7 @@ __device__ __forceinline__ void lobeSetup(const Material& m, float eta, float Vz
     p.metalPr = p.metalWt * Luminance(mix(m.baseColor, f3(1.0f), schlickWt));
     p.glassPr = p.glassWt;
     p.clearCtPr = 0.25f * m.clearcoat;
-    float invTotalWt = 1.0f / (p.diffPr + p.dielectricPr + p.metalPr + p.glassPr + p.clearCtPr);
+    float invTotalWt = fdiv(1.0f, p.diffPr + p.dielectricPr + p.metalPr + p.glassPr + p.clearCtPr);
     p.diffPr *= invTotalWt; p.dielectricPr *= invTotalWt; p.metalPr *= invTotalWt; p.glassPr *= invTotalWt; p.clearCtPr *= invTotalWt;
 }
 
@@ -593,8 +596,8 @@ __device__ __forceinline__ float3 EvalMicrofacetReflection(const Material& mat, 
     float D = GTR2Aniso(H.z, H.x, H.y, mat.ax, mat.ay);
     float G1 = SmithGAniso(fabsf(V.z), V.x, V.y, mat.ax, mat.ay);
     float G2 = G1 * SmithGAniso(fabsf(L.z), L.x, L.y, mat.ax, mat.ay);
-    pdf = G1 * D / (4.0f * V.z);
-    return F * D * G2 / (4.0f * L.z * V.z);
+    pdf = fdiv(G1 * D, 4.0f * V.z);
+    return F * fdiv(D * G2, 4.0f * L.z * V.z);
 }
 
 // DisneyEval (disney.glsl:244-351) in the local frame (T,B,N); V,L already local; p = lobeSetup(mat, eta, V.z) (depends on V only,
@@ -625,7 +628,7 @@ __device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta
             float Fd = (1.0f - 0.5f * FL) * (1.0f - 0.5f * FV);
             float Fss90 = 0.5f * Rr;
             float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
-            float ss = 1.25f * (Fss * (1.0f / (L.z + V.z) - 0.5f) + 0.5f);
+            float ss = 1.25f * (Fss * (fdiv(1.0f, L.z + V.z) - 0.5f) + 0.5f);
             float FH = SchlickWeight(LDotH);
             float3 Fsheen = FH * mat.sheen * p.Csheen;
             tmpPdf = L.z * PTB_INV_PI;
@@ -636,7 +639,7 @@ __device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta
     }
     if (p.dielectricPr > 0.0f && reflect)
     {
-        float F = (DielectricFresnel(VDotH, 1.0f / mat.ior) - p.F0) / (1.0f - p.F0);
+        float F = fdiv(DielectricFresnel(VDotH, fdiv(1.0f, mat.ior)) - p.F0, 1.0f - p.F0);
         f += EvalMicrofacetReflection(mat, V, L, H, mix(p.Cspec0, f3(1.0f), F), tmpPdf) * p.dielectricWt;
         pdf += tmpPdf * p.dielectricPr;
     }
@@ -668,9 +671,9 @@ __device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta
                 float denom = LDotH + VDotH2 * eta;
                 denom *= denom;
                 float eta2 = eta * eta;
-                float jacobian = fabsf(LDotH) / denom;
-                tmpPdf = G1 * fmaxf(0.0f, VDotH2) * D * jacobian / V.z;
-                fr = vpow(mat.baseColor, 0.5f) * (f3(1.0f) - f3(F)) * D * G2 * fabsf(VDotH2) * jacobian * eta2 / fabsf(L.z * V.z);
+                float jacobian = fdiv(fabsf(LDotH), denom);
+                tmpPdf = fdiv(G1 * fmaxf(0.0f, VDotH2) * D * jacobian, V.z);
+                fr = vpow(mat.baseColor, 0.5f) * (f3(1.0f) - f3(F)) * fdiv(D * G2 * fabsf(VDotH2) * jacobian * eta2, fabsf(L.z * V.z));
             }
             f += fr * p.glassWt;
             pdf += tmpPdf * p.glassPr * (1.0f - F);
@@ -686,7 +689,7 @@ __device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta
             float F = mixf(0.04f, 1.0f, SchlickWeight(VDotH2));
             float D = GTR1(H.z, mat.clearcoatRoughness);
             float G = SmithG(L.z, 0.25f) * SmithG(V.z, 0.25f);
-            float jacobian = 1.0f / (4.0f * VDotH2);
+            float jacobian = fdiv(1.0f, 4.0f * VDotH2);
             tmpPdf = D * H.z * jacobian;
             fc = f3(F) * D * G;
         }
@@ -739,7 +742,7 @@ __device__ __forceinline__ float3 DisneySampleFr(const Material& mat, float eta,
         float3 H = SampleGGXVNDF(V, mat.ax, mat.ay, r1, r2);
         float F = DielectricFresnel(fabsf(dot(V, H)), eta);
         if (H.z < 0.0f) H = -H;
-        r3 = (r3 - cdf2) / (cdf3 - cdf2);
+        r3 = fdiv(r3 - cdf2, cdf3 - cdf2);
         if (r3 < F) L = normalize(reflect(-V, H));
         else L = normalize(refract(-V, H, eta));
     }
@@ -777,7 +780,7 @@ __device__ __forceinline__ void materialFromRow(const float4* P, Material& mat, 
 __device__ __forceinline__ void materialFinish(Material& mat)
 {
     float aspect = sqrtf(1.0f - mat.anisotropic * 0.9f);
-    mat.ax = fmaxf(0.001f, mat.roughness / aspect);
+    mat.ax = fmaxf(0.001f, fdiv(mat.roughness, aspect));
     mat.ay = fmaxf(0.001f, mat.roughness * aspect);
 }
 

@@ -773,12 +773,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
     const uint32_t n = ctrThis[CTR_NPATHS];
     const uint32_t lane = threadIdx.x & 31u;
     InlineCounters ic{0u, 0u};
+    uint32_t nextBase = 0;
+    if (lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);
     while (true)
     {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t base = __shfl_sync(0xffffffffu, nextBase, 0);
         if (base >= n) break;
+        if (lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);      // prefetch the next chunk index
         const uint32_t i = base + lane;
         bool cont = false;
         ShadowOut sa, sb; sa.valid = false; sb.valid = false;
