@@ -251,7 +251,9 @@ void refreshDerivedFlags(PtbCtx* c)
         if (m[4] != 0.f || m[5] != 0.f || m[6] != 0.f || m[27] >= 0.f) anyEmission = true;
     }
     FrameParams& F = c->F;
-    F.general = ((f & (PTB_OPT_ENVMAP | PTB_OPT_MEDIUM | PTB_OPT_ALPHA_TEST | PTB_OPT_ROUGHNESS_MOLLIFICATION)) != 0u) || c->S.numTextures > 0 || anyEmission;
+    // shade specialisation: 0 = lights only, 1 = + env map / textures / emission / mollification, 2 = + media / alpha test / inline shadow rays
+    F.general = (f & (PTB_OPT_MEDIUM | PTB_OPT_ALPHA_TEST)) ? 2
+              : (((f & (PTB_OPT_ENVMAP | PTB_OPT_ROUGHNESS_MOLLIFICATION)) != 0u) || c->S.numTextures > 0 || anyEmission) ? 1 : 0;
     F.inlineShadow = (((f & PTB_OPT_ALPHA_TEST) && !(f & PTB_OPT_MEDIUM) && anyBlend) || ((f & PTB_OPT_MEDIUM) && (f & PTB_OPT_VOL_MIS))) ? 1 : 0;
 }
 

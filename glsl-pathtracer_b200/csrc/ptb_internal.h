@@ -64,7 +64,7 @@ struct FrameParams
     // derived switches
     int cullBoxes;       // cull child boxes whose entry distance exceeds the current hit distance
     int inlineShadow;    // shadow rays consume path RNG draws (BLEND alpha in AnyHit / EvalTransmittance) -> traced inside shade
-    int general;         // 0: lights-only fast specialisation is valid
+    int general;         // shade kernel specialisation: 0 lights only, 1 + env/textures/emission, 2 + media/alpha/inline shadows
 };
 
 // One wavefront: S sample passes of a pixel rectangle.

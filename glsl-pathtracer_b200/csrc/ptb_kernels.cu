@@ -368,11 +368,12 @@ __device__ __forceinline__ void triangleSurface(const DevScene& S, int slot, int
 }
 
 // GetMaterial (pathtrace.glsl:25-115).  prevRoughness = state.mat.roughness of the previous call (mollification).
-template <bool GEN>
+template <int MODE>
 __device__ __forceinline__ void getMaterial(const DevScene& S, const FrameParams& F, Surf& sf, float3 rd, int depth, float prevRoughness, Material& mat, float& eta)
 {
     int4 tex;
     materialFromRow(S.materials + (size_t)sf.matID * 8, mat, tex);
+    constexpr bool GEN = MODE >= 1;
     if (GEN)
     {
         if (tex.x >= 0)
@@ -492,7 +493,7 @@ __device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameP
         int kind = closestFull(S, F, ro, rd, 0, sf, ic);
         if (kind != 1) break;                       // miss or emitter
         Material mat; float eta;
-        getMaterial<true>(S, F, sf, rd, 0, 0.f, mat, eta);
+        getMaterial<2>(S, F, sf, rd, 0, 0.f, mat, eta);
         bool alphatest = (mat.alphaMode == 2 && mat.opacity < mat.alphaCutoff) || (mat.alphaMode == 1 && rng.rand() > mat.opacity);
         bool refractive = (1.0f - mat.metallic) * mat.specTrans > 0.0f;
         if (!(alphatest || refractive)) return f3(0.0f);
@@ -511,14 +512,15 @@ struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 
 // DirectLight (pathtrace.glsl:158-283).  Deferred mode: fills sa (env) / sb (light) with contribution*throughput.
 // Inline mode (shadow rays draw from the path RNG): traces here and returns Ld.
-template <bool GEN>
+template <int MODE>
 __device__ __forceinline__ float3 directLight(const DevScene& S, const FrameParams& F, float3 rd, const Surf& sf, const Material& mat, float eta, const ShadeFrame& fr,
                                               bool isSurface, float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
 {
     float3 Ld = f3(0.0f);
     const float3 scatterPos = sf.fhp + sf.normal * PTB_EPS;
-    const bool volMis = GEN && OPT(F, O_MEDIUM) && OPT(F, O_VOLMIS);
-    const bool inl = GEN && F.inlineShadow;
+    constexpr bool GEN = MODE >= 1, FULL = MODE == 2;       // FULL: media, alpha test, RNG-consuming (inline) shadow rays
+    const bool volMis = FULL && OPT(F, O_MEDIUM) && OPT(F, O_VOLMIS);
+    const bool inl = FULL && F.inlineShadow;
 
     if (GEN && OPT(F, O_ENVMAP) && !OPT(F, O_UNIFORM))
     {
@@ -579,7 +581,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
 }
 
 // One iteration of the PathTrace loop body after ClosestHit (pathtrace.glsl:303-471) for path slot p.
-template <bool GEN>
+template <int MODE>
 __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool firstIter, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
 {
     const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], hit4 = P.hit[p];
@@ -591,6 +593,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
     bool inMedium = (fl & PTB_FLAG_INMEDIUM) != 0u, surfaceScatter = (fl & PTB_FLAG_SURFSCAT) != 0u;
     float3 ro = f3(ro4), rd = f3(rd4), thr = f3(thr4), rad = f3(rad4);
     float alpha = rad4.w, prevPdf = ro4.w, prevRough = thr4.w;
+    constexpr bool GEN = MODE >= 1, FULL = MODE == 2;
     cont = false;
 
     if (hitInst == -1)      // miss: pathtrace.glsl:305-339
@@ -604,7 +607,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                 float4 e = EvalEnvMap(S, F, rd);
                 float misWeight = 1.0f;
                 if (depth > 0) misWeight = PowerHeuristic(prevPdf, e.w);
-                if (OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
+                if (FULL && OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
                 if (misWeight > 0) rad += misWeight * f3(e) * thr * F.envMapIntensity;
             }
         }
@@ -616,7 +619,8 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
     Surf sf;
     Material mat; float eta = 1.0f;
     float4 med = make_float4(0.f, 0.f, 0.f, 0.f), medCol = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (GEN) { med = P.med[p]; medCol = P.medCol[p]; }
+    if (GEN) med = P.med[p];            // .w carries the previous matID
+    if (FULL) medCol = P.medCol[p];
 
     if (hitInst <= -2)      // analytic light hit: pathtrace.glsl:341-364 with the stale matID/texCoord of SURVEY Q2
     {
@@ -633,7 +637,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
         lightHitInfo(S, li, ro, rd, t, lpdf, lem);
         float misWeight = 1.0f;
         if (depth > 0) misWeight = PowerHeuristic(prevPdf, lpdf);
-        if (GEN && OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
+        if (FULL && OPT(F, O_MEDIUM) && !OPT(F, O_VOLMIS)) { if (!surfaceScatter) misWeight = 1.0f; }
         rad += misWeight * lem * thr;
         P.rad[p] = make_float4(rad.x, rad.y, rad.z, alpha);
         return;
@@ -643,7 +647,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
         const int slot = __float_as_int(hit4.w);
         int matID = __float_as_int(__ldg(S.instTrav + (size_t)hitInst * 4 + 1).w);
         triangleSurface(S, slot, hitInst, hit4.y, hit4.z, ro, rd, t, GEN, GEN && materialNeedsTangents(S, matID), sf);
-        getMaterial<GEN>(S, F, sf, rd, depth, prevRough, mat, eta);
+        getMaterial<MODE>(S, F, sf, rd, depth, prevRough, mat, eta);
     }
     if (GEN) rad += mat.emission * thr;                      // pathtrace.glsl:344
 
@@ -652,7 +656,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
 
     if (!terminated)
     {
-        if (GEN && OPT(F, O_MEDIUM))                          // :370-410
+        if (FULL && OPT(F, O_MEDIUM))                         // :370-410
         {
             surfaceScatter = false;
             if (inMedium)
@@ -672,7 +676,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                         ro += rd * scatterDist;
                         sf.fhp = ro;
                         ShadeFrame noFrame;
-                        rad += directLight<GEN>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic) * thr;
+                        rad += directLight<MODE>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic) * thr;
                         float hr1 = rng.rand(), hr2 = rng.rand();
                         float3 scatterDir = SampleHG(-rd, aniso, hr1, hr2);
                         prevPdf = PhaseHG(dot(-rd, scatterDir), aniso);
@@ -685,7 +689,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
         {
             bool skipped = false;
             float3 L = rd;
-            if (GEN && OPT(F, O_ALPHA))                       // :416-426
+            if (FULL && OPT(F, O_ALPHA))                      // :416-426
             {
                 if ((mat.alphaMode == 2 && mat.opacity < mat.alphaCutoff) || (mat.alphaMode == 1 && rng.rand() > mat.opacity))
                 {
@@ -698,7 +702,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                 surfaceScatter = true;
                 ShadeFrame fr;
                 frameSetup(mat, eta, -rd, sf.ffnormal, fr);
-                rad += directLight<GEN>(S, F, rd, sf, mat, eta, fr, true, 0.f, thr, rng, sa, sb, ic) * thr;  // :431
+                rad += directLight<MODE>(S, F, rd, sf, mat, eta, fr, true, 0.f, thr, rng, sa, sb, ic) * thr;  // :431
                 float r1 = rng.rand(), r2 = rng.rand(), r3 = rng.rand();
                 float pdf;
                 float3 f = DisneySampleFr(mat, eta, fr, L, pdf, r1, r2, r3);                                 // :434
@@ -709,7 +713,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
             {
                 rd = L;
                 ro = sf.fhp + rd * PTB_EPS;                   // :442-443
-                if (GEN && OPT(F, O_MEDIUM))                  // :447-458
+                if (FULL && OPT(F, O_MEDIUM))                 // :447-458
                 {
                     if (dot(rd, sf.normal) < 0 && mat.medType != 0)
                     {
@@ -744,7 +748,8 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
         if (GEN)
         {
             med.w = __int_as_float(sf.matID);
-            P.med[p] = med; P.medCol[p] = medCol; P.prevUV[p] = sf.uv;
+            P.med[p] = med; P.prevUV[p] = sf.uv;
+            if (FULL) P.medCol[p] = medCol;
         }
         cont = true;
     }
@@ -766,7 +771,7 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
     }
 }
 
-template <bool GEN, int MINB>
+template <int MODE, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
                                                           uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
 {
@@ -787,7 +792,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
         if (i < n)
         {
             p = queue[i];
-            shadePath<GEN>(S, F, P, p, firstIter != 0, cont, sa, sb, ic);
+            shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic);
         }
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (m)
@@ -797,10 +802,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             b = __shfl_sync(0xffffffffu, b, 0);
             if (cont) nextQueue[b + __popc(m & ((1u << lane) - 1u))] = p;
         }
-        if (GEN) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
+        if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
         pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
     }
-    if (GEN && (ic.segs | ic.shadows))
+    if (MODE == 2 && (ic.segs | ic.shadows))
     {
         atomicAdd(&stats->pathSegments, (unsigned long long)ic.segs);
         atomicAdd(&stats->shadowRays, (unsigned long long)ic.shadows);
@@ -1082,21 +1087,17 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
 {
-    static int bpsGen = 0, bpsFast = 0, occ = 0;
-    if (!bpsGen)
+    static int bps[3] = {0, 0, 0};
+    if (!bps[0])
     {
-        const char* e = getenv("PTB_SHADE_OCC");      // tuning knob: resident 128-thread blocks per SM the fast shade kernel is compiled for
-        occ = e ? atoi(e) : 4;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsGen, k_shade<true, 3>, SHADE_THREADS, 0);
-        if (occ >= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 8>, SHADE_THREADS, 0);
-        else if (occ >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 6>, SHADE_THREADS, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsFast, k_shade<false, 4>, SHADE_THREADS, 0);
-        if (bpsGen < 1) bpsGen = 1; if (bpsFast < 1) bpsFast = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 4>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 3>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 3>, SHADE_THREADS, 0);
+        for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
     }
-    if (F.general) k_shade<true, 3><<<c.numSMs * bpsGen, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else if (occ >= 8) k_shade<false, 8><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else if (occ >= 6) k_shade<false, 6><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else k_shade<false, 4><<<c.numSMs * bpsFast, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    if (F.general == 2) k_shade<2, 3><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else if (F.general == 1) k_shade<1, 3><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     g_launches++;
 }
 
