@@ -1092,10 +1092,10 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
     {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 4>, SHADE_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 4>, SHADE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 3>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 4>, SHADE_THREADS, 0);
         for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
     }
-    if (F.general == 2) k_shade<2, 3><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     else if (F.general == 1) k_shade<1, 4><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     g_launches++;
