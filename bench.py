@@ -135,6 +135,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload):
+    """DRAM bytes of the dominant kernel per step from the committed ncu capture (profiles/), headline workload only."""
+    p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
+    if workload == SCENE and os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["k_trace_dram_bytes_per_step"])
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -261,7 +270,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit two-level BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak if achieved else None), "traffic": measured_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": rays_last_step * bytes_per_ray,
+                         "traffic_note": "dram bytes of all k_trace launches of one step (ncu, profiles/r01_trace_traffic.json); achieved/algorithmic are per step as well",
                          "bytes_per_ray_culled": ab["culled"]["closest"], "bytes_per_ray_unculled": ab["unculled"]["closest"],
                          "bytes_per_shadow_ray": ab["culled"]["any"], "rays_per_step": rays_last_step, "trace_ms_per_step": trace_ms_last,
                          "mrays_per_s_kernel": (rays_last_step / (trace_ms_last * 1e-3) / 1e6 if trace_ms_last > 0 else None),
