@@ -50,6 +50,10 @@ template <class T> struct DevBuf
         return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }          // temporaries in the parity entry points are freed on every return path
 };
 
 // inverse(mat4) of the row-major reference Mat4 (adjugate / determinant, fp32, no contraction) — the GLSL `inverse(transMat)`

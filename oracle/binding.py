@@ -68,6 +68,7 @@ def lib():
         L.orc_render_samples.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_render_samples_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_render_tile.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_render_preview.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_get_stats.argtypes = [C.c_void_p, C.POINTER(OrcStats)]
         L.orc_reset_stats.argtypes = [C.c_void_p]
@@ -179,6 +180,11 @@ class Oracle:
         else:
             lib().orc_render_samples_rect(self.h, first_sample, n_samples, *rect, accum.ctypes.data)
         return accum
+
+    def render_preview(self, w, h):
+        out = np.zeros((h, w, 4), np.float32)
+        lib().orc_render_preview(self.h, w, h, out.ctypes.data)
+        return out
 
     def render_tile(self, tx, ty, frame, accum):
         lib().orc_render_tile(self.h, tx, ty, frame, accum.ctypes.data)

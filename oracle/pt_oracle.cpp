@@ -1603,6 +1603,44 @@ void orc_camera_rays(OrcCtx* h, int32_t sample, float* rays)
         }
 }
 
+// preview.glsl:41-71 (+ Renderer.cpp:555-560,798): low-resolution 1-spp image, InitRNG(gl_FragCoord.xy, 1), TexCoords over the whole
+// target, `resolution` uniform = the full render size, maxDepth forced to 2 by the caller of the shader; no accumulation.
+void orc_render_preview(OrcCtx* h, int32_t w, int32_t hgt, float* out)
+{
+    OrcOptions o2 = h->o;
+    o2.maxDepth = 2;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < hgt; y++)
+        for (int x = 0; x < w; x++)
+        {
+            Ctx c{h, &o2, Rng{}, nullptr};
+            const OrcOptions& o = o2;
+            c.rng.init((float)x + 0.5f, (float)y + 0.5f, 1);
+            float r1 = 2.0f * c.rand();
+            float r2 = 2.0f * c.rand();
+            vec2 jitter;
+            jitter.x = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
+            jitter.y = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
+            jitter.x /= ((float)o.renderW * 0.5f); jitter.y /= ((float)o.renderH * 0.5f);
+            vec2 tc = {((float)x + 0.5f) / (float)w, ((float)y + 0.5f) / (float)hgt};
+            vec2 d = {(2.0f * tc.x - 1.0f) + jitter.x, (2.0f * tc.y - 1.0f) + jitter.y};
+            float scale = tanf(o.camFov * 0.5f);
+            d.y *= (float)o.renderH / (float)o.renderW * scale;
+            d.x *= scale;
+            vec3 right = {o.camRight[0], o.camRight[1], o.camRight[2]}, up = {o.camUp[0], o.camUp[1], o.camUp[2]},
+                 fwd = {o.camForward[0], o.camForward[1], o.camForward[2]}, pos = {o.camPosition[0], o.camPosition[1], o.camPosition[2]};
+            vec3 rayDir = normalize(d.x * right + d.y * up + fwd);
+            vec3 focalPoint = o.camFocalDist * rayDir;
+            float cam_r1 = c.rand() * TWO_PI;
+            float cam_r2 = c.rand() * o.camAperture;
+            vec3 randomAperturePos = (cosf(cam_r1) * right + sinf(cam_r1) * up) * sqrtf(cam_r2);
+            vec3 finalRayDir = normalize(focalPoint - randomAperturePos);
+            vec4 px = PathTrace(c, Ray{pos + randomAperturePos, finalRayDir});
+            float* a = &out[((size_t)y * w + x) * 4];
+            a[0] = px.x; a[1] = px.y; a[2] = px.z; a[3] = px.w;
+        }
+}
+
 void orc_render_samples(OrcCtx* h, int32_t firstSample, int32_t nSamples, float* accum)
 {
     renderRect(h, firstSample, nSamples, 0, 0, h->o.renderW, h->o.renderH, accum, -1, -1, -1);

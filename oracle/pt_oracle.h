@@ -103,6 +103,9 @@ void orc_render_samples_rect(OrcCtx*, int32_t firstSample, int32_t nSamples, int
 /* One Renderer::Render() tile draw (Renderer.cpp:566-580). */
 void orc_render_tile(OrcCtx*, int32_t tx, int32_t ty, int32_t frameNum, float* accum);
 
+/* preview.glsl:41-71: w x h preview (1 spp, depth 2, frame 1), out = w*h*4 floats, no accumulation. */
+void orc_render_preview(OrcCtx*, int32_t w, int32_t h, float* out);
+
 /* tonemap.glsl:97-133 + GL float->unorm8 conversion; out RGBA8, row 0 = bottom. */
 void orc_tonemap(const float* accum, int32_t w, int32_t h, float invSampleCounter, int32_t enableTonemap, int32_t enableAces,
                  int32_t simpleAcesFit, const float* backgroundCol, int32_t optBackground, int32_t optTransparentBackground, uint8_t* out);

@@ -220,11 +220,15 @@ def test_renderer_state_machine_matches_reference_semantics(oracle_mod):
     orc.close()
 
 
-def test_preview_matches_oracle_convention():
-    sc = scene_at("cornell_box_orig", 128, 128, 64, 64)
-    ctx = _ctx(sc)
+def test_preview_matches_oracle(oracle_mod):
+    """preview.glsl: quarter-resolution, frame 1 seeds, full-resolution jitter scale, depth forced to 2 (Renderer.cpp:798)."""
+    sc = scene_at("cornell_box_orig", 128, 128, 64, 64, 5)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
     p = ctx.render_preview(32, 32)
+    o = orc.render_preview(32, 32)
     assert p.shape == (32, 32, 4) and np.isfinite(p).all() and p[..., :3].max() > 0
+    assert rel_mse(o, p) <= 1e-3 and np.isclose(p, o, rtol=1e-3, atol=1e-4).all(axis=-1).mean() > 0.95
+    orc.close()
     # the preview never touches the accumulation buffer (Renderer.cpp:555-560)
     assert not ctx.read_accum().any()
     ctx.close()
@@ -250,3 +254,36 @@ def test_update_instances_moves_geometry(oracle_mod):
     assert np.array_equal(o["matID"], after["matID"]) and np.array_equal(o["t"].view(np.uint32), after["t"].view(np.uint32))
     assert ctx.read_nodes().tobytes() == sc2.nodes.tobytes()
     ctx.close(); orc.close()
+
+
+# ---------------------------------------------------------------- full BASELINE size ---------------------------------
+def test_full_size_hyperion_1080p(oracle_mod):
+    """BASELINE configs[2] at its real size: primary-ray hits bit-exact for all 2 073 600 pixels, a 2-spp RNG-matched image against the
+    oracle, and size-independent properties of the wavefront (strided shards sum to the whole; tile passes equal a whole-frame pass)."""
+    sc = scene_at("hyperion_rect_lights", 1920, 1080)
+    assert (sc.renderOptions.tileWidth, sc.renderOptions.tileHeight, sc.renderOptions.maxDepth) == (256, 144, 3)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc); orc_c = oracle_mod.Oracle(sc, cull=True)
+    rays = orc.camera_rays(1)
+    assert np.array_equal(ctx.camera_rays(1).view(np.uint32), rays.view(np.uint32))
+    g, o = ctx.trace_closest(rays), orc_c.trace_closest(rays)
+    for f in ("kind", "instance", "matID", "primSlot", "triIDx", "lightIdx"):
+        assert np.array_equal(g[f], o[f]), f
+    assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+    ctx.set_cull(False)
+    g2, o2 = ctx.trace_closest(rays), orc.trace_closest(rays)
+    assert g2.tobytes() == o2.tobytes()
+    ctx.set_cull(True)
+    ctx.render_samples(1, 2)
+    a = ctx.read_accum()
+    ref = orc.render(1, 2)
+    assert rel_mse(ref / 2, a / 2) <= 1e-3
+    assert np.isclose(a[..., :3], ref[..., :3], rtol=1e-3, atol=1e-4).all(axis=-1).mean() > 0.97
+    # shards: pass 1 on one context + pass 2 on another == both passes on one
+    s1 = _ctx(sc); s1.render_samples(1, 1, 2); s2 = _ctx(sc); s2.render_samples(2, 1, 2)
+    np.testing.assert_allclose(s1.read_accum() + s2.read_accum(), a, rtol=1e-6, atol=1e-6)
+    # one over-hanging tile (top-right: 128 x 72 visible pixels of a 256 x 144 tile) equals the same rectangle of a whole-frame pass
+    t = _ctx(sc); t.render_tile(7, 7, 2 + 7)          # first tile of the schedule is (0,7); (7,7) is ordinal 7 of pass 1
+    ta = t.read_accum()
+    assert ta[1008:, 1792:].tobytes() == s1.read_accum()[1008:, 1792:].tobytes() and not ta[:1008].any()
+    for c in (ctx, s1, s2, t): c.close()
+    orc.close(); orc_c.close()
