@@ -6,7 +6,7 @@ One "step" = one pass of the hot path over one batch: SPP_PER_STEP full-frame sa
 frameNum schedule) rendered by the CUDA wavefront pipeline through the C ABI.
 
   python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched with torchrun, one rank per GPU)
-  python bench.py --impl reference ...                      the CPU oracle (restated reference shader) on the host cores
+  python bench.py --impl reference ...                      the reference's own shader text compiled for the host (oracle/glsl_ref)
 
 The JSON line carries `roofline` (dominant kernel = closest-hit traversal, algorithmic bytes from the instrumented oracle
 on a bounded sample of the same workload), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
@@ -113,18 +113,41 @@ def algorithmic_bytes(sc, rect=None):
     return out
 
 
+def reference_arm(sc):
+    """The reference's own shader text compiled for the host (oracle/_ref/glsl_ref, built by __graft_entry__.build() where
+    /root/reference exists; the prebuilt object travels to the GPU box).  None if no object for this option set is available."""
+    try:
+        from oracle.glsl_ref import binding as gb
+        return gb.GlslRef(sc)
+    except (FileNotFoundError, OSError, RuntimeError):
+        return None
+
+
 def cpu_baseline(sc, spp=2):
-    """The oracle (CPU restatement of the reference shader, OpenMP over all host cores) on a bounded sample: spp full-frame passes."""
+    """CPU baseline on a bounded sample (spp full-frame passes, all host threads).  kind "reference": the reference's own
+    tile.glsl (+common/*.glsl) compiled by g++ -O2 (oracle/glsl_ref); the oracle port (hand-written restatement, bit-identical
+    output, so identical path segments) is timed beside it and counts the segments."""
     from oracle import binding as ob
     o = ob.Oracle(sc)
     t0 = time.time()
     o.render(1, spp)
-    dt = time.time() - t0
+    dt_port = time.time() - t0
     st = o.stats(); o.close()
-    return {"value": st["closestRays"] / dt / 1e6, "unit": METRIC, "spp_per_s": spp / dt, "cores": ob.lib().orc_num_threads(), "kind": "port",
+    cores = ob.lib().orc_num_threads()
+    port = {"value": st["closestRays"] / dt_port / 1e6, "spp_per_s": spp / dt_port}
+    g = reference_arm(sc)
+    note = ("reference GLSL under Mesa llvmpipe is not runnable in this image (no GL/Mesa/Xvfb); instead the reference's own shader text is "
+            "compiled for the host by g++ (oracle/glsl_ref) and run on all host threads")
+    if g is None:
+        return {"value": port["value"], "unit": METRIC, "spp_per_s": port["spp_per_s"], "cores": cores, "kind": "port",
+                "sample": f"{spp} full-frame sample passes of the same {W}x{H} workload ({dt_port:.1f} s wall)",
+                "note": note + "; no prebuilt reference-shader object for this option set: oracle port timed instead"}
+    t0 = time.time()
+    g.render(1, spp)
+    dt = time.time() - t0
+    return {"value": st["closestRays"] / dt / 1e6, "unit": METRIC, "spp_per_s": spp / dt, "cores": g.num_threads(), "kind": "reference",
             "sample": f"{spp} full-frame sample passes of the same {W}x{H} workload ({dt:.1f} s wall)",
-            "note": "reference GLSL under Mesa llvmpipe is not runnable in this image (no GL/Mesa/Xvfb); the oracle is a compiled C++ restatement, "
-                    "expected to be faster than llvmpipe-JIT GLSL"}
+            "oracle_port": {"value": port["value"], "spp_per_s": port["spp_per_s"], "wall_s": dt_port}, "note": note}
 
 
 def peaks():
@@ -145,28 +168,39 @@ def measured_traffic(workload):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own shader text (oracle/_ref/glsl_ref) on all host threads; the oracle port only if no
+    reference-shader object exists for this option set.  One bounded sample (1 full-frame pass) per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sc = load_workload(args.workload)
     from oracle import binding as ob
     o = ob.Oracle(sc)
+    g = reference_arm(sc)
+    kind = "reference" if g is not None else "port"
+    arm = g if g is not None else o
     spp_step = 1                       # bounded sample per step: one full-frame pass
     for _ in range(min(args.warmup, 1)):
-        o.render(1, 1, rect=(0, 0, W, 64))
+        arm.render(1, 1, rect=(0, 0, W, 64))
     o.stats(reset=True)
-    t0 = time.time()
+    dt = 0.0
     for k in range(args.steps):
-        o.render(1 + k, spp_step)
-    dt = time.time() - t0
+        t0 = time.time()
+        arm.render(1 + k, spp_step)
+        dt += time.time() - t0
+        if g is not None:
+            o.render(1 + k, spp_step)   # untimed: counts the path segments of the same passes (bit-identical paths)
     st = o.stats()
     val = st["closestRays"] / dt / 1e6
-    cores = ob.lib().orc_num_threads()
+    cores = g.num_threads() if g is not None else ob.lib().orc_num_threads()
+    what = ("the reference's tile.glsl + common/*.glsl compiled by g++ -O2 (oracle/glsl_ref)" if g is not None
+            else "oracle port (no reference-shader object for this option set)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "spp_per_s": args.steps * spp_step / dt, "n_gpus": 0,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": f"scene fixture built by the reference host code ({sc.name})",
-            "config": workload_config(sc, {"reference_step": "1 full-frame sample pass per step (bounded sample of the same workload)"}),
-            "cpu_baseline": {"value": val, "unit": METRIC, "cores": cores, "kind": "port",
+            "config": workload_config(sc, {"reference_step": "1 full-frame sample pass per step (bounded sample of the same workload)",
+                                           "reference_impl": what}),
+            "cpu_baseline": {"value": val, "unit": METRIC, "cores": cores, "kind": kind,
                              "sample": f"{args.steps} x 1 full-frame {W}x{H} sample pass on {cores} host threads"},
             "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
