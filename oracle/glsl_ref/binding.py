@@ -86,6 +86,9 @@ def _load(defines):
         L.gref_render_preview.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
         L.gref_tonemap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.gref_num_threads.restype = C.c_int
+        L.gref_trace_closest.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gref_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.gref_bsdf_eval.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         _LIBS[key] = L
     return _LIBS[key]
 
@@ -157,6 +160,27 @@ class GlslRef:
         a = np.ascontiguousarray(accum, np.float32)
         self.L.gref_tonemap(a.ctypes.data, w, h, inv_sample_counter, int(ro.enableTonemap), int(ro.enableAces), int(ro.simpleAcesFit),
                             bg.ctypes.data, out.ctypes.data)
+        return out
+
+    def trace_closest(self, rays, depth=0):
+        """The shader's own ClosestHit: (t, kind 0 miss / 1 triangle / 2 light, matID)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        t = np.zeros(len(rays), np.float32); kind = np.zeros(len(rays), np.int32); mat = np.zeros(len(rays), np.int32)
+        self.L.gref_trace_closest(rays.ctypes.data, len(rays), depth, t.ctypes.data, kind.ctypes.data, mat.ctypes.data)
+        return t, kind, mat
+
+    def trace_any(self, rays, max_dist):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        md = np.ascontiguousarray(np.broadcast_to(np.asarray(max_dist, np.float32), (len(rays),)))
+        out = np.zeros(len(rays), np.int32)
+        self.L.gref_trace_any(rays.ctypes.data, md.ctypes.data, len(rays), out.ctypes.data)
+        return out
+
+    def bsdf_eval(self, queries):
+        from oracle.binding import BSDF_QUERY_DTYPE, BSDF_RESULT_DTYPE
+        q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
+        out = np.zeros(len(q), BSDF_RESULT_DTYPE)
+        self.L.gref_bsdf_eval(q.ctypes.data, len(q), out.ctypes.data)
         return out
 
     def num_threads(self):

@@ -316,6 +316,59 @@ void gref_tonemap(const float* accum, int32_t w, int32_t h, float invSampleCount
         }
 }
 
+// ---- probes: the shader's own ClosestHit / AnyHit / DisneyEval called directly (G1 / G2 pins) -----------------------------
+// rays: n x 6 floats.  t = state.hitDist (1e6 on a miss), kind 0 miss / 1 triangle / 2 analytic light (state.isEmitter),
+// matID = state.matID for triangle hits (else -1).
+void gref_trace_closest(const float* rays, int64_t n, int32_t depth, float* t, int32_t* kind, int32_t* matID)
+{
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; i++)
+    {
+        using namespace tile_prog;
+        Ray r = Ray(vec3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), vec3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]));
+        State state; state.depth = depth; state.matID = -1;
+        LightSampleRec lightSample;
+        bool hit = ClosestHit(r, state, lightSample);
+        t[i] = hit ? state.hitDist : 1000000.0f;
+        kind[i] = !hit ? 0 : (state.isEmitter ? 2 : 1);
+        matID[i] = (hit && !state.isEmitter) ? state.matID : -1;
+    }
+}
+// AnyHit(r, maxDist) for rays whose alpha test (if compiled in) draws nothing from the RNG: MASK / OPAQUE materials.
+void gref_trace_any(const float* rays, const float* maxDist, int64_t n, int32_t* out)
+{
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; i++)
+    {
+        using namespace tile_prog;
+        Ray r = Ray(vec3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), vec3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]));
+        out[i] = AnyHit(r, maxDist[i]) ? 1 : 0;
+    }
+}
+// DisneyEval(state, V, N, L, pdf) with state.mat produced by the shader's own GetMaterial from the query's material row
+// (texture slots disabled), state.eta as given.  Serial: GetMaterial reads the materialsTex uniform.
+void gref_bsdf_eval(const OrcBsdfQuery* q, int64_t n, OrcBsdfResult* out)
+{
+    using namespace tile_prog;
+    const sampler2D saved = materialsTex;
+    for (int64_t i = 0; i < n; i++)
+    {
+        float row[32]; memcpy(row, q[i].mat, sizeof(row));
+        row[24] = row[25] = row[26] = row[27] = -1.0f;
+        materialsTex = sampler2D{row, 8, 1, 4, false};
+        State state; state.matID = 0; state.depth = 0;
+        state.normal = vec3(q[i].N[0], q[i].N[1], q[i].N[2]); state.ffnormal = state.normal;
+        Ray r = Ray(vec3(0.0f), -vec3(q[i].V[0], q[i].V[1], q[i].V[2]));
+        GetMaterial(state, r);
+        state.eta = q[i].eta;
+        float pdf = 0.0f;
+        vec3 f = DisneyEval(state, vec3(q[i].V[0], q[i].V[1], q[i].V[2]), state.ffnormal, vec3(q[i].L[0], q[i].L[1], q[i].L[2]), pdf);
+        out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf;
+        out[i].L[0] = q[i].L[0]; out[i].L[1] = q[i].L[1]; out[i].L[2] = q[i].L[2];
+    }
+    materialsTex = saved;
+}
+
 int gref_num_threads(void)
 {
 #ifdef _OPENMP

@@ -142,3 +142,47 @@ def test_translator_is_lexical_only(glsl_mod):
         return [t for t in re.findall(r"[A-Za-z_]\w*", s) if t not in drop and not re.fullmatch(r"[eE]\d*|\d+f", t)]
     a, b = idents(src), idents(out)
     assert a == b
+
+
+# ---------------------------------------------------------------- G1 / G2 pins against the shader's own functions -----------
+@pytest.mark.parametrize("name", ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light",
+                                  "volume_cube", "ibl_spheres", "instancing"])
+def test_closest_hit_and_any_hit_equal_the_shader_functions(name, glsl_mod, oracle_mod):
+    """G1 pin: the oracle's host traversal == the reference's ClosestHit / AnyHit text on primary, random (incl. axis-parallel)
+    and bounce-like rays: hit kind, material id and t bit-identical; occlusion identical."""
+    from test_gpu_trace import random_rays
+    sc = scene_at(name, 96, 54, 48, 27)
+    g = live(glsl_mod, sc); orc = oracle_mod.Oracle(sc)
+    rays = np.concatenate([orc.camera_rays(1), random_rays(sc, 30_000, 11)])
+    for depth in (0, 1):                                   # depth matters under OPT_HIDE_EMITTERS only; cheap to cover
+        o = orc.trace_closest(rays, depth)
+        t, kind, mat = g.trace_closest(rays, depth)
+        assert np.array_equal(kind, o["kind"])
+        assert np.array_equal(t.view(np.uint32), o["t"].view(np.uint32))
+        tri = kind == 1
+        assert np.array_equal(mat[tri], o["matID"][tri])
+    # bounce-like rays: leave the first hit point in a random direction; shadow-like: bounded by a random distance
+    rng = np.random.default_rng(5)
+    hit = o["kind"] == 1
+    org = rays[hit, :3] + rays[hit, 3:] * o["t"][hit, None]
+    d = rng.normal(size=org.shape).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = np.concatenate([org + d * np.float32(3e-4), d], axis=1).astype(np.float32)
+    ob2 = orc.trace_closest(b, 1); t2, k2, m2 = g.trace_closest(b, 1)
+    assert np.array_equal(k2, ob2["kind"]) and np.array_equal(t2.view(np.uint32), ob2["t"].view(np.uint32))
+    md = (rng.random(len(b), dtype=np.float32) * np.float32(2.0) * np.nanmedian(o["t"][hit])).astype(np.float32)
+    assert np.array_equal(g.trace_any(b, md), orc.trace_any(b, md))
+    assert 0 < g.trace_any(b, md).mean() < 1
+    orc.close()
+
+
+def test_disney_eval_equals_the_shader_function(glsl_mod, oracle_mod):
+    """G2 pin: the oracle's DisneyEval (f, pdf) == the reference's DisneyEval text, bit for bit, on the G2 query table
+    (every in-repo material + sheen / tint / anisotropy / transmission rows; grazing, back-side and refraction configurations)."""
+    from test_gpu_render import bsdf_queries
+    sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
+    g = live(glsl_mod, sc); orc = oracle_mod.Oracle(sc)
+    q = bsdf_queries(oracle_mod, seed=1, per_mat=200)
+    a, b = g.bsdf_eval(q), orc.bsdf(q)
+    assert np.count_nonzero(b["pdf"] > 0) > len(q) // 4
+    assert bits_equal(a["pdf"], b["pdf"]) and bits_equal(a["f"], b["f"])
+    orc.close()
