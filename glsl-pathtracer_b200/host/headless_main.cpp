@@ -7,6 +7,7 @@
 #include <chrono>
 #include "Scene.h"
 #include "Loader.h"
+#include "GLTFLoader.h"
 #include "Renderer.h"
 #include "RendererB200Ext.h"
 #include "ptb200.h"
@@ -35,7 +36,15 @@ int main(int argc, char** argv)
     Scene* scene = new Scene();
     RenderOptions renderOptions;
     renderOptions.simpleAcesFit = false;
-    if (!LoadSceneFromFile(sceneFile, scene, renderOptions)) { printf("Unable to load scene\n"); return 1; }   // Main.cpp:137-141
+    {   // Main.cpp:125-141: dispatch on the file extension
+        std::string ext = sceneFile.substr(sceneFile.find_last_of(".") + 1);
+        Mat4 xform;
+        bool success = false;
+        if (ext == "scene") success = LoadSceneFromFile(sceneFile, scene, renderOptions);
+        else if (ext == "gltf") success = LoadGLTF(sceneFile, scene, renderOptions, xform, false);
+        else if (ext == "glb") success = LoadGLTF(sceneFile, scene, renderOptions, xform, true);
+        if (!success) { printf("Unable to load scene\n"); return 1; }
+    }
     if (w > 0) { renderOptions.renderResolution = iVec2(w, h); renderOptions.windowResolution = iVec2(w, h); }
     if (depth >= 0) renderOptions.maxDepth = depth;
     renderOptions.maxSpp = spp + 1;                      // Q1: maxSpp = M renders M-1 passes

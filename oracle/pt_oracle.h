@@ -8,7 +8,7 @@
  *
  * Parity pinning: PINNED against the executing reference.  The reference ships no tests or golden vectors
  * and no GL/Mesa exists in this image, but its shader text is C-like: oracle/glsl_ref compiles the reference's own
- * tile.glsl / preview.glsl / tonemap.glsl (+ common/*.glsl), read in place from /root/reference, with g++ (lexical rewrites
+ * tile.glsl / preview.glsl / tonemap.glsl (+ the common/ includes), read in place from /root/reference, with g++ (lexical rewrites
  * only) and runs them on the host.  This restatement is BIT-IDENTICAL to that executing reference on 8 scenes + 15 feature
  * variants (accumulation buffers, previews, RGBA8 readbacks), on ClosestHit / AnyHit per ray and on DisneyEval per query
  * (tests/test_glsl_ref.py; golden vectors tests/golden/glslref_golden.npz).  The flattened BVH / mesh arrays consumed here

@@ -22,6 +22,7 @@
 
 #include "Scene.h"
 #include "Loader.h"
+#include "GLTFLoader.h"
 #include "Camera.h"
 
 using namespace GLSLPT;
@@ -63,14 +64,22 @@ struct Scalars
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { fprintf(stderr, "usage: scene_dump <file.scene> <out.ptscene>\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: scene_dump <file.scene|.gltf|.glb> <out.ptscene>\n"); return 2; }
     static_assert(sizeof(RadeonRays::BvhTranslator::Node) == 36, "node layout");
     static_assert(sizeof(Material) == 128 && sizeof(Light) == 60 && sizeof(Mat4) == 64 && sizeof(Indices) == 12, "layouts");
 
     Scene* scene = new Scene();
     RenderOptions ro;                       // Main.cpp:71 (process-global in the app)
     ro.simpleAcesFit = false;               // uninitialised in the reference ctor (Renderer.h:39-70); pin it
-    if (!LoadSceneFromFile(argv[1], scene, ro)) { fprintf(stderr, "load failed\n"); return 1; }
+    {   // Main.cpp:125-134: dispatch on the file extension
+        std::string name = argv[1], ext = name.substr(name.find_last_of(".") + 1);
+        Mat4 xform;
+        bool ok = false;
+        if (ext == "scene") ok = LoadSceneFromFile(name, scene, ro);
+        else if (ext == "gltf") ok = LoadGLTF(name, scene, ro, xform, false);
+        else if (ext == "glb") ok = LoadGLTF(name, scene, ro, xform, true);
+        if (!ok) { fprintf(stderr, "load failed\n"); return 1; }
+    }
     scene->renderOptions = ro;              // Main.cpp:154
     scene->ProcessScene();                  // Renderer.cpp:78-79
 

@@ -16,7 +16,7 @@ from oracle.glsl_ref import binding as gb
 
 W, H, TW, TH, SPP = 48, 32, 20, 12, 4
 SCENES = ("cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "ibl_spheres",
-          "teapot", "instancing")
+          "teapot", "instancing", "gltf_mix")
 
 
 def cases():

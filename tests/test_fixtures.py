@@ -15,6 +15,9 @@ PINNED = {  # FNV-1a-64 over the raw bytes of bvhTranslator.no
     # synthetic stand-ins (tests/golden/gen_synthetic.py, seed 42) built by the same unmodified reference host code; regression pins
     "ibl_spheres": (1190, 1184, 0x07664C04E651EC2E),
     "instancing": (21186, 1184, 0x4C5BB29432A17014),
+    # glTF input (tests/golden/gen_gltf.py): a .gltf and the same model as .glb loaded by the reference's GLTFLoader.cpp through
+    # `gltf {}` blocks of one .scene file
+    "gltf_mix": (2732, 2708, 0xC97D61FC347013C0),
 }
 
 
@@ -71,3 +74,18 @@ def test_vert_indices_follow_scene_cpp_packing():
     sc = load_scene_cached("hyperion_rect_lights")
     vi = sc.vertIndices
     assert np.array_equal(vi[:, 1], vi[:, 0] + 1) and np.array_equal(vi[:, 2], vi[:, 0] + 2) and (vi[:, 0] % 3 == 0).all()
+
+
+def test_gltf_fixture_shows_the_loader_semantics():
+    """GLTFLoader.cpp: one mesh instance per primitive (:44-46, 6 per load), sqrt(roughnessFactor) (:259), MASK/BLEND alpha modes,
+    KHR_materials_transmission, texture ids offset by the textures already in the scene on the second load, including the
+    reference's `normalTexture.index + sceneTexIdx` for materials WITHOUT a normal map (:264: -1 + 4 = texture 3)."""
+    sc = load_scene_cached("gltf_mix")
+    m = sc.materials
+    assert len(sc.transforms) == 12 and len(m) == 13 and sc.textures.shape == (8, 128, 128, 4) and len(sc.lights) == 1
+    first, second = m[1:7], m[7:13]                       # material 0 is the loader's default material
+    assert np.allclose(first[0, 9], np.sqrt(0.5)) and first[1, 16] == 1.0 and first[2, 29] == 2 and first[4, 29] == 1 and first[4, 28] == np.float32(0.45)
+    assert list(first[0, 24:27]) == [0, 1, 2] and list(second[0, 24:27]) == [4, 5, 6]
+    assert list(first[:, 26]) == [2, -1, -1, -1, -1, -1] and list(second[:, 26]) == [6, 3, 3, 3, 3, 3]
+    f = scene_io.derive_features(sc)
+    assert f & scene_io.OPT_ALPHA_TEST and f & scene_io.OPT_ENVMAP and f & scene_io.OPT_LIGHTS

@@ -16,7 +16,7 @@ import feature_scenes as fs
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "glslref_golden.npz")
 W, H, TW, TH, SPP = 48, 32, 20, 12, 4
 SCENES = ("cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "ibl_spheres",
-          "teapot", "instancing")
+          "teapot", "instancing", "gltf_mix")
 CASES = list(SCENES) + ["variant_" + v for v in fs.VARIANTS]
 
 
@@ -84,7 +84,7 @@ def test_committed_golden_is_current(case, golden, glsl_mod):
 
 @pytest.mark.parametrize("name,size", [("cornell_box_orig", (96, 64, 40, 24)), ("hyperion_rect_lights", (160, 90, 64, 36)),
                                         ("hyperion_sphere_light", (96, 54, 96, 54)), ("volume_cube", (96, 64, 48, 32)),
-                                        ("ibl_spheres", (128, 72, 50, 30)), ("instancing", (96, 54, 32, 32))])
+                                        ("ibl_spheres", (128, 72, 50, 30)), ("instancing", (96, 54, 32, 32)), ("gltf_mix", (128, 72, 48, 40))])
 def test_live_reference_shaders_equal_oracle(name, size, glsl_mod, oracle_mod):
     """Other sizes and tile layouts, a later sample range (frame counter schedule), one explicit tile draw."""
     sc = scene_at(name, *size)
@@ -146,7 +146,7 @@ def test_translator_is_lexical_only(glsl_mod):
 
 # ---------------------------------------------------------------- G1 / G2 pins against the shader's own functions -----------
 @pytest.mark.parametrize("name", ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light",
-                                  "volume_cube", "ibl_spheres", "instancing"])
+                                  "volume_cube", "ibl_spheres", "instancing", "gltf_mix"])
 def test_closest_hit_and_any_hit_equal_the_shader_functions(name, glsl_mod, oracle_mod):
     """G1 pin: the oracle's host traversal == the reference's ClosestHit / AnyHit text on primary, random (incl. axis-parallel)
     and bounce-like rays: hit kind, material id and t bit-identical; occlusion identical."""
@@ -170,8 +170,12 @@ def test_closest_hit_and_any_hit_equal_the_shader_functions(name, glsl_mod, orac
     ob2 = orc.trace_closest(b, 1); t2, k2, m2 = g.trace_closest(b, 1)
     assert np.array_equal(k2, ob2["kind"]) and np.array_equal(t2.view(np.uint32), ob2["t"].view(np.uint32))
     md = (rng.random(len(b), dtype=np.float32) * np.float32(2.0) * np.nanmedian(o["t"][hit])).astype(np.float32)
-    assert np.array_equal(g.trace_any(b, md), orc.trace_any(b, md))
-    assert 0 < g.trace_any(b, md).mean() < 1
+    from glsl_pathtracer_b200 import scene_io as sio
+    f = sio.derive_features(sc)
+    if not (f & sio.OPT_ALPHA_TEST) or (f & sio.OPT_MEDIUM):
+        # (with the alpha test compiled in, AnyHit samples textures and draws from the path RNG: covered by the image tests instead)
+        assert np.array_equal(g.trace_any(b, md), orc.trace_any(b, md))
+        assert 0 < g.trace_any(b, md).mean() < 1
     orc.close()
 
 

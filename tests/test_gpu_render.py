@@ -93,7 +93,9 @@ CASES = [("cornell_box_orig", 128, 128, 64, 64, 4, 8, 0.97), ("cornell_box_spher
          # generated HDR environment (SampleEnvMap / EvalEnvMap / CDF binary search, env NEE shadow queue), checker texture with REPEAT wrap
          ("ibl_spheres", 240, 136, 64, 36, None, 8, 0.95),
          # 10 001 instances, TLAS height 15, rotated + non-uniformly scaled transforms, depth 8, glass/metal/clearcoat/sheen/anisotropic materials
-         ("instancing", 240, 136, 64, 36, None, 4, 0.93)]
+         ("instancing", 240, 136, 64, 36, None, 4, 0.93),
+         # glTF input loaded by the reference's GLTFLoader.cpp: all four texture-map kinds, MASK + BLEND alpha, transmission, env map + quad light
+         ("gltf_mix", 240, 136, 64, 36, None, 8, 0.9)]
 
 
 @pytest.mark.parametrize("name,w,h,tw,th,depth,spp,minfrac", CASES)

@@ -6,7 +6,7 @@ import pytest
 from conftest import scene_at
 
 pytestmark = pytest.mark.gpu
-SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing"]
+SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
 
 
 def _ctx(sc):
