@@ -118,7 +118,12 @@ int main(int argc, char** argv)
     add("vertIndices", scene->vertIndices.data(), scene->vertIndices.size() * 12);
     add("verticesUVX", scene->verticesUVX.data(), scene->verticesUVX.size() * 16);
     add("normalsUVY", scene->normalsUVY.data(), scene->normalsUVY.size() * 16);
-    add("materials", scene->materials.data(), scene->materials.size() * 128);
+    {   // Material::padding1 / padding2 are never initialised by the reference (Material.h:56,84) and never read by a shader
+        // (pathtrace.glsl:31-67 takes .rgb of texel 1 and .xyz of texel 7): zero them so that the blob is reproducible
+        std::vector<Material> mats = scene->materials;
+        for (auto& m : mats) { m.padding1 = 0.0f; m.padding2 = 0.0f; }
+        add("materials", mats.data(), mats.size() * 128);
+    }
     add("transforms", scene->transforms.data(), scene->transforms.size() * 64);
     add("lights", scene->lights.data(), scene->lights.size() * 60);
     add("textures", scene->textureMapsArray.data(), scene->textureMapsArray.size());

@@ -239,6 +239,12 @@ def main():
         print("gltf == glb:", la)
         with open(raw, "rb") as f, lzma.open(os.path.join(out_dir, "gltf_mix.ptscene.xz"), "wb", preset=6) as g:
             g.write(f.read())
+        # the generated inputs themselves, for the C++ drop-in binary on the GPU box (oracle/_ref is git-ignored but travels)
+        import shutil
+        dst = os.path.join(ROOT, "oracle", "_ref", "assets", "gltf_mix")
+        shutil.rmtree(dst, ignore_errors=True); os.makedirs(dst)
+        for fn in ("gltf_mix.scene", "mix.gltf", "mix.bin", "mix.glb", "sky.hdr", "base.png", "mr.png", "normal.png", "emissive.png"):
+            shutil.copy(os.path.join(tmp, fn), dst)
 
 
 if __name__ == "__main__":
