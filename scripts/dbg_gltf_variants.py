@@ -62,18 +62,6 @@ def smooth_tex(sc):
 def diffuse_all(sc):
     only_albedo_opaque(sc)
     sc.materials[:, 8] = 0; sc.materials[:, 9] = 0.7; sc.materials[:, 16] = 0
-def mirror_probe(sc):
-    only_albedo_opaque(sc)
-    m = sc.materials
-    m[:, 8] = 0; m[:, 9] = 0.7; m[:, 16] = 0; m[:, 4:7] = 0; m[:, 0:3] = 1
-    for k in (1, 7, 4, 10, 2, 8):    # balls + split ball halves -> untextured mirrors
-        m[k, 24:28] = -1; m[k, 8] = 1.0; m[k, 9] = 0.001
-    sc.lights = sc.lights[:0]
-    ro = sc.renderOptions
-    ro.enableEnvMap = False; ro.enableUniformLight = True; ro.uniformLightCol = (1.0, 1.0, 1.0); ro.enableRR = False
-    sc.textures = sc.textures.copy()
-    h, w = sc.textures.shape[1:3]
-    y, x = np.mgrid[0:h, 0:w]
-    sc.textures[:, ..., 0] = (x * 255 // (w - 1)).astype(np.uint8); sc.textures[:, ..., 1] = (y * 255 // (h - 1)).astype(np.uint8)
-    sc.textures[:, ..., 2] = 255; sc.textures[:, ..., 3] = 255
-run("mirror probe", mirror_probe, depth=2, spp=1)
+for tag, f in [("as is", noop), ("all opaque", opaque), ("no BLEND", no_blend), ("no MASK", no_mask), ("no normal maps", no_normalmap), ("group 2 no normal map", g2_nonormal),
+               ("no metallic-roughness maps", no_mr), ("no albedo maps", no_albedo), ("no textures", no_tex), ("no glass", no_glass), ("no env", no_env), ("no lights", no_lights)]:
+    run(tag, f, depth=4)

@@ -134,8 +134,8 @@ def build_model(tmp):
         {"name": "root", "children": [1, 2, 3], "scale": [1.0, 1.0, 1.0], "translation": [0.0, 0.0, 0.0]},
         {"name": "group", "children": [4, 5], "rotation": q((0, 1, 0), 0.6), "translation": [0.0, 1.0, 0.0], "scale": [1.0, 1.1, 1.0]},
         {"name": "ground", "mesh": 3},
-        # column-major matrix node: rotation about y by 30 deg, non-uniform scale, translation
-        {"name": "crate", "mesh": 2, "matrix": [c30 * 1.2, 0, -s30 * 1.2, 0, 0, 0.9, 0, 0, s30, 0, c30, 0, 2.2, 0.63, 1.8, 1]},
+        # column-major matrix node: rotation about y by 30 deg, non-uniform scale, translation (5 cm above the ground: no coplanar faces)
+        {"name": "crate", "mesh": 2, "matrix": [c30 * 1.2, 0, -s30 * 1.2, 0, 0, 0.9, 0, 0, s30, 0, c30, 0, 2.2, 0.68, 1.8, 1]},
         {"name": "ball", "mesh": 0, "translation": [-1.4, 0.0, -0.8]},
         {"name": "pair", "children": [6, 7], "translation": [1.3, 0.1, -1.6], "scale": [0.8, 0.8, 0.8]},
         {"name": "split_ball", "mesh": 1},

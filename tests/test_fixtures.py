@@ -17,7 +17,7 @@ PINNED = {  # FNV-1a-64 over the raw bytes of bvhTranslator.no
     "instancing": (21186, 1184, 0x4C5BB29432A17014),
     # glTF input (tests/golden/gen_gltf.py): a .gltf and the same model as .glb loaded by the reference's GLTFLoader.cpp through
     # `gltf {}` blocks of one .scene file
-    "gltf_mix": (2732, 2708, 0x4C36508F6A10E47B),
+    "gltf_mix": (2732, 2708, 0x80FF272081464E8A),
 }
 
 
