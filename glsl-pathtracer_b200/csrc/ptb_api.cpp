@@ -182,9 +182,16 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
         const float* L = N + (size_t)l * 9; const float* R = N + (size_t)r * 9;
         uint32_t lm = metaOf(N, l, err), rm = metaOf(N, r, err);
         REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+#if PTB_PACKED_SLAB
+        // pairs for the packed (f32x2) slab test: {Lmin.xy | Lmax.xy}, {Lmin.z Lmax.z | Rmin.z Rmax.z}, {Rmin.xy | Rmax.xy}
+        q[0] = make_float4(L[0], L[1], L[3], L[4]);
+        q[1] = make_float4(L[2], L[5], R[2], R[5]);
+        q[2] = make_float4(R[0], R[1], R[3], R[4]);
+#else
         q[0] = make_float4(L[0], L[1], L[2], L[3]);
         q[1] = make_float4(L[4], L[5], R[0], R[1]);
         q[2] = make_float4(R[2], R[3], R[4], R[5]);
+#endif
         q[3] = make_float4(u2f(lm), u2f(rm), 0.f, 0.f);
     }
     CK(c->inner.alloc((size_t)c->numNodes * 4));

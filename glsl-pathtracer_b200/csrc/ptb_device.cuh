@@ -113,6 +113,29 @@ __device__ __forceinline__ float aabbHit(float minx, float miny, float minz, flo
     return (t1 >= t0) ? (t0 > 0.f ? t0 : t1) : -1.0f;
 }
 
+// Packed variant: two IEEE fp32 operations per instruction (sub.rn.f32x2 / mul.rn.f32x2, sm_100+).  Each half is rounded exactly as
+// the scalar __fsub_rn / __fmul_rn, so hits stay bit-identical; the traversal kernels are issue-bound, the slab test is 24 of the
+// ~80 instructions of an internal-node step and becomes 12.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 xs2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 xm2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+struct RayPk { f32x2 oXY, oZZ, iXY, iZZ; };
+__device__ __forceinline__ RayPk packRay(float3 o, float3 inv) { RayPk r; r.oXY = pk2(o.x, o.y); r.oZZ = pk2(o.z, o.z); r.iXY = pk2(inv.x, inv.y); r.iZZ = pk2(inv.z, inv.z); return r; }
+// Both children of one inner node: minXY/maxXY = {min.x,min.y}/{max.x,max.y}, zz = {min.z,max.z}
+__device__ __forceinline__ float aabbHitPk(f32x2 minXY, f32x2 maxXY, f32x2 zz, const RayPk& r, float& entry)
+{
+    float nx, ny, fx, fy, nz, fz;
+    upk2(xm2(xs2(minXY, r.oXY), r.iXY), nx, ny);
+    upk2(xm2(xs2(maxXY, r.oXY), r.iXY), fx, fy);
+    upk2(xm2(xs2(zz, r.oZZ), r.iZZ), nz, fz);
+    float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+    float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+    entry = t0;
+    return (t1 >= t0) ? (t0 > 0.f ? t0 : t1) : -1.0f;
+}
+
 // intersection.glsl:47-66 (RectIntersect) split into its plane part and its rectangle part.  Lights that share a plane
 // bit-for-bit (same normal, same plane.w — e.g. the 17 ceiling strips of hyperion_rect_lights) reuse dt, t and p: the same
 // inputs give the same IEEE results, so the outcome per light is unchanged (closest_hit.glsl:49-53 hoisted to upload time).
@@ -267,7 +290,14 @@ struct NoAlpha { };
 template <bool ANY, bool ALPHA, bool CULL>
 struct Trav
 {
+#if PTB_PACKED_SLAB
+    float3 o, d, rd, invW;
+    RayPk rp;           // current-space origin and reciprocal direction in the register pairs the packed slab test consumes
+    __device__ __forceinline__ float3 roNow() const { float3 r; float z2; upk2(rp.oXY, r.x, r.y); upk2(rp.oZZ, r.z, z2); return r; }
+#else
     float3 o, d, ro, rd, inv, invW;
+    __device__ __forceinline__ float3 roNow() const { return ro; }
+#endif
     float t;
     uint32_t cur;
     int curInst;
@@ -278,8 +308,14 @@ struct Trav
     template <class Stack>
     __device__ __forceinline__ void begin(const DevScene& S, float3 o_, float3 d_, float tmax, Stack& stk)
     {
+#if PTB_PACKED_SLAB
+        o = o_; d = d_; rd = d_;
+        invW = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z));
+        rp = packRay(o_, invW);
+#else
         o = o_; d = d_; ro = o_; rd = d_;
         inv = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z)); invW = inv;
+#endif
         t = tmax; cur = S.rootMeta; curInst = -1; inBlas = false; occluded = false;
         stk.reset();
         stk.push(PTB_META_NONE);
@@ -293,10 +329,18 @@ struct Trav
         while (cur < (1u << 30))                              // PTB_K_INNER: closest_hit.glsl:173-205
         {
             const float4* n = innerBase + (size_t)cur * 4;
-            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
             float e0, e1;
+#if PTB_PACKED_SLAB
+            const ulonglong2 p0 = __ldg(reinterpret_cast<const ulonglong2*>(n)), p1 = __ldg(reinterpret_cast<const ulonglong2*>(n + 1)),
+                             p2 = __ldg(reinterpret_cast<const ulonglong2*>(n + 2));
+            const float4 q3 = __ldg(n + 3);
+            float lh = aabbHitPk(p0.x, p0.y, p1.x, rp, e0);
+            float rh = aabbHitPk(p2.x, p2.y, p1.y, rp, e1);
+#else
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
             float lh = aabbHit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ro, inv, e0);
             float rh = aabbHit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ro, inv, e1);
+#endif
             if (CULL) { const float tc = t * 1.00001f; if (e0 > tc) lh = -1.0f; if (e1 > tc) rh = -1.0f; }
             const uint32_t lm = __float_as_uint(q3.x), rm = __float_as_uint(q3.y);
             const bool hl = lh > 0.0f, hr = rh > 0.0f;
@@ -322,7 +366,7 @@ struct Trav
                 // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard)
                 float3 pv = xcross(rd, e1);
                 float det = xdot(e0, pv);
-                float3 tv = xsub(ro, v0);
+                float3 tv = xsub(roNow(), v0);
                 float3 qv = xcross(tv, e0);
                 float ux = xd(xdot(tv, pv), det);
                 float uy = xd(xdot(rd, qv), det);
@@ -346,13 +390,18 @@ struct Trav
             const float4* ip = S.instTrav + (size_t)curInst * 4;
             const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
             // rTrans = inverse(transform) * (origin,1) / (direction,0); the inverse is precomputed at upload
-            ro = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
+            const float3 roI = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
                     xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
                     xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
             rd = f3(xa(xa(xa(xm(d.x, r0.x), xm(d.y, r1.x)), xm(d.z, r2.x)), xm(0.0f, r3.x)),
                     xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
                     xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
+#if PTB_PACKED_SLAB
+            rp = packRay(roI, f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z)));
+#else
+            ro = roI;
             inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
+#endif
             stk.push(PTB_META_NONE);                          // marker: back to the TLAS when it is popped
             cur = __float_as_uint(r0.w);                      // BLAS root meta
             inBlas = true;
@@ -362,8 +411,13 @@ struct Trav
             if (!inBlas) { h.t = t; return true; }
             inBlas = false;
             cur = stk.pop();
+#if PTB_PACKED_SLAB
+            rd = d;
+            rp = packRay(o, invW);                           // 1/direction of the world-space ray, computed once in begin()
+#else
             ro = o; rd = d;
             inv = invW;                                      // 1/direction of the world-space ray, computed once in begin()
+#endif
         }
         return false;
     }

@@ -1,5 +1,10 @@
 // ptb_internal.h — POD structures shared by the host side (ptb_api.cpp, g++) and the kernels (ptb_kernels.cu, nvcc).
 #pragma once
+// 1: inner nodes are laid out in (x,y)/(z,z) pairs and the slab test runs on Blackwell's packed fp32 pipe (add/mul.rn.f32x2 ->
+// FADD2/FMUL2: two IEEE-rounded operations per issue slot, bit-identical results).  0: scalar __f*_rn operations.
+#ifndef PTB_PACKED_SLAB
+#define PTB_PACKED_SLAB 0
+#endif
 #include <stdint.h>
 #include <stddef.h>
 
