@@ -288,7 +288,9 @@ def run_ours(args):
         total_spp = args.steps * SPP_PER_STEP * world
         value = segs / (ms * 1e-3) / 1e6
         peak, peak_src = peaks()
-        ab = algorithmic_bytes(sc)
+        # bounded sample for the oracle's byte count: the whole frame up to 1080p, else a centred 1920x1080 window of it
+        ab_rect = None if W * H <= 1920 * 1080 else ((W - 1920) // 2, (H - 1080) // 2, (W - 1920) // 2 + 1920, (H - 1080) // 2 + 1080)
+        ab = algorithmic_bytes(sc, ab_rect)
         rays_last_step = segs / args.steps / world          # rank-0 share of one step
         bytes_per_ray = ab["culled" if args.cull else "unculled"]["closest"]
         achieved = rays_last_step * bytes_per_ray / (trace_ms_last * 1e-3) / 1e9 if trace_ms_last > 0 else None
