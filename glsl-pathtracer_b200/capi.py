@@ -60,7 +60,7 @@ SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_derive_features",
            "ptb_update_instances", "ptb_update_envmap", "ptb_reset_accum", "ptb_render_tile", "ptb_render_samples", "ptb_render_preview",
            "ptb_read_accum_f32", "ptb_write_accum_f32", "ptb_accum_device_ptr", "ptb_read_output_rgba8", "ptb_get_stats", "ptb_reset_stats",
            "ptb_set_profiling", "ptb_set_stream", "ptb_synchronize", "ptb_set_cull", "ptb_trace_closest", "ptb_trace_any", "ptb_bsdf_eval",
-           "ptb_bsdf_sample", "ptb_camera_rays", "ptb_trace_closest_device", "ptb_read_nodes", "ptb_stack_depth"]
+           "ptb_bsdf_sample", "ptb_lambert_eval", "ptb_lambert_sample", "ptb_camera_rays", "ptb_trace_closest_device", "ptb_read_nodes", "ptb_stack_depth"]
 
 _lib = None
 
@@ -87,7 +87,7 @@ def load():
         "ptb_accum_device_ptr": [vp, C.POINTER(vp), C.POINTER(C.c_uint64)], "ptb_read_output_rgba8": [vp, f32, vp],
         "ptb_get_stats": [vp, C.POINTER(PtbStats)], "ptb_reset_stats": [vp], "ptb_set_profiling": [vp, i32], "ptb_set_stream": [vp, vp],
         "ptb_synchronize": [vp], "ptb_set_cull": [vp, i32], "ptb_trace_closest": [vp, vp, i64, i32, vp], "ptb_trace_any": [vp, vp, vp, i64, vp],
-        "ptb_bsdf_eval": [vp, vp, i64, vp], "ptb_bsdf_sample": [vp, vp, i64, vp], "ptb_camera_rays": [vp, i32, vp],
+        "ptb_bsdf_eval": [vp, vp, i64, vp], "ptb_bsdf_sample": [vp, vp, i64, vp], "ptb_lambert_eval": [vp, vp, i64, vp], "ptb_lambert_sample": [vp, vp, i64, vp], "ptb_camera_rays": [vp, i32, vp],
         "ptb_trace_closest_device": [vp, vp, i64, i32, vp], "ptb_read_nodes": [vp, vp, i32], "ptb_stack_depth": [vp, C.POINTER(i32)],
     }
     for name, args in protos.items():
@@ -292,6 +292,14 @@ class Context:
         q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
         out = np.zeros(len(q), BSDF_RESULT_DTYPE)
         fn = load().ptb_bsdf_sample if sample else load().ptb_bsdf_eval
+        check(fn(self.h, _ptr(q), len(q), _ptr(out)))
+        return out
+
+    def lambert(self, queries, sample=False):
+        """lambert.glsl (dead code in the reference's PathTrace): eval, or sample with the query's r1, r2."""
+        q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
+        out = np.zeros(len(q), BSDF_RESULT_DTYPE)
+        fn = load().ptb_lambert_sample if sample else load().ptb_lambert_eval
         check(fn(self.h, _ptr(q), len(q), _ptr(out)))
         return out
 

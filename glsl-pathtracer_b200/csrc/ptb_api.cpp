@@ -903,6 +903,8 @@ static int bsdfBatch(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult*
 }
 int ptb_bsdf_eval(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 0); }
 int ptb_bsdf_sample(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 1); }
+int ptb_lambert_eval(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 2); }
+int ptb_lambert_sample(PtbCtx* c, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out) { return bsdfBatch(c, q, n, out, 3); }
 
 int ptb_camera_rays(PtbCtx* c, int32_t sample, float* outRays)
 {

@@ -818,6 +818,22 @@ __device__ __forceinline__ float3 DisneySample(const Material& mat, float eta, f
     return DisneySampleFr(mat, eta, fr, Lw, pdf, r1, r2, r3);
 }
 
+// lambert.glsl:25-46.  Included by tile.glsl but never called from PathTrace; built for the parity entry point only.
+__device__ __forceinline__ float3 LambertEval(const Material& mat, float3 V, float3 N, float3 L, float& pdf)
+{
+    pdf = dot(N, L) * (1.0f / PTB_PI);
+    return (1.0f / PTB_PI) * mat.baseColor * dot(N, L);
+}
+__device__ __forceinline__ float3 LambertSample(const Material& mat, float3 V, float3 N, float3& L, float& pdf, float r1, float r2)
+{
+    float3 T, B;
+    Onb(N, T, B);
+    L = CosineSampleHemisphere(r1, r2);
+    L = T * L.x + B * L.y + N * L.z;
+    pdf = dot(N, L) * (1.0f / PTB_PI);
+    return (1.0f / PTB_PI) * mat.baseColor * dot(N, L);
+}
+
 // Material row -> Material (pathtrace.glsl:31-67 + :109-114), textures handled by the caller.
 __device__ __forceinline__ void materialFromRow(const float4* P, Material& mat, int4& texIDs)
 {

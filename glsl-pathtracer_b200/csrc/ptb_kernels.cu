@@ -1018,7 +1018,9 @@ __global__ void k_bsdf_batch(const BsdfQuery* __restrict__ q, long long n, BsdfR
     materialFinish(mat);
     float3 V = f3(q[i].V[0], q[i].V[1], q[i].V[2]), N = f3(q[i].N[0], q[i].N[1], q[i].N[2]), L = f3(q[i].L[0], q[i].L[1], q[i].L[2]);
     float pdf; float3 f;
-    if (sample) f = DisneySample(mat, q[i].eta, V, N, L, pdf, q[i].r1, q[i].r2, q[i].r3);
+    if (sample == 1) f = DisneySample(mat, q[i].eta, V, N, L, pdf, q[i].r1, q[i].r2, q[i].r3);
+    else if (sample == 2) f = LambertEval(mat, V, N, L, pdf);
+    else if (sample == 3) f = LambertSample(mat, V, N, L, pdf, q[i].r1, q[i].r2);
     else f = DisneyEval(mat, q[i].eta, V, N, L, pdf);
     out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf; out[i].L[0] = L.x; out[i].L[1] = L.y; out[i].L[2] = L.z;
 }

@@ -173,6 +173,10 @@ int  ptb_trace_closest(PtbCtx* ctx, const float* rays, int64_t n, int32_t depth,
 int  ptb_trace_any(PtbCtx* ctx, const float* rays, const float* maxDist, int64_t n, int32_t* outOccluded);
 int  ptb_bsdf_eval(PtbCtx* ctx, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out);
 int  ptb_bsdf_sample(PtbCtx* ctx, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out);
+/* lambert.glsl:25-46 (LambertEval / LambertSample with r1, r2 of the query).  The reference includes these in tile.glsl but never
+ * calls them from PathTrace, so they are not on the render path here either; exposed for parity only. */
+int  ptb_lambert_eval(PtbCtx* ctx, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out);
+int  ptb_lambert_sample(PtbCtx* ctx, const PtbBsdfQuery* q, int64_t n, PtbBsdfResult* out);
 /* Camera rays of 1-based sample pass `sample` for every pixel (tile.glsl:41-68): w*h*6 floats to the host. */
 int  ptb_camera_rays(PtbCtx* ctx, int32_t sample, float* outRays);
 /* Device-resident variants for benchmarking the traversal kernel alone (inputs/outputs already in HBM). */

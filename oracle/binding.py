@@ -64,6 +64,7 @@ def lib():
         L.orc_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_bsdf_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_lambert.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_render_samples.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_render_samples_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -163,6 +164,12 @@ class Oracle:
         q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
         out = np.zeros(len(q), BSDF_RESULT_DTYPE)
         (lib().orc_bsdf_sample if sample else lib().orc_bsdf_eval)(self.h, q.ctypes.data, len(q), out.ctypes.data)
+        return out
+
+    def lambert(self, queries, sample=False):
+        q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
+        out = np.zeros(len(q), BSDF_RESULT_DTYPE)
+        lib().orc_lambert(self.h, q.ctypes.data, len(q), int(sample), out.ctypes.data)
         return out
 
     def camera_rays(self, sample=1):

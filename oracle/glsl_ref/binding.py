@@ -89,6 +89,8 @@ def _load(defines):
         L.gref_trace_closest.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.gref_bsdf_eval.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.gref_lambert_eval.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.gref_lambert_sample.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIBS[key] = L
     return _LIBS[key]
 
@@ -182,6 +184,22 @@ class GlslRef:
         out = np.zeros(len(q), BSDF_RESULT_DTYPE)
         self.L.gref_bsdf_eval(q.ctypes.data, len(q), out.ctypes.data)
         return out
+
+    def lambert_eval(self, queries):
+        from oracle.binding import BSDF_QUERY_DTYPE, BSDF_RESULT_DTYPE
+        q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
+        out = np.zeros(len(q), BSDF_RESULT_DTYPE)
+        self.L.gref_lambert_eval(q.ctypes.data, len(q), out.ctypes.data)
+        return out
+
+    def lambert_sample(self, queries, seeds):
+        """The shader's LambertSample with its own RNG seeded per query; returns (results, the two rand() draws it consumed)."""
+        from oracle.binding import BSDF_QUERY_DTYPE, BSDF_RESULT_DTYPE
+        q = np.ascontiguousarray(queries, BSDF_QUERY_DTYPE)
+        seeds = np.ascontiguousarray(seeds, np.uint32).reshape(len(q), 4)
+        out = np.zeros(len(q), BSDF_RESULT_DTYPE); r12 = np.zeros((len(q), 2), np.float32)
+        self.L.gref_lambert_sample(q.ctypes.data, len(q), seeds.ctypes.data, out.ctypes.data, r12.ctypes.data)
+        return out, r12
 
     def num_threads(self):
         return self.L.gref_num_threads()

@@ -369,6 +369,38 @@ void gref_bsdf_eval(const OrcBsdfQuery* q, int64_t n, OrcBsdfResult* out)
     materialsTex = saved;
 }
 
+// The shader's own LambertEval (lambert.glsl:41-46) on the same queries.
+void gref_lambert_eval(const OrcBsdfQuery* q, int64_t n, OrcBsdfResult* out)
+{
+    using namespace tile_prog;
+    for (int64_t i = 0; i < n; i++)
+    {
+        State state;
+        state.mat.baseColor = vec3(q[i].mat[0], q[i].mat[1], q[i].mat[2]);
+        float pdf = 0.0f;
+        vec3 f = LambertEval(state, vec3(q[i].V[0], q[i].V[1], q[i].V[2]), vec3(q[i].N[0], q[i].N[1], q[i].N[2]), vec3(q[i].L[0], q[i].L[1], q[i].L[2]), pdf);
+        out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf;
+        out[i].L[0] = q[i].L[0]; out[i].L[1] = q[i].L[1]; out[i].L[2] = q[i].L[2];
+    }
+}
+// The shader's own LambertSample (lambert.glsl:25-39); it draws r1, r2 from the shader RNG, so the seed is given per query and the
+// two draws are returned for the caller to feed the oracle / CUDA entry points.
+void gref_lambert_sample(const OrcBsdfQuery* q, int64_t n, const uint32_t* seeds4, OrcBsdfResult* out, float* r12)
+{
+    using namespace tile_prog;
+    for (int64_t i = 0; i < n; i++)
+    {
+        State state;
+        state.mat.baseColor = vec3(q[i].mat[0], q[i].mat[1], q[i].mat[2]);
+        seed = uvec4(seeds4[i * 4 + 0], seeds4[i * 4 + 1], seeds4[i * 4 + 2], seeds4[i * 4 + 3]);
+        r12[i * 2 + 0] = tile_prog::rand(); r12[i * 2 + 1] = tile_prog::rand();
+        seed = uvec4(seeds4[i * 4 + 0], seeds4[i * 4 + 1], seeds4[i * 4 + 2], seeds4[i * 4 + 3]);
+        float pdf = 0.0f; vec3 L;
+        vec3 f = LambertSample(state, vec3(q[i].V[0], q[i].V[1], q[i].V[2]), vec3(q[i].N[0], q[i].N[1], q[i].N[2]), L, pdf);
+        out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf; out[i].L[0] = L.x; out[i].L[1] = L.y; out[i].L[2] = L.z;
+    }
+}
+
 int gref_num_threads(void)
 {
 #ifdef _OPENMP

@@ -1587,6 +1587,35 @@ void orc_bsdf_sample(OrcCtx* h, const OrcBsdfQuery* q, int64_t n, OrcBsdfResult*
     }
 }
 
+// lambert.glsl:25-46 — included by tile.glsl, never called by PathTrace
+static vec3 LambertEval(const State& state, vec3 V, vec3 N, vec3 L, float& pdf)   // :41-46
+{
+    (void)V;
+    pdf = dot(N, L) * (1.0f / PI);
+    return (1.0f / PI) * state.mat.baseColor * dot(N, L);
+}
+static vec3 LambertSampleR(const State& state, vec3 V, vec3 N, vec3& L, float& pdf, float r1, float r2)   // :25-39 with the two rand() draws passed in
+{
+    (void)V;
+    vec3 T, B;
+    Onb(N, T, B);
+    L = CosineSampleHemisphere(r1, r2);
+    L = T * L.x + B * L.y + N * L.z;
+    pdf = dot(N, L) * (1.0f / PI);
+    return (1.0f / PI) * state.mat.baseColor * dot(N, L);
+}
+void orc_lambert(OrcCtx* h, const OrcBsdfQuery* q, int64_t n, int32_t sample, OrcBsdfResult* out)
+{
+    for (int64_t i = 0; i < n; i++)
+    {
+        State st = stateFromQuery(h, q[i]);
+        vec3 V = {q[i].V[0], q[i].V[1], q[i].V[2]}, N = {q[i].N[0], q[i].N[1], q[i].N[2]}, L = {q[i].L[0], q[i].L[1], q[i].L[2]};
+        float pdf;
+        vec3 f = sample ? LambertSampleR(st, V, N, L, pdf, q[i].r1, q[i].r2) : LambertEval(st, V, N, L, pdf);
+        out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf; out[i].L[0] = L.x; out[i].L[1] = L.y; out[i].L[2] = L.z;
+    }
+}
+
 void orc_camera_rays(OrcCtx* h, int32_t sample, float* rays)
 {
     const OrcOptions& o = h->o;

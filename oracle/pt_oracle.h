@@ -92,6 +92,8 @@ void orc_trace_closest_brute(OrcCtx*, const float* rays, int64_t n, int32_t dept
 
 void orc_bsdf_eval(OrcCtx*, const OrcBsdfQuery* q, int64_t n, OrcBsdfResult* out);
 void orc_bsdf_sample(OrcCtx*, const OrcBsdfQuery* q, int64_t n, OrcBsdfResult* out);
+/* lambert.glsl:25-46 (dead code in the reference's PathTrace): sample = 0 LambertEval, 1 LambertSample with the query's r1, r2. */
+void orc_lambert(OrcCtx*, const OrcBsdfQuery* q, int64_t n, int32_t sample, OrcBsdfResult* out);
 
 /* Camera rays of sample pass `sample` (1-based) for every pixel: n = w*h, 6 floats each (tile.glsl:41-68). */
 void orc_camera_rays(OrcCtx*, int32_t sample, float* rays);

@@ -190,3 +190,21 @@ def test_disney_eval_equals_the_shader_function(glsl_mod, oracle_mod):
     assert np.count_nonzero(b["pdf"] > 0) > len(q) // 4
     assert bits_equal(a["pdf"], b["pdf"]) and bits_equal(a["f"], b["f"])
     orc.close()
+
+
+def test_lambert_equals_the_shader_functions(glsl_mod, oracle_mod):
+    """a14: LambertEval / LambertSample (dead code in the reference's PathTrace) — the oracle's copies == the shader text bit for bit;
+    the sample comparison feeds the oracle the two draws the shader's own RNG produced."""
+    from test_gpu_render import bsdf_queries
+    sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
+    g = live(glsl_mod, sc); orc = oracle_mod.Oracle(sc)
+    q = bsdf_queries(oracle_mod, seed=3, per_mat=50)
+    a, b = g.lambert_eval(q), orc.lambert(q)
+    assert bits_equal(a["pdf"], b["pdf"]) and bits_equal(a["f"], b["f"])
+    seeds = np.random.default_rng(4).integers(0, 2 ** 32, size=(len(q), 4), dtype=np.uint64).astype(np.uint32)
+    sa, r12 = g.lambert_sample(q, seeds)
+    q2 = q.copy(); q2["r1"], q2["r2"] = r12[:, 0], r12[:, 1]
+    sb = orc.lambert(q2, sample=True)
+    assert bits_equal(sa["L"], sb["L"]) and bits_equal(sa["pdf"], sb["pdf"]) and bits_equal(sa["f"], sb["f"])
+    assert np.all(sb["pdf"] >= 0) and np.all(r12 >= 0) and np.all(r12 <= 1)
+    orc.close()

@@ -63,6 +63,18 @@ def test_bsdf_eval_matches_oracle(oracle_mod):
     ctx.close(); orc.close()
 
 
+def test_lambert_matches_oracle(oracle_mod):
+    """a14 (lambert.glsl, dead code in the reference's render loop): eval and sample through the C ABI vs the oracle, 1e-4 relative."""
+    sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    q = bsdf_queries(oracle_mod, seed=5, per_mat=60)
+    for sample in (False, True):
+        g, o = ctx.lambert(q, sample=sample), orc.lambert(q, sample=sample)
+        assert (_close(g["pdf"], o["pdf"]) & _close(g["f"], o["f"]).all(axis=1)).all()
+        assert (np.abs(g["L"] - o["L"]) <= 1e-5).all()
+    ctx.close(); orc.close()
+
+
 def test_bsdf_sample_matches_oracle(oracle_mod):
     sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
     ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
