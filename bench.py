@@ -123,7 +123,7 @@ def reference_arm(sc):
         return None
 
 
-def cpu_baseline(sc, spp=2):
+def cpu_baseline(sc, spp=8):
     """CPU baseline on a bounded sample (spp full-frame passes, all host threads).  kind "reference": the reference's own
     tile.glsl (+common/*.glsl) compiled by g++ -O2 (oracle/glsl_ref); the oracle port (hand-written restatement, bit-identical
     output, so identical path segments) is timed beside it and counts the segments."""
