@@ -123,14 +123,20 @@ def reference_arm(sc):
         return None
 
 
-def cpu_baseline(sc, spp=8):
-    """CPU baseline on a bounded sample (spp full-frame passes, all host threads).  kind "reference": the reference's own
+def cpu_baseline(sc, spp=None):
+    """CPU baseline on a bounded sample (full-frame passes, all host threads; the pass count is chosen from the first pass so that each
+    arm takes about 5-10 s: 8 passes on the headline workload, 1 on the 4K depth-8 scene).  kind "reference": the reference's own
     tile.glsl (+common/*.glsl) compiled by g++ -O2 (oracle/glsl_ref); the oracle port (hand-written restatement, bit-identical
     output, so identical path segments) is timed beside it and counts the segments."""
     from oracle import binding as ob
     o = ob.Oracle(sc)
     t0 = time.time()
-    o.render(1, spp)
+    o.render(1, 1)
+    dt1 = time.time() - t0
+    if spp is None:
+        spp = max(1, min(8, int(6.0 / max(dt1, 1e-3))))
+    if spp > 1:
+        o.render(2, spp - 1)
     dt_port = time.time() - t0
     st = o.stats(); o.close()
     cores = ob.lib().orc_num_threads()
