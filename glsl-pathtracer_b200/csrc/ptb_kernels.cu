@@ -510,11 +510,32 @@ __device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameP
 // ------------------------------------------------------------------ shade ----------------------------------------
 struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 
+#ifndef PTB_IMMEDIATE_SHADOW_PUSH
+#define PTB_IMMEDIATE_SHADOW_PUSH 1
+#endif
+// Where a deferred shadow ray is produced it is appended to its queue at once by the lanes that are converged there (one atomic per group),
+// instead of being carried in 10 registers to a warp-converged push at the end of the iteration.  Queue order does not matter for the
+// result: every path has at most one entry per queue and k_shadow adds it to that path's radiance.
+struct ShadowSink { const PathState* P; uint32_t* ctrA; uint32_t* ctrB; uint32_t path; };
+__device__ __forceinline__ void pushShadowNow(const ShadowSink& sk, int which, float3 o, float3 d, float maxDist, float3 c)
+{
+    const unsigned m = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t b = 0;
+    if ((int)lane == leader) b = atomicAdd(which ? sk.ctrB : sk.ctrA, (uint32_t)__popc(m));
+    b = __shfl_sync(m, b, leader);
+    const uint32_t k = b + __popc(m & ((1u << lane) - 1u));
+    sk.P->shO[which][k] = make_float4(o.x, o.y, o.z, maxDist);
+    sk.P->shD[which][k] = make_float4(d.x, d.y, d.z, __uint_as_float(sk.path));
+    sk.P->shC[which][k] = make_float4(c.x, c.y, c.z, 0.f);
+}
+
 // DirectLight (pathtrace.glsl:158-283).  Deferred mode: fills sa (env) / sb (light) with contribution*throughput.
 // Inline mode (shadow rays draw from the path RNG): traces here and returns Ld.
 template <int MODE>
 __device__ __forceinline__ float3 directLight(const DevScene& S, const FrameParams& F, float3 rd, const Surf& sf, const Material& mat, float eta, const ShadeFrame& fr,
-                                              bool isSurface, float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+                                              bool isSurface, float medAniso, float3 thr, Rng& rng, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic, const ShadowSink& sink)
 {
     float3 Ld = f3(0.0f);
     const float3 scatterPos = sf.fhp + sf.normal * PTB_EPS;
@@ -543,7 +564,11 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f * F.envMapIntensity / lightPdf;
                     if (volMis || inl) Ld += c;
+#if PTB_IMMEDIATE_SHADOW_PUSH
+                    else pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr);
+#else
                     else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; }
+#endif
                 }
             }
         }
@@ -572,7 +597,11 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f / ls.pdf;
                     if (volMis || inl) Ld += c;
+#if PTB_IMMEDIATE_SHADOW_PUSH
+                    else pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr);
+#else
                     else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
+#endif
                 }
             }
         }
@@ -582,8 +611,10 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
 
 // One iteration of the PathTrace loop body after ClosestHit (pathtrace.glsl:303-471) for path slot p.
 template <int MODE>
-__device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool firstIter, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic)
+__device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool firstIter, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic,
+                                          uint32_t* ctrThis)
 {
+    const ShadowSink sink{&P, &ctrThis[CTR_NSHA], &ctrThis[CTR_NSHB], p};
     const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], hit4 = P.hit[p];
     const float4 thr4 = firstIter ? make_float4(1.f, 1.f, 1.f, 0.f) : P.thr[p], rad4 = firstIter ? make_float4(0.f, 0.f, 0.f, 1.f) : P.rad[p];
     const int hitInst = P.hitInst[p];
@@ -676,7 +707,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                         ro += rd * scatterDist;
                         sf.fhp = ro;
                         ShadeFrame noFrame;
-                        rad += directLight<MODE>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic) * thr;
+                        rad += directLight<MODE>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic, sink) * thr;
                         float hr1 = rng.rand(), hr2 = rng.rand();
                         float3 scatterDir = SampleHG(-rd, aniso, hr1, hr2);
                         prevPdf = PhaseHG(dot(-rd, scatterDir), aniso);
@@ -702,7 +733,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                 surfaceScatter = true;
                 ShadeFrame fr;
                 frameSetup(mat, eta, -rd, sf.ffnormal, fr);
-                rad += directLight<MODE>(S, F, rd, sf, mat, eta, fr, true, 0.f, thr, rng, sa, sb, ic) * thr;  // :431
+                rad += directLight<MODE>(S, F, rd, sf, mat, eta, fr, true, 0.f, thr, rng, sa, sb, ic, sink) * thr;  // :431
                 float r1 = rng.rand(), r2 = rng.rand(), r3 = rng.rand();
                 float pdf;
                 float3 f = DisneySampleFr(mat, eta, fr, L, pdf, r1, r2, r3);                                 // :434
@@ -792,7 +823,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
         if (i < n)
         {
             p = queue[i];
-            shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic);
+            shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis);
         }
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (m)
@@ -802,8 +833,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             b = __shfl_sync(0xffffffffu, b, 0);
             if (cont) nextQueue[b + __popc(m & ((1u << lane) - 1u))] = p;
         }
+#if !PTB_IMMEDIATE_SHADOW_PUSH
         if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
         pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
+#endif
     }
     if (MODE == 2 && (ic.segs | ic.shadows))
     {
@@ -1092,14 +1125,14 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
     static int bps[3] = {0, 0, 0};
     if (!bps[0])
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 4>, SHADE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 4>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 5>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 5>, SHADE_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 4>, SHADE_THREADS, 0);
         for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
     }
     if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else if (F.general == 1) k_shade<1, 4><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else k_shade<0, 5><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     g_launches++;
 }
 
