@@ -510,12 +510,12 @@ __device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameP
 // ------------------------------------------------------------------ shade ----------------------------------------
 struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 
-#ifndef PTB_IMMEDIATE_SHADOW_PUSH
-#define PTB_IMMEDIATE_SHADOW_PUSH 1
-#endif
-// Where a deferred shadow ray is produced it is appended to its queue at once by the lanes that are converged there (one atomic per group),
-// instead of being carried in 10 registers to a warp-converged push at the end of the iteration.  Queue order does not matter for the
-// result: every path has at most one entry per queue and k_shadow adds it to that path's radiance.
+// Immediate push (k_shade<1>: env map + lights, two pending records = 20 registers): where a deferred shadow ray is produced it is appended
+// to its queue at once by the lanes that are converged there (one atomic per group), instead of being carried to a warp-converged push at
+// the end of the iteration.  Queue order does not matter for the result: every path has at most one entry per queue and k_shadow adds it
+// to that path's radiance.  Measured on one box: ibl_spheres 944 -> 976 spp/s (with 5 blocks/SM); k_shade<0> (one record, hyperion) loses 2 %
+// with it (846 -> 828: the light-NEE queue of bounce 0 is no longer in pixel order), so modes 0 and 2 keep the converged push.
+template <int MODE> struct ImmediatePush { static constexpr bool value = (MODE == 1); };
 struct ShadowSink { const PathState* P; uint32_t* ctrA; uint32_t* ctrB; uint32_t path; };
 __device__ __forceinline__ void pushShadowNow(const ShadowSink& sk, int which, float3 o, float3 d, float maxDist, float3 c)
 {
@@ -564,11 +564,8 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f * F.envMapIntensity / lightPdf;
                     if (volMis || inl) Ld += c;
-#if PTB_IMMEDIATE_SHADOW_PUSH
-                    else pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr);
-#else
+                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr);
                     else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; }
-#endif
                 }
             }
         }
@@ -597,11 +594,8 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f / ls.pdf;
                     if (volMis || inl) Ld += c;
-#if PTB_IMMEDIATE_SHADOW_PUSH
-                    else pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr);
-#else
+                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr);
                     else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
-#endif
                 }
             }
         }
@@ -833,10 +827,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             b = __shfl_sync(0xffffffffu, b, 0);
             if (cont) nextQueue[b + __popc(m & ((1u << lane) - 1u))] = p;
         }
-#if !PTB_IMMEDIATE_SHADOW_PUSH
-        if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
-        pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
-#endif
+        if constexpr (!ImmediatePush<MODE>::value)
+        {
+            if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
+            pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
+        }
     }
     if (MODE == 2 && (ic.segs | ic.shadows))
     {
@@ -1125,14 +1120,14 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
     static int bps[3] = {0, 0, 0};
     if (!bps[0])
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 5>, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 4>, SHADE_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 5>, SHADE_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 4>, SHADE_THREADS, 0);
         for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
     }
     if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else k_shade<0, 5><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
     g_launches++;
 }
 
