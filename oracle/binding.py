@@ -65,6 +65,7 @@ def lib():
         L.orc_bsdf_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_lambert.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.orc_capture_rays.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_render_samples.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_render_samples_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -177,6 +178,13 @@ class Oracle:
         rays = np.zeros((h * w, 6), np.float32)
         lib().orc_camera_rays(self.h, sample, rays.ctypes.data)
         return rays
+
+    def capture_rays(self, sample=1, depth=1):
+        """(rays (h, w, 6), valid (h, w)): the ray traced at path-loop depth `depth` (analysis aid for scripts/simd_sim.py)."""
+        w, h = self.size
+        rays = np.zeros((h, w, 6), np.float32); valid = np.zeros((h, w), np.uint8)
+        lib().orc_capture_rays(self.h, sample, depth, rays.ctypes.data, valid.ctypes.data)
+        return rays, valid.astype(bool)
 
     def render(self, first_sample=1, n_samples=1, accum=None, rect=None):
         w, h = self.size

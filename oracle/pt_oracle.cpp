@@ -138,6 +138,7 @@ namespace {
 struct Ctx   // per-evaluation view: scene + options + RNG of the current path ("global" shader state)
 {
     const OrcCtx* s; const OrcOptions* o; Rng rng; Counters* cnt;
+    float* capRay = nullptr; int capDepth = -1; bool capDone = false;     // orc_capture_rays: the ray traced at loop depth capDepth
     float rand() { return rng.rand(); }
 };
 
@@ -1191,6 +1192,11 @@ vec4 PathTrace(Ctx& c, Ray r)   // :285-476
 
     for (state.depth = 0;; state.depth++)
     {
+        if (c.capRay && !c.capDone && state.depth == c.capDepth)
+        {
+            c.capRay[0] = r.origin.x; c.capRay[1] = r.origin.y; c.capRay[2] = r.origin.z;
+            c.capRay[3] = r.direction.x; c.capRay[4] = r.direction.y; c.capRay[5] = r.direction.z; c.capDone = true;
+        }
         bool hit = ClosestHit(c, r, state, lightSample);
         if (!hit)
         {
@@ -1614,6 +1620,25 @@ void orc_lambert(OrcCtx* h, const OrcBsdfQuery* q, int64_t n, int32_t sample, Or
         vec3 f = sample ? LambertSampleR(st, V, N, L, pdf, q[i].r1, q[i].r2) : LambertEval(st, V, N, L, pdf);
         out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z; out[i].pdf = pdf; out[i].L[0] = L.x; out[i].L[1] = L.y; out[i].L[2] = L.z;
     }
+}
+
+// Analysis aid (scripts/simd_sim.py): the closest-hit ray every pixel's path traces at loop depth `depth` of sample pass `sample`
+// (valid[i] = 0 where the path ended earlier).  rays: w*h*6 floats, row 0 = bottom.
+void orc_capture_rays(OrcCtx* h, int32_t sample, int32_t depth, float* rays, uint8_t* valid)
+{
+    const OrcOptions& o = h->o;
+    TileGrid g = tileGrid(o);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < o.renderH; y++)
+        for (int x = 0; x < o.renderW; x++)
+        {
+            int tx = x / o.tileW, ty = y / o.tileH, lx = x % o.tileW, ly = y % o.tileH;
+            Ctx c{h, &h->o, Rng{}, nullptr};
+            c.capRay = &rays[((size_t)y * o.renderW + x) * 6]; c.capDepth = depth;
+            Ray ray = cameraRay(c, g, tx, ty, lx, ly, frameNumOf(g, sample, tx, ty));
+            PathTrace(c, ray);
+            valid[(size_t)y * o.renderW + x] = c.capDone ? 1 : 0;
+        }
 }
 
 void orc_camera_rays(OrcCtx* h, int32_t sample, float* rays)

@@ -98,6 +98,9 @@ void orc_lambert(OrcCtx*, const OrcBsdfQuery* q, int64_t n, int32_t sample, OrcB
 /* Camera rays of sample pass `sample` (1-based) for every pixel: n = w*h, 6 floats each (tile.glsl:41-68). */
 void orc_camera_rays(OrcCtx*, int32_t sample, float* rays);
 
+/* Analysis aid: the closest-hit ray each pixel's path traces at loop depth `depth` of pass `sample`; valid[i] = 0 if the path ended before. */
+void orc_capture_rays(OrcCtx*, int32_t sample, int32_t depth, float* rays, uint8_t* valid);
+
 /* Adds `nSamples` full-frame passes (all tiles, reference frameNum schedule, Renderer.cpp:745-783)
  * starting at 1-based pass `firstSample` to accum (w*h*4 floats, row 0 = bottom). */
 void orc_render_samples(OrcCtx*, int32_t firstSample, int32_t nSamples, float* accum);
