@@ -45,3 +45,17 @@ def rel_mse(a, b, eps=1e-2):
     """relMSE of b against reference a over rgb: mean((a-b)^2 / (a^2 + eps))."""
     a = np.asarray(a, np.float64)[..., :3]; b = np.asarray(b, np.float64)[..., :3]
     return float(np.mean((a - b) ** 2 / (a * a + eps)))
+
+
+def edited_scene(name, w, h, tw=None, th=None):
+    """(scene, edited scene): the instance edit of tests/golden/instance_edit.npz — transforms / materials / TLAS slice as the
+    reference's Scene::RebuildInstances() produced them (tests/golden/make_instance_edit_fixture.py)."""
+    import copy
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "instance_edit.npz"))
+    sc = scene_at(name, w, h, tw, th)
+    sc2 = copy.deepcopy(sc)
+    assert int(fx[name + "/top"]) == sc.topLevelIndex
+    sc2.nodes = sc.nodes.copy(); sc2.nodes[sc.topLevelIndex:] = fx[name + "/tlas"]
+    sc2.transforms = fx[name + "/transforms"].reshape(sc.transforms.shape).copy()
+    sc2.materials = fx[name + "/materials"].copy()
+    return sc, sc2

@@ -1,5 +1,6 @@
 """The scene fixtures are the output of the UNMODIFIED reference host code (oracle/ref_host); their flattened-BVH hashes must
 equal the values pinned in SURVEY.md §8(c), and the array element sizes must match the reference structs."""
+import os
 import numpy as np
 import pytest
 from conftest import load_scene_cached
@@ -89,3 +90,20 @@ def test_gltf_fixture_shows_the_loader_semantics():
     assert list(first[:, 26]) == [2, -1, -1, -1, -1, -1] and list(second[:, 26]) == [6, 3, 3, 3, 3, 3]
     f = scene_io.derive_features(sc)
     assert f & scene_io.OPT_ALPHA_TEST and f & scene_io.OPT_ENVMAP and f & scene_io.OPT_LIGHTS
+
+
+@pytest.mark.parametrize("name", ["cornell_box_orig", "hyperion_rect_lights"])
+def test_instance_edit_fixture_is_a_tlas_only_change(name):
+    """Scene::RebuildInstances (Scene.cpp:200-214) rebuilds only the TLAS slice: same node count, BLAS part untouched, one transform
+    row changed; the material id of the edited instance travels in its TLAS leaf (bvh_translator.cpp:70-78)."""
+    from conftest import edited_scene
+    sc, sc2 = edited_scene(name, 64, 64)
+    top = sc.topLevelIndex
+    assert sc2.nodes.shape == sc.nodes.shape and np.array_equal(sc.nodes[:top], sc2.nodes[:top]) and not np.array_equal(sc.nodes[top:], sc2.nodes[top:])
+    assert (sc.transforms.reshape(-1, 16) != sc2.transforms.reshape(-1, 16)).any(axis=1).sum() == 1
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "instance_edit.npz"))
+    k, mat = int(fx[name + "/edit"][0]), int(fx[name + "/edit"][5])
+    leaves = sc2.nodes[top:][sc2.nodes[top:, 8] < 0]
+    assert sorted((-leaves[:, 8] - 1).astype(int).tolist()) == list(range(len(sc.transforms.reshape(-1, 16))))
+    if mat >= 0:
+        assert int(leaves[(-leaves[:, 8] - 1).astype(int) == k][0, 7]) == mat

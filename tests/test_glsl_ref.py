@@ -208,3 +208,16 @@ def test_lambert_equals_the_shader_functions(glsl_mod, oracle_mod):
     assert bits_equal(sa["L"], sb["L"]) and bits_equal(sa["pdf"], sb["pdf"]) and bits_equal(sa["f"], sb["f"])
     assert np.all(sb["pdf"] >= 0) and np.all(r12 >= 0) and np.all(r12 <= 1)
     orc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_box_orig", "hyperion_rect_lights"])
+def test_live_instance_edit_equals_oracle(name, glsl_mod, oracle_mod):
+    """After a reference-made instance edit (scaled + translated instance, TLAS rebuilt by Scene::RebuildInstances): the shader's
+    inverse(transMat) / normal-matrix path on a non-trivial transform, reference shaders == oracle bit for bit."""
+    from conftest import edited_scene
+    sc, sc2 = edited_scene(name, 96, 64, 48, 32)
+    g = live(glsl_mod, sc2); orc = oracle_mod.Oracle(sc2)
+    a, b = g.render(1, 2), orc.render(1, 2)
+    assert bits_equal(a, b)
+    assert not bits_equal(b, oracle_mod.Oracle(sc).render(1, 2))
+    orc.close()
