@@ -59,7 +59,7 @@ def reorder_keys(sc, r):
 
 def run(L, sc, arrays, r, policy, cull, warp=32):
     nodes, vi, verts, invT = arrays
-    t = np.zeros(len(r), np.float32); prim = np.zeros(len(r), np.int32); out = np.zeros(8)
+    t = np.zeros(len(r), np.float32); prim = np.zeros(len(r), np.int32); out = np.zeros(9)
     L.simd_sim(nodes.ctypes.data, len(nodes), sc.topLevelIndex, vi.ctypes.data, verts.ctypes.data, invT.ctypes.data, r.ctypes.data, len(r),
                policy, cull, warp, t.ctypes.data, prim.ctypes.data, out.ctypes.data)
     return out
@@ -68,15 +68,17 @@ def run(L, sc, arrays, r, policy, cull, warp=32):
 def reorder_study(L, sc, arrays, orc, depth=1):
     rays, valid = orc.capture_rays(1, depth)
     r = np.ascontiguousarray(rays.reshape(-1, 6)[queue_order(valid)], np.float32)
-    base = run(L, sc, arrays, r, 0, 1)[0] / len(r)
-    print(f"  depth {depth}: queue order {base:.1f} slots/ray")
+    b = run(L, sc, arrays, r, 0, 1)
+    base = b[0] / len(r); basew = b[8] / len(r)
+    print(f"  depth {depth}: queue order {base:.1f} slots/ray, {basew:.1f} L1 wavefronts/ray")
     for warp in (16, 8, 1):
         o = run(L, sc, arrays, r, 0, 1, warp)
         print(f"    (hypothetical {warp:2d}-lane warps: utilisation {o[1] / (warp * o[0]):.3f})")
     for name, key in reorder_keys(sc, r).items():
         for tile in (2048, 1 << 30):
             o = run(L, sc, arrays, tile_sort(r, key, tile), 0, 1)
-            print(f"    sorted by {name:22s} in tiles of {'2048' if tile == 2048 else 'all '}: {o[0] / len(r):7.1f} slots/ray ({o[0] / len(r) / base * 100:5.1f} %), utilisation {o[1] / (32 * o[0]):.3f}")
+            print(f"    sorted by {name:22s} in tiles of {'2048' if tile == 2048 else 'all '}: {o[0] / len(r):7.1f} slots/ray ({o[0] / len(r) / base * 100:5.1f} %), utilisation {o[1] / (32 * o[0]):.3f},"
+                  f" L1 wavefronts/ray {o[8] / len(r):6.1f} ({o[8] / len(r) / basew * 100:5.1f} %)")
 
 
 def main():
@@ -98,7 +100,7 @@ def main():
             base = None
             for policy, pname in ((0, "while-while (shipped)"), (1, "postponed leaf"), (2, "if-if")):
                 for warp in (32,):
-                    t = np.zeros(len(r), np.float32); prim = np.zeros(len(r), np.int32); out = np.zeros(8)
+                    t = np.zeros(len(r), np.float32); prim = np.zeros(len(r), np.int32); out = np.zeros(9)
                     L.simd_sim(nodes.ctypes.data, len(nodes), sc.topLevelIndex, vi.ctypes.data, verts.ctypes.data, invT.ctypes.data, r.ctypes.data, len(r),
                                policy, cull, warp, t.ctypes.data, prim.ctypes.data, out.ctypes.data)
                     tri = ref["kind"] == 1
@@ -108,7 +110,7 @@ def main():
                     base = base or slots
                     print(f"  depth {depth} {len(r):8d} rays  {pname:22s} slots/ray {slots:8.1f} ({slots / base * 100:5.1f} %)  utilisation {out[1] / (32 * out[0]):.3f}"
                           f"  inner {out[2] / len(r):7.1f} (util {out[3] / max(1, 32 * out[2]):.2f}, {out[7] / len(r):.1f} steps/ray)  tri {out[4] / len(r):6.1f} (util {out[5] / max(1, 32 * out[4]):.2f})"
-                          f"  other {out[6] / len(r):5.1f}  same prim as oracle {same:.5f}")
+                          f"  other {out[6] / len(r):5.1f}  L1 wavefronts/ray {out[8] / len(r):6.1f}  same prim as oracle {same:.5f}")
     print("ray reordering before the bounce trace (tile-local sort is ~0.05 ms per bounce on the GPU):")
     reorder_study(L, sc, (nodes, vi, verts, invT), orc, 1)
     orc.close()

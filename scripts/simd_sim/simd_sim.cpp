@@ -115,7 +115,16 @@ inline void popMarker(Lane& L)
     L.ro = L.o; L.rd = L.d; L.inv = L.invW;
 }
 
-struct Stats { double slots = 0, laneSlots = 0, innerSlots = 0, innerLane = 0, triSlots = 0, triLane = 0, otherSlots = 0; long rays = 0, innerSteps = 0; };
+struct Stats { double slots = 0, laneSlots = 0, innerSlots = 0, innerLane = 0, triSlots = 0, triLane = 0, otherSlots = 0, wavefronts = 0; long rays = 0, innerSteps = 0; };
+
+// L1 wavefronts of one warp-wide fetch: distinct 128-byte lines among the lanes' addresses (a 64-byte node is 4 x LDG.128, a 48-byte
+// triangle record 3 x LDG.128; each of those instructions is replayed once per distinct line).
+inline int distinctLines(const long* addr, int n)
+{
+    long lines[32]; int m = 0;
+    for (int i = 0; i < n; i++) { long l = addr[i] >> 7; bool seen = false; for (int j = 0; j < m; j++) if (lines[j] == l) { seen = true; break; } if (!seen) lines[m++] = l; }
+    return m;
+}
 
 void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, float* outT, int32_t* outPrim, Stats& st)
 {
@@ -147,7 +156,7 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
         // inner phase
         while (true)
         {
-            int cnt = 0;
+            int cnt = 0; long addr[32];
             for (int i = 0; i < n; i++)
             {
                 if (L[i].done) continue;
@@ -157,14 +166,15 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
                     L[i].pending = L[i].cur; L[i].cur = L[i].stack[--L[i].sp];
                     k = kindOf(S, L[i].cur);
                 }
-                if (k == K_INNER) { stepInner(S, L[i], cull); cnt++; }
+                if (k == K_INNER) { addr[cnt] = (long)L[i].cur * 64; stepInner(S, L[i], cull); cnt++; }
             }
             if (!cnt) break;
+            st.wavefronts += 4.0 * distinctLines(addr, cnt);
             st.slots += C_INNER; st.innerSlots += C_INNER; st.innerLane += (double)C_INNER * cnt; st.laneSlots += (double)C_INNER * cnt; st.innerSteps += cnt;
         }
         // leaf phase: parked leaf first, then the current one (reference order)
         auto leafPass = [&](bool parked) {
-            int maxTri = 0, triLane = 0;
+            int maxTri = 0, triLane = 0; long triAddr[4][32]; int triN[4] = {0, 0, 0, 0};
             for (int i = 0; i < n; i++)
             {
                 if (L[i].done) continue;
@@ -174,9 +184,11 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
                 if (node < 0) continue;
                 int c = leafCount(S, node);
                 for (int j = 0; j < c; j++) testTri(S, L[i], node, j);
+                for (int j = 0; j < c && j < 4; j++) triAddr[j][triN[j]++] = ((long)S.nodes[node * 9 + 6] + j) * 48;
                 maxTri = std::max(maxTri, c); triLane += c;
                 if (!parked) L[i].cur = L[i].stack[--L[i].sp];
             }
+            for (int j = 0; j < 4; j++) if (triN[j]) st.wavefronts += 3.0 * distinctLines(triAddr[j], triN[j]);
             if (maxTri) { double c = C_LEAF_SETUP + (double)C_TRI * maxTri; st.slots += c; st.triSlots += c; st.triLane += (double)C_TRI * triLane; st.laneSlots += (double)C_TRI * triLane; }
         };
         if (policy == 1) leafPass(true);
@@ -200,7 +212,7 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
 }  // namespace
 
 extern "C" void simd_sim(const float* nodes, int numNodes, int top, const int32_t* vi, const float* verts, const float* invT,
-                         const float* rays, int64_t n, int policy, int cull, int warp, float* outT, int32_t* outPrim, double* out8)
+                         const float* rays, int64_t n, int policy, int cull, int warp, float* outT, int32_t* outPrim, double* out9)
 {
     Scene S{nodes, numNodes, top, vi, verts, invT};
     Stats total;
@@ -213,9 +225,9 @@ extern "C" void simd_sim(const float* nodes, int numNodes, int top, const int32_
 #pragma omp critical
         {
             total.slots += st.slots; total.laneSlots += st.laneSlots; total.innerSlots += st.innerSlots; total.innerLane += st.innerLane;
-            total.triSlots += st.triSlots; total.triLane += st.triLane; total.otherSlots += st.otherSlots; total.rays += st.rays; total.innerSteps += st.innerSteps;
+            total.triSlots += st.triSlots; total.triLane += st.triLane; total.otherSlots += st.otherSlots; total.rays += st.rays; total.innerSteps += st.innerSteps; total.wavefronts += st.wavefronts;
         }
     }
-    out8[0] = total.slots; out8[1] = total.laneSlots; out8[2] = total.innerSlots; out8[3] = total.innerLane; out8[4] = total.triSlots;
-    out8[5] = total.triLane; out8[6] = total.otherSlots; out8[7] = (double)total.innerSteps;
+    out9[0] = total.slots; out9[1] = total.laneSlots; out9[2] = total.innerSlots; out9[3] = total.innerLane; out9[4] = total.triSlots;
+    out9[5] = total.triLane; out9[6] = total.otherSlots; out9[7] = (double)total.innerSteps; out9[8] = total.wavefronts;
 }
