@@ -122,7 +122,9 @@ struct PtbCtx
     size_t slotCap = 0; bool stateGeneral = false;
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
-    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist;
+    DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
+    int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
+                               //    tiles of 2048 slots, instead of over the compacted arrival-order queue (PTB_SLOT_ORDER)
     int sortMode = 3;          // 0 off, 1 global sort of bounces >= 1, 2 global sort of every bounce, 3 tile-local sort of bounces >= 1 (default: +3 % over 1)
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
@@ -387,7 +389,7 @@ int ensureWaveState(PtbCtx* c, size_t slots)
         c->stateGeneral = true;
     }
     CK(c->counters.alloc((size_t)(PTB_MAX_ITERS + 2) * PTB_CTR_STRIDE));
-    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n));
+    CK(c->sortKeys.alloc(n)); CK(c->sortedQueue.alloc(n)); CK(c->slotKeys.alloc(n)); CK(c->slotSorted.alloc(n));
     c->slotCap = n;
     return PTB_OK;
 }
@@ -440,6 +442,9 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
     const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
     const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
     const int nominal = F.maxDepth + 1;
+    // slot-ordered bounce 1 needs the tile-local material sorter (it drops the holes for k_shade) and is kept to scenes without alpha re-traces
+    const bool useSlotOrder = c->slotOrder && c->sortMode == 3 && numKeys + 1 <= 4096 && !alphaScene && F.maxDepth >= 1 && !W.previewMode;
+    if (useSlotOrder) CK(cudaMemsetAsync(c->slotKeys.p, 0x07, (size_t)W.nSlots * sizeof(uint32_t), c->stream));   // 0x07070707 clamps to 7 = ended / never live
     int it = 0;
     while (true)
     {
@@ -447,17 +452,27 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut
         uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
         const bool sortThis = c->sortMode == 2 || ((c->sortMode == 1 || c->sortMode == 3) && it >= 1);
-        ptbk_trace(L, c->S, F, P, P.queue[it & 1], ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
-                   sortThis ? c->sortKeys.p : nullptr, c->sortHist.p);
+        // bounce 1 over the slots in screen order (95 % of them still alive there): see slotOrder
+        const bool slotIter = useSlotOrder && it == 1;
+        const uint32_t nOv = slotIter ? W.nSlots : 0u;
+        const uint32_t* traceQueue = P.queue[it & 1];
+        if (slotIter)
+        {
+            ptbk_sort_tile_local(L, nullptr, c->slotKeys.p, ci + CTR_NPATHS, 8, c->slotSorted.p, 7, W.nSlots);
+            traceQueue = c->slotSorted.p;
+        }
+        ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
+                   sortThis ? c->sortKeys.p : nullptr, c->sortHist.p, nOv, (uint32_t)numKeys);
         if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
-        const uint32_t* shadeQueue = P.queue[it & 1];
+        const uint32_t* shadeQueue = traceQueue;
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)
-            if (c->sortMode == 3 && numKeys <= 4096) ptbk_sort_tile_local(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, numKeys, c->sortedQueue.p);
-            else ptbk_sort(L, P.queue[it & 1], c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
+            if (slotIter) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys + 1, c->sortedQueue.p, numKeys, W.nSlots);
+            else if (c->sortMode == 3 && numKeys <= 4096) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys, c->sortedQueue.p);
+            else ptbk_sort(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
             shadeQueue = c->sortedQueue.p;
         }
-        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0);
+        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0, (useSlotOrder && it == 0) ? c->slotKeys.p : nullptr, nOv);
         if (!F.inlineShadow)
         {
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
@@ -583,6 +598,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
+    if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
     *out = c;
     return PTB_OK;
 }
@@ -597,7 +613,7 @@ int ptb_destroy(PtbCtx* c)
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
-    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release();
+    c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->slotKeys.release(); c->slotSorted.release();
     c->counters.release(); c->dstats.release();
     for (auto e : c->traceEvents) cudaEventDestroy(e);
     if (c->evStart) cudaEventDestroy(c->evStart);

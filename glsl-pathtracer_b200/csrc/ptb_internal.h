@@ -131,12 +131,12 @@ struct LaunchCfg { int numSMs; void* stream; };
 
 void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
 void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist);
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride = 0, uint32_t holeKey = 0);
 void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
                uint32_t* sorted);
-void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted);
+void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey = -1, uint32_t nOverride = 0);
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter);
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys = nullptr, uint32_t nOverride = 0);
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);

@@ -155,7 +155,7 @@ __device__ __forceinline__ uint32_t shadeKey(const DevScene& S, int hitInst)
 // and did not help the incoherent bounces (1.33 -> 1.35 ms), see DESIGN.md.
 template <bool CULL>
 __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* __restrict__ queue, uint32_t n,
-                                          uint32_t* fetchCtr, int lightsFromDepth, uint32_t* __restrict__ keys, uint32_t* hist)
+                                          uint32_t* fetchCtr, int lightsFromDepth, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t holeKey)
 {
     const uint32_t lane = threadIdx.x & 31u;
     SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
@@ -167,9 +167,11 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
-        if (i < n)
+        const uint32_t pq = i < n ? queue[i] : 0xffffffffu;
+        if (i < n && pq == 0xffffffffu) { if (keys) keys[i] = holeKey; }      // hole of a slot-ordered queue (dead path): nothing to trace
+        else if (i < n)
         {
-            const uint32_t p = queue[i];
+            const uint32_t p = pq;
             const float4 o4 = P.rayO[p], d4 = P.rayD[p];
             const float3 o = f3(o4), d = f3(d4);
             HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
@@ -196,12 +198,13 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
 
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
                                                           const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats,
-                                                          uint32_t* __restrict__ keys, uint32_t* hist)
+                                                          uint32_t* __restrict__ keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey)
 {
-    const uint32_t n = *countPtr;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->pathSegments, (unsigned long long)n);
-    if (F.cullBoxes) traceLoop<true>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist);
-    else traceLoop<false>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist);
+    const uint32_t live = *countPtr;                     // rays actually traced (statistics)
+    const uint32_t n = nOverride ? nOverride : live;     // queue length: the slot count when the queue is slot-ordered with holes
+    if (blockIdx.x == 0 && threadIdx.x == 0 && live) atomicAdd(&stats->pathSegments, (unsigned long long)live);
+    if (F.cullBoxes) traceLoop<true>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
+    else traceLoop<false>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
 }
 
 // Exclusive scan of the key histogram into bucket cursors (one warp); clears the histogram for the next bounce.
@@ -259,12 +262,14 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
 }
 // Tile-local variant: entries are grouped by key only inside their own tile of 2048 queue entries.  Warps become material-coherent
 // while every warp still touches path slots from one 2048-entry window, so the scattered state fetches stay sector/page local.
+// queue == nullptr: the entries are the indices themselves (slot order).  Entries whose key is holeKey come out as 0xffffffff ("hole") at the
+// end of their tile; keys above numKeys-1 are clamped.  nOverride != 0 replaces *countPtr as the number of entries.
 __global__ void __launch_bounds__(256) k_sort_tile_local(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
-                                                          uint32_t* __restrict__ sorted, int numKeys)
+                                                          uint32_t* __restrict__ sorted, int numKeys, int holeKey, uint32_t nOverride)
 {
     extern __shared__ uint32_t sm[];
     uint32_t* hist = sm; uint32_t* base = sm + numKeys;
-    const uint32_t n = *countPtr;
+    const uint32_t n = nOverride ? nOverride : *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tileSize = 256u * SORT_ITEMS;
     for (uint32_t tile = blockIdx.x * tileSize; tile < n; tile += gridDim.x * tileSize)
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(256) k_sort_tile_local(const uint32_t* __restr
         for (int j = 0; j < SORT_ITEMS; j++)
         {
             const uint32_t i = tile + j * 256u + threadIdx.x;
-            key[j] = i < n ? keys[i] : 0xffffffffu;
+            key[j] = i < n ? min(keys[i], (uint32_t)(numKeys - 1)) : 0xffffffffu;
             const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
             const int leader = __ffs(peers) - 1;
             uint32_t off = 0;
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(256) k_sort_tile_local(const uint32_t* __restr
         for (int j = 0; j < SORT_ITEMS; j++)
         {
             const uint32_t i = tile + j * 256u + threadIdx.x;
-            if (key[j] != 0xffffffffu) sorted[tile + base[key[j]] + rank[j]] = queue[i];
+            if (key[j] != 0xffffffffu) sorted[tile + base[key[j]] + rank[j]] = ((int)key[j] == holeKey) ? 0xffffffffu : (queue ? queue[i] : i);
         }
         __syncthreads();
     }
@@ -798,9 +803,9 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
 
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
-                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
+                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* __restrict__ slotKeys, uint32_t nOverride)
 {
-    const uint32_t n = ctrThis[CTR_NPATHS];
+    const uint32_t n = nOverride ? nOverride : ctrThis[CTR_NPATHS];
     const uint32_t lane = threadIdx.x & 31u;
     InlineCounters ic{0u, 0u};
     uint32_t nextBase = 0;
@@ -817,7 +822,22 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
         if (i < n)
         {
             p = queue[i];
-            shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis);
+            if (p != 0xffffffffu)                     // (hole of a slot-ordered queue)
+            {
+                shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis);
+                if (slotKeys)
+                {   // direction class of the continuation ray (dominant axis, sign) per path SLOT, 7 = path ended: the bounce-1 trace runs over
+                    // the slots in screen order, grouped by this class inside tiles
+                    uint32_t k = 7u;
+                    if (cont)
+                    {
+                        const float4 d4 = P.rayD[p];
+                        const float ax = fabsf(d4.x), ay = fabsf(d4.y), az = fabsf(d4.z);
+                        k = (ax >= ay && ax >= az) ? (d4.x < 0.f ? 1u : 0u) : (ay >= az ? (d4.y < 0.f ? 3u : 2u) : (d4.z < 0.f ? 5u : 4u));
+                    }
+                    slotKeys[p] = k;
+                }
+            }
         }
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (m)
@@ -1092,16 +1112,16 @@ void ptbk_camera(const LaunchCfg& c, const DevScene& S, const FrameParams& F, co
 }
 
 void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist)
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey)
 {
     int bps = traceBlocksPerSM(S);
-    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist);
+    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist, nOverride, holeKey);
     g_launches++;
 }
 
-void ptbk_sort_tile_local(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted)
+void ptbk_sort_tile_local(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey, uint32_t nOverride)
 {
-    k_sort_tile_local<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys);
+    k_sort_tile_local<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys, holeKey, nOverride);
     g_launches++;
 }
 
@@ -1115,7 +1135,7 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter)
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride)
 {
     static int bps[3] = {0, 0, 0};
     if (!bps[0])
@@ -1125,9 +1145,9 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 4>, SHADE_THREADS, 0);
         for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
     }
-    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
-    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter);
+    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
+    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
+    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     g_launches++;
 }
 
