@@ -66,6 +66,7 @@ def lib():
         L.orc_bsdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_lambert.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.orc_capture_rays.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_capture_shadow_rays.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_render_samples.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_render_samples_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -184,6 +185,13 @@ class Oracle:
         w, h = self.size
         rays = np.zeros((h, w, 6), np.float32); valid = np.zeros((h, w), np.uint8)
         lib().orc_capture_rays(self.h, sample, depth, rays.ctypes.data, valid.ctypes.data)
+        return rays, valid.astype(bool)
+
+    def capture_shadow_rays(self, sample=1, depth=0):
+        """(rays (h, w, 8) = origin, direction, maxDist, light index; valid (h, w)): the light-NEE shadow ray traced at loop depth `depth`."""
+        w, h = self.size
+        rays = np.zeros((h, w, 8), np.float32); valid = np.zeros((h, w), np.uint8)
+        lib().orc_capture_shadow_rays(self.h, sample, depth, rays.ctypes.data, valid.ctypes.data)
         return rays, valid.astype(bool)
 
     def render(self, first_sample=1, n_samples=1, accum=None, rect=None):

@@ -139,6 +139,7 @@ struct Ctx   // per-evaluation view: scene + options + RNG of the current path (
 {
     const OrcCtx* s; const OrcOptions* o; Rng rng; Counters* cnt;
     float* capRay = nullptr; int capDepth = -1; bool capDone = false;     // orc_capture_rays: the ray traced at loop depth capDepth
+    float* capShadow = nullptr; bool capShadowDone = false;              // orc_capture_shadow_rays: the light-NEE shadow ray of that depth
     float rand() { return rng.rand(); }
 };
 
@@ -1165,6 +1166,13 @@ vec3 DirectLight(Ctx& c, const Ray& r, const State& state, bool isSurface)   // 
             }
             else
             {
+                if (c.capShadow && !c.capShadowDone && state.depth == c.capDepth)
+                {
+                    float* q = c.capShadow;
+                    q[0] = shadowRay.origin.x; q[1] = shadowRay.origin.y; q[2] = shadowRay.origin.z;
+                    q[3] = shadowRay.direction.x; q[4] = shadowRay.direction.y; q[5] = shadowRay.direction.z;
+                    q[6] = lightSample.dist - EPS; q[7] = (float)idx; c.capShadowDone = true;
+                }
                 bool inShadow = AnyHit(c, shadowRay, lightSample.dist - EPS);
                 if (!inShadow)
                 {
@@ -1638,6 +1646,25 @@ void orc_capture_rays(OrcCtx* h, int32_t sample, int32_t depth, float* rays, uin
             Ray ray = cameraRay(c, g, tx, ty, lx, ly, frameNumOf(g, sample, tx, ty));
             PathTrace(c, ray);
             valid[(size_t)y * o.renderW + x] = c.capDone ? 1 : 0;
+        }
+}
+
+// Analysis aid: the light-NEE shadow ray (origin, direction, maxDist, light index: 8 floats) each pixel's path traces while shading at loop
+// depth `depth`; valid[i] = 0 where none is traced.
+void orc_capture_shadow_rays(OrcCtx* h, int32_t sample, int32_t depth, float* rays8, uint8_t* valid)
+{
+    const OrcOptions& o = h->o;
+    TileGrid g = tileGrid(o);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < o.renderH; y++)
+        for (int x = 0; x < o.renderW; x++)
+        {
+            int tx = x / o.tileW, ty = y / o.tileH, lx = x % o.tileW, ly = y % o.tileH;
+            Ctx c{h, &h->o, Rng{}, nullptr};
+            c.capShadow = &rays8[((size_t)y * o.renderW + x) * 8]; c.capDepth = depth;
+            Ray ray = cameraRay(c, g, tx, ty, lx, ly, frameNumOf(g, sample, tx, ty));
+            PathTrace(c, ray);
+            valid[(size_t)y * o.renderW + x] = c.capShadowDone ? 1 : 0;
         }
 }
 

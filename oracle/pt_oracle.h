@@ -100,6 +100,8 @@ void orc_camera_rays(OrcCtx*, int32_t sample, float* rays);
 
 /* Analysis aid: the closest-hit ray each pixel's path traces at loop depth `depth` of pass `sample`; valid[i] = 0 if the path ended before. */
 void orc_capture_rays(OrcCtx*, int32_t sample, int32_t depth, float* rays, uint8_t* valid);
+/* Analysis aid: the light-NEE shadow ray (origin, direction, maxDist, light index = 8 floats) traced while shading at loop depth `depth`. */
+void orc_capture_shadow_rays(OrcCtx*, int32_t sample, int32_t depth, float* rays8, uint8_t* valid);
 
 /* Adds `nSamples` full-frame passes (all tiles, reference frameNum schedule, Renderer.cpp:745-783)
  * starting at 1-based pass `firstSample` to accum (w*h*4 floats, row 0 = bottom). */

@@ -45,7 +45,7 @@ inline float slab(const float* n, V3 o, V3 inv, float& entry)
 
 struct Lane
 {
-    bool active = false, done = true, inBlas = false;
+    bool active = false, done = true, inBlas = false, anyHit = false, occluded = false;
     V3 o, d, ro, rd, inv, invW;
     float t; int prim;
     int cur;                 // node index, or -1 marker / sentinel
@@ -92,7 +92,11 @@ inline void testTri(const Scene& S, Lane& L, int node, int i)
     V3 pv = cross(L.rd, e1); float det = dot(e0, pv);
     V3 tv = L.ro - v0; V3 qv = cross(tv, e0);
     float ux = dot(tv, pv) / det, uy = dot(L.rd, qv) / det, uz = dot(e1, qv) / det, uw = 1.0f - ux - uy;
-    if (ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < L.t) { L.t = uz; L.prim = first + i; }
+    if (ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < L.t)
+    {
+        if (L.anyHit) { L.occluded = true; L.done = true; L.prim = first + i; }      // any-hit: first accepted hit ends the ray (t stays maxDist)
+        else { L.t = uz; L.prim = first + i; }
+    }
 }
 inline void enterInst(const Scene& S, Lane& L)
 {
@@ -126,10 +130,10 @@ inline int distinctLines(const long* addr, int n)
     return m;
 }
 
-void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, float* outT, int32_t* outPrim, Stats& st)
+void runWarp(const Scene& S, const float* rays, const float* maxDist, int n, int policy, bool cull, float* outT, int32_t* outPrim, Stats& st)
 {
     Lane L[32];
-    for (int i = 0; i < n; i++) L[i].begin(S, rays + (size_t)i * 6);
+    for (int i = 0; i < n; i++) { L[i].begin(S, rays + (size_t)i * 6); if (maxDist) { L[i].anyHit = true; L[i].t = maxDist[i]; } }
     auto anyLive = [&] { for (int i = 0; i < n; i++) if (!L[i].done) return true; return false; };
     while (anyLive())
     {
@@ -183,10 +187,10 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
                 else if (kindOf(S, L[i].cur) == K_LEAF) node = L[i].cur;
                 if (node < 0) continue;
                 int c = leafCount(S, node);
-                for (int j = 0; j < c; j++) testTri(S, L[i], node, j);
+                for (int j = 0; j < c && !L[i].done; j++) testTri(S, L[i], node, j);
                 for (int j = 0; j < c && j < 4; j++) triAddr[j][triN[j]++] = ((long)S.nodes[node * 9 + 6] + j) * 48;
                 maxTri = std::max(maxTri, c); triLane += c;
-                if (!parked) L[i].cur = L[i].stack[--L[i].sp];
+                if (!parked && !L[i].done) L[i].cur = L[i].stack[--L[i].sp];
             }
             for (int j = 0; j < 4; j++) if (triN[j]) st.wavefronts += 3.0 * distinctLines(triAddr[j], triN[j]);
             if (maxTri) { double c = C_LEAF_SETUP + (double)C_TRI * maxTri; st.slots += c; st.triSlots += c; st.triLane += (double)C_TRI * triLane; st.laneSlots += (double)C_TRI * triLane; }
@@ -212,7 +216,7 @@ void runWarp(const Scene& S, const float* rays, int n, int policy, bool cull, fl
 }  // namespace
 
 extern "C" void simd_sim(const float* nodes, int numNodes, int top, const int32_t* vi, const float* verts, const float* invT,
-                         const float* rays, int64_t n, int policy, int cull, int warp, float* outT, int32_t* outPrim, double* out9)
+                         const float* rays, int64_t n, int policy, int cull, int warp, float* outT, int32_t* outPrim, double* out9, const float* maxDist)
 {
     Scene S{nodes, numNodes, top, vi, verts, invT};
     Stats total;
@@ -221,7 +225,7 @@ extern "C" void simd_sim(const float* nodes, int numNodes, int top, const int32_
         Stats st;
 #pragma omp for schedule(dynamic, 64)
         for (int64_t b = 0; b < n; b += warp)
-            runWarp(S, rays + (size_t)b * 6, (int)std::min<int64_t>(warp, n - b), policy, cull != 0, outT + b, outPrim + b, st);
+            runWarp(S, rays + (size_t)b * 6, maxDist ? maxDist + b : nullptr, (int)std::min<int64_t>(warp, n - b), policy, cull != 0, outT + b, outPrim + b, st);
 #pragma omp critical
         {
             total.slots += st.slots; total.laneSlots += st.laneSlots; total.innerSlots += st.innerSlots; total.innerLane += st.innerLane;
