@@ -221,3 +221,13 @@ def test_live_instance_edit_equals_oracle(name, glsl_mod, oracle_mod):
     assert bits_equal(a, b)
     assert not bits_equal(b, oracle_mod.Oracle(sc).render(1, 2))
     orc.close()
+
+
+def test_live_full_size_pass_equals_oracle(glsl_mod, oracle_mod):
+    """BASELINE size: one full 1920x1080 sample pass of hyperion_rect_lights (64 tiles of 256x144, over-hanging last column / top row):
+    all 2 073 600 pixels of the reference shaders' accumulation buffer bit-identical to the oracle's."""
+    sc = scene_at("hyperion_rect_lights", 1920, 1080)
+    g = live(glsl_mod, sc); orc = oracle_mod.Oracle(sc)
+    a, b = g.render(2, 1), orc.render(2, 1)
+    assert bits_equal(a, b) and np.isfinite(b).all() and b[..., :3].mean() > 0.01
+    orc.close()
