@@ -9,7 +9,11 @@ frameNum schedule) rendered by the CUDA wavefront pipeline through the C ABI.
   python bench.py --impl reference ...                      the reference's own shader text compiled for the host (oracle/glsl_ref)
 
 The JSON line carries `roofline` (dominant kernel = closest-hit traversal, algorithmic bytes from the instrumented oracle
-on a bounded sample of the same workload), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
+on a bounded sample of the same workload; the lane-issue ceiling that actually binds is quoted from the committed ncu capture,
+labelled with the capture's commit), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, and beside the weak-scaling headline:
+`cull0` (the reference-order unculled traversal), `strong` (BASELINE's fixed-1024-spp time to image, one reduce + tonemap + D2H),
+`image_check` (the N-GPU reduced image against a 1-GPU render of the same passes), `e2e_dropin` (the C++ drop-in driven by the
+reference's Update/Render-per-tile loop) and `other_workloads` (the other BASELINE configs).  `--quick` prints the headline only.
 """
 from __future__ import annotations
 import argparse, copy, ctypes as C, json, os, subprocess, sys, threading, time
@@ -129,6 +133,7 @@ def cpu_baseline(sc, spp=None):
     tile.glsl (+common/*.glsl) compiled by g++ -O2 (oracle/glsl_ref); the oracle port (hand-written restatement, bit-identical
     output, so identical path segments) is timed beside it and counts the segments."""
     from oracle import binding as ob
+    use_all_host_threads()
     o = ob.Oracle(sc)
     t0 = time.time()
     o.render(1, 1)
@@ -164,13 +169,34 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(workload):
-    """DRAM bytes of the dominant kernel per step from the committed ncu capture (profiles/), headline workload only."""
-    p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
-    if workload == SCENE and os.path.exists(p):
+def capture(workload):
+    """ncu-derived figures of the committed capture (profiles/r02_capture.json, written by scripts/make_profiles.py from the raw ncu
+    reports): DRAM bytes of the dominant kernel per step, thread/warp instructions of the traversal kernels, L2 bytes.  They are
+    properties of the kernels at the capture's commit (recorded in the file), not of this run — bench.py cannot count instructions
+    without a profiler — and are passed through labelled as such; absent file or other workload: None."""
+    p = os.path.join(ROOT, "profiles", "r02_capture.json")
+    if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["k_trace_dram_bytes_per_step"])
+            c = json.load(f)
+        if c.get("workload") == workload:
+            return c
     return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """The CPU arms use every host core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)           # for OpenMP runtimes not loaded yet
+    from oracle import binding as ob
+    ob.lib().orc_set_num_threads(n)                  # the runtime is shared by the oracle and the reference-shader objects
+    return n
 
 
 def run_reference(args):
@@ -181,6 +207,7 @@ def run_reference(args):
         return 0
     sc = load_workload(args.workload)
     from oracle import binding as ob
+    use_all_host_threads()
     o = ob.Oracle(sc)
     g = reference_arm(sc)
     kind = "reference" if g is not None else "port"
@@ -213,6 +240,146 @@ def run_reference(args):
     return 0
 
 
+class Rig:
+    """One rank's context for one workload, on a torch stream, with a torch view of its running sum for the NCCL reduce."""
+
+    def __init__(self, workload, local, rank, world, samples_per_wave, cull, w=None, h=None):
+        import torch
+        from glsl_pathtracer_b200 import capi, multigpu
+        self.torch, self.capi, self.multigpu = torch, capi, multigpu
+        self.rank, self.world, self.local = rank, world, local
+        self.sc = load_workload(workload, w, h)
+        self.ctx = capi.Context(self.sc, device=local, samples_per_wave=samples_per_wave)
+        self.ctx.set_cull(cull)
+        self.stream = torch.cuda.Stream(device=local)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.accum_t = multigpu.DeviceAccumView(self.ctx).tensor(torch.device("cuda", local))
+        self.scratch = None
+        self.dev = torch.device("cuda", local)
+
+    def reduced_ptr(self):
+        """Device pointer of the summed image on rank 0 (None = this context's own running sum when there is one rank).  The reduce goes
+        into a scratch tensor on the context's stream; the per-rank running sums stay partial sums (progressive readbacks are correct)."""
+        if self.world == 1:
+            return None
+        with self.torch.cuda.stream(self.stream):
+            self.scratch = self.multigpu.reduce_accum(self.accum_t, dst=0, scratch=self.scratch)
+        return self.scratch.data_ptr()
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+        self.torch.cuda.synchronize()
+
+    def step(self, k, spp, e2e):
+        """One step: `spp` full-frame passes per GPU (rank r renders passes first + r + i*world: weak scaling); e2e adds the host uniforms in
+        and the tonemapped RGBA8 image out (reduce -> tonemap -> D2H into page-locked memory on rank 0)."""
+        first = 1 + k * spp * self.world + self.rank
+        if e2e:
+            self.ctx.set_camera(self.sc.camera)
+            self.ctx.set_options(self.ctx.opts)
+        self.ctx.render_samples(first, spp, self.world)
+        if e2e:
+            ptr = self.reduced_ptr()
+            if self.rank == 0:
+                return self.ctx.read_output(1.0 / float((k + 1) * spp * self.world), dev_accum=ptr, pinned=True)
+        return None
+
+    def timed(self, steps, spp, e2e):
+        """K steps bracketed by barrier + synchronize; device time (CUDA events on the launching stream) for the kernel-only number, wall
+        clock between the synchronisations for e2e (it contains host work); MAX over ranks."""
+        torch = self.torch
+        self.ctx.reset_accum(); self.ctx.reset_stats()
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        ev0.record(self.stream)
+        for k in range(steps):
+            self.step(k, spp, e2e)
+        ev1.record(self.stream)
+        self.barrier()
+        wall = time.time() - t0
+        ms = ev0.elapsed_time(ev1) if not e2e else wall * 1e3
+        st = self.ctx.stats()
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        segs = torch.tensor([st["pathSegments"], st["shadowRays"]], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            torch.distributed.all_reduce(segs, op=torch.distributed.ReduceOp.SUM)
+        return float(t.item()), float(segs[0].item()), float(segs[1].item()), st
+
+    def image_check(self, passes=16):
+        """Passes 1..passes sharded over the ranks and reduced, against rank 0 rendering the same passes alone: equal up to fp32 add order."""
+        torch = self.torch
+        self.ctx.reset_accum()
+        f, c, s_ = self.multigpu.shard_passes(1, passes, self.rank, self.world)
+        if c:
+            self.ctx.render_samples(f, c, s_)
+        ptr = self.reduced_ptr()
+        self.barrier()
+        out = None
+        if self.rank == 0:
+            summed = self.scratch.cpu().numpy() if ptr is not None else self.ctx.read_accum()
+            self.ctx.reset_accum()
+            self.ctx.render_samples(1, passes, 1)
+            single = self.ctx.read_accum()
+            err = float(np.max(np.abs(summed - single) / (np.abs(single) + 1e-3)))
+            out = {"passes": passes, "ranks": self.world, "max_rel_err": err, "ok": bool(err <= 1e-4),
+                   "what": "sharded passes reduced with NCCL into a scratch sum vs the same passes on one GPU (fp32 add order differs)"}
+        self.barrier()
+        return out
+
+    def strong(self, total_spp=1024):
+        """BASELINE's strong-scaling figure: a FIXED total of sample passes split over the ranks; time to the tonemapped image on the host
+        (render + one reduce + tonemap + D2H), wall clock between synchronisations, max over ranks."""
+        torch = self.torch
+        self.ctx.reset_accum()
+        self.barrier()
+        t0 = time.time()
+        f, c, s_ = self.multigpu.shard_passes(1, total_spp, self.rank, self.world)
+        if c:
+            self.ctx.render_samples(f, c, s_)
+        ptr = self.reduced_ptr()
+        if self.rank == 0:
+            self.ctx.read_output(1.0 / float(total_spp), dev_accum=ptr, pinned=True)
+        self.barrier()
+        t = torch.tensor([(time.time() - t0) * 1e3], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"spp_total": total_spp, "time_to_image_ms": ms, "spp_per_s": total_spp / (ms * 1e-3), "scaling": "strong",
+                "what": "fixed total sample count split over the ranks; render + one NCCL reduce + tonemap + D2H of the RGBA8 image"}
+
+    def close(self):
+        self.ctx.close()
+
+
+def dropin_bench(workload, gpus):
+    """The C++ drop-in (the reference's unmodified Scene/loaders/Renderer.h + host/Renderer_b200.cpp) driven by the reference's own loop —
+    one Update + one Render (one tile) + Present per iteration, Main.cpp:175-213 — on the same workload; the image is copied to the host
+    once at the end (GetOutputBuffer).  `tile_path` is the same loop without pass coalescing: one wavefront per tile, as the reference draws."""
+    exe = os.path.join(ROOT, "glsl-pathtracer_b200", "host", "build", "ptb_headless")
+    scene = os.path.join(ROOT, "oracle", "_ref", "assets", workload + ".scene")
+    if not (os.path.exists(exe) and os.path.exists(scene)):
+        return None
+    def run(extra, spp, warm):
+        cmd = [exe, "-s", scene, "-o", "/tmp/ptb_dropin.png", "--res", str(W), str(H), "--spp", str(spp), "--warmup", str(warm)] + extra
+        if gpus > 1:
+            cmd += ["--devices", ",".join(str(i) for i in range(gpus))]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        for l in r.stdout.splitlines():
+            if l.startswith("BENCH "):
+                d = json.loads(l[6:])
+                return {"value": d["path_segments"] / d["seconds"] / 1e6, "unit": METRIC, "spp_per_s": d["spp"] / d["seconds"], "spp": d["spp"],
+                        "updates": d["updates"], "gpu_launches": d["kernel_launches"], "gpus": d["gpus"]}
+        return {"error": (r.stdout + r.stderr)[-300:]}
+    out = run([], 256, 32)
+    if out is not None and "error" not in out:
+        out["what"] = "ptb_headless: reference Update()+Render()-per-tile loop over Renderer_b200.cpp, 256 passes timed after 32, incl. the GetOutputBuffer copy"
+        out["tile_path"] = run(["--no-coalesce"], 6, 2)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -223,72 +390,63 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sc = load_workload(args.workload)
-    ctx = capi.Context(sc, device=local, samples_per_wave=args.samples_per_wave)
-    ctx.set_cull(args.cull)
-    stream = torch.cuda.Stream(device=local)
-    ctx.set_stream(stream.cuda_stream)
-    ptr, nbytes = ctx.accum_device_ptr()
+    rig = Rig(args.workload, local, rank, world, args.samples_per_wave, args.cull)
+    sc, ctx = rig.sc, rig.ctx
+    warm = max(args.warmup, 3)
 
-    class _Wrap:   # expose the accumulation buffer to torch for the NCCL reduce
-        __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "<f4", "data": (ptr, False), "version": 3}
-    accum_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
-
-    def step(k, e2e):
-        # sample sharding: rank r renders passes {first + r + i*world}; the per-GPU work is fixed (weak scaling)
-        first = 1 + k * SPP_PER_STEP * world + rank
-        if e2e:
-            ctx.set_camera(sc.camera)                                  # per-step inputs from the host (uniforms)
-            ctx.set_options(ctx.opts)
-        ctx.render_samples(first, SPP_PER_STEP, world)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)      # one NCCL reduce per readback over NVLink
-        if e2e and rank == 0:
-            return ctx.read_output(1.0 / float((k + 1) * SPP_PER_STEP * world))   # tonemap + D2H RGBA8 (GetOutputBuffer)
-        return None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(e2e, steps):
-        ctx.reset_accum(); ctx.reset_stats()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        ev0.record(stream)
-        for k in range(steps):
-            step(k, e2e)
-        ev1.record(stream)
-        barrier()
-        wall = time.time() - t0
-        ms = ev0.elapsed_time(ev1) if not e2e else wall * 1e3          # e2e includes host-side copies/syncs: wall clock bracketed by syncs
-        t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        st = ctx.stats()
-        segs = torch.tensor([st["pathSegments"], st["shadowRays"]], dtype=torch.float64, device=torch.device("cuda", local))
-        if world > 1:
-            dist.all_reduce(segs, op=dist.ReduceOp.SUM)
-        return float(t.item()), float(segs[0].item()), float(segs[1].item()), st
-
-    for k in range(max(args.warmup, 3)):
-        step(k, False)
-    barrier()
+    check = None if args.quick else rig.image_check()
+    for k in range(warm):
+        rig.step(k, SPP_PER_STEP, False)
+    rig.barrier()
     ctx.set_profiling(True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     launches0 = ctx.stats()["kernelLaunches"]
-    ms, segs, shadows, st = timed(False, args.steps)
+    ms, segs, shadows, st = rig.timed(args.steps, SPP_PER_STEP, False)
     launches = ctx.stats()["kernelLaunches"] - launches0
     clk = clocks.stop() if rank == 0 else None
     ctx.set_profiling(False)
     trace_ms_last = st["lastTraceMs"]                 # closest-hit launches of the LAST step (events recorded in-stream)
-    e2e_ms, e2e_segs, _, _ = timed(True, max(2, min(args.steps, 5)))
     e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms, e2e_segs, _, _ = rig.timed(e2e_steps, SPP_PER_STEP, True)
+
+    extras = {}
+    if not args.quick:
+        # the reference-order (unculled) traversal on the same workload: same paths up to exact ties, ~30 % more closest-hit work
+        ctx.set_cull(0 if args.cull else 1)
+        for k in range(2):
+            rig.step(k, SPP_PER_STEP, False)
+        c_steps = max(2, args.steps // 4)
+        c_ms, c_segs, _, _ = rig.timed(c_steps, SPP_PER_STEP, False)
+        ctx.set_cull(args.cull)
+        extras["cull0" if args.cull else "cull1"] = {"value": c_segs / (c_ms * 1e-3) / 1e6, "unit": METRIC, "spp_per_s": c_steps * SPP_PER_STEP * world / (c_ms * 1e-3),
+                                                      "ms_per_step": c_ms / c_steps, "steps": c_steps,
+                                                      "what": ("ptb_set_cull(0): the reference's visiting order without t-culling of child boxes (IDs and t bit-identical to a "
+                                                               "host traversal of closest_hit.glsl)" if args.cull else "ptb_set_cull(1): t-culled traversal")}
+        extras["strong"] = rig.strong(1024)
+    rig_main_close = rig.close
+
+    others = {}
+    if not args.quick and not args.no_other_workloads:
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                spp = 8 if name == "instancing" else SPP_PER_STEP
+                r2 = Rig(name, local, rank, world, args.samples_per_wave, args.cull)
+                for k in range(3):
+                    r2.step(k, spp, False)
+                n = 3 if name == "instancing" else 5
+                m2, s2, sh2, _ = r2.timed(n, spp, False)
+                e2, es2, _, _ = r2.timed(2, spp, True)
+                others[name] = {"value": s2 / (m2 * 1e-3) / 1e6, "unit": METRIC, "spp_per_s": n * spp * world / (m2 * 1e-3), "ms_per_step": m2 / n, "steps": n,
+                                "spp_per_step": spp, "mrays_per_s": (s2 + sh2) / (m2 * 1e-3) / 1e6, "e2e_spp_per_s": 2 * spp * world / (e2 * 1e-3),
+                                "workload": workload_config(r2.sc)["workload"].replace(f"{SPP_PER_STEP} spp per step", f"{spp} spp per step")}
+                r2.close()
+            except Exception as ex:     # a failing side workload must not take the headline line with it
+                others[name] = {"error": repr(ex)[:200]}
+        load_workload(args.workload)      # restore the module-level W, H of the headline workload
 
     if rank == 0:
         total_spp = args.steps * SPP_PER_STEP * world
@@ -300,34 +458,58 @@ def run_ours(args):
         rays_last_step = segs / args.steps / world          # rank-0 share of one step
         bytes_per_ray = ab["culled" if args.cull else "unculled"]["closest"]
         achieved = rays_last_step * bytes_per_ray / (trace_ms_last * 1e-3) / 1e9 if trace_ms_last > 0 else None
+        cap = capture(args.workload)
+        roof = {"bound": "hbm", "kernel": "k_trace (closest-hit two-level BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak if achieved else None), "traffic": (cap or {}).get("k_trace_dram_bytes_per_step"), "peak_source": peak_src,
+                "algorithmic_bytes_per_step": rays_last_step * bytes_per_ray,
+                "traffic_note": "dram bytes of all k_trace launches of one step, from the committed ncu capture (see `capture`), not from this run; achieved/algorithmic are per step as well",
+                "bytes_per_ray_culled": ab["culled"]["closest"], "bytes_per_ray_unculled": ab["unculled"]["closest"],
+                "bytes_per_shadow_ray": ab["culled"]["any"], "rays_per_step": rays_last_step, "trace_ms_per_step": trace_ms_last,
+                "mrays_per_s_kernel": (rays_last_step / (trace_ms_last * 1e-3) / 1e6 if trace_ms_last > 0 else None),
+                "note": "the scene (15 MB) is L1/L2-resident, so the survey-defined HBM fraction is a fetch-rate figure that exceeds 1 and does not bind; the ceiling that binds "
+                        "the traversal kernels is instruction issue x SIMD width: see lane_issue"}
+        if cap:
+            # lane-issue ceiling: thread instructions executed / (SMs x 4 schedulers x 32 lanes x clock x time); instruction counts are a property of
+            # the kernels on this workload (deterministic paths), taken from the capture; the time is THIS run's k_trace time
+            sms, clk_hz = 148, (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1965.0) * 1e6
+            ti = cap.get("k_trace_thread_inst_per_step")
+            roof["lane_issue"] = {"k_trace_thread_inst_per_step": ti, "k_trace_warp_inst_per_step": cap.get("k_trace_warp_inst_per_step"),
+                                  "frac": (ti / (sms * 4 * 32 * clk_hz * trace_ms_last * 1e-3) if ti and trace_ms_last > 0 else None),
+                                  "k_shadow_frac_in_capture": cap.get("k_shadow_lane_issue_frac"), "k_trace_frac_in_capture": cap.get("k_trace_lane_issue_frac"),
+                                  "l2_gbs_in_capture": cap.get("k_trace_l2_gbs"), "capture_commit": cap.get("commit"), "capture_file": "profiles/r02_capture.json",
+                                  "what": "thread instructions / (148 SMs x 4 issue slots x 32 lanes x SM clock x k_trace time of this run)"}
         line = {
-            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": f"scene fixture built by the reference host code ({sc.name}), reference RNG/frame schedule",
-            "config": workload_config(sc, {"parallelism": f"sample-range sharding x{world}, NCCL reduce per readback", "cull_boxes": bool(args.cull)}),
+            "config": workload_config(sc, {"parallelism": f"sample-range sharding x{world}, NCCL reduce into a scratch sum per readback", "cull_boxes": bool(args.cull)}),
             "spp_per_s": total_spp / (ms * 1e-3), "mshadow_rays_per_s": shadows / (ms * 1e-3) / 1e6, "mrays_per_s": (segs + shadows) / (ms * 1e-3) / 1e6,
             "e2e": {"value": e2e_segs / (e2e_ms * 1e-3) / 1e6, "unit": METRIC, "spp_per_s": e2e_steps * SPP_PER_STEP * world / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": C.sizeof(capi.PtbCamera) + C.sizeof(capi.PtbOptions), "d2h_bytes_per_step": W * H * 4,
-                    "what": "Context.set_camera + set_options (host uniforms) + render_samples + tonemapped RGBA8 readback to host per step"},
+                    "what": "Context.set_camera + set_options (host uniforms) + render_samples + (N>1: NCCL reduce) + tonemapped RGBA8 readback into page-locked host memory, per step"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit two-level BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak if achieved else None), "traffic": measured_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": rays_last_step * bytes_per_ray,
-                         "traffic_note": "dram bytes of all k_trace launches of one step (ncu, profiles/r01_trace_traffic.json); achieved/algorithmic are per step as well",
-                         "bytes_per_ray_culled": ab["culled"]["closest"], "bytes_per_ray_unculled": ab["unculled"]["closest"],
-                         "bytes_per_shadow_ray": ab["culled"]["any"], "rays_per_step": rays_last_step, "trace_ms_per_step": trace_ms_last,
-                         "mrays_per_s_kernel": (rays_last_step / (trace_ms_last * 1e-3) / 1e6 if trace_ms_last > 0 else None),
-                         "note": "scene (15 MB) is L2-resident: achieved = algorithmic fetch bytes served mostly by L1/L2, see profiles/ for dram bytes and L2 hit rate"},
+            "roofline": roof,
         }
-        if not args.no_cpu_baseline and world == 1:
+        line.update(extras)
+        if check is not None:
+            line["image_check"] = check
+        if others:
+            line["other_workloads"] = others
+        if not args.quick and world == 1:
+            d = dropin_bench(args.workload, 1)
+            if d is not None:
+                line["e2e_dropin"] = d
+        if not args.no_cpu_baseline and not args.quick and world == 1:
             line["cpu_baseline"] = cpu_baseline(sc)
         print(json.dumps(line))
+        if check is not None and not check["ok"]:
+            print(f"bench.py: N-GPU image check FAILED: {check}", file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
-    return 0
+    rig_main_close()
+    return 0 if (check is None or rank != 0 or check["ok"]) else 1
 
 
 def main():
@@ -339,6 +521,8 @@ def main():
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--samples-per-wave", type=int, default=0, help="0 = library default (~16 M paths in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the other BASELINE configs (other_workloads key)")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (profiling runs): no image check, cull0, strong, other workloads, drop-in, CPU baseline")
     ap.add_argument("--workload", default=SCENE, choices=sorted(WORKLOADS))
     args = ap.parse_args()
     if args.impl == "reference":

@@ -60,7 +60,12 @@ SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_derive_features",
            "ptb_update_instances", "ptb_update_envmap", "ptb_reset_accum", "ptb_render_tile", "ptb_render_samples", "ptb_render_preview",
            "ptb_read_accum_f32", "ptb_write_accum_f32", "ptb_accum_device_ptr", "ptb_read_output_rgba8", "ptb_get_stats", "ptb_reset_stats",
            "ptb_set_profiling", "ptb_set_stream", "ptb_synchronize", "ptb_set_cull", "ptb_trace_closest", "ptb_trace_any", "ptb_bsdf_eval",
-           "ptb_bsdf_sample", "ptb_lambert_eval", "ptb_lambert_sample", "ptb_camera_rays", "ptb_trace_closest_device", "ptb_read_nodes", "ptb_stack_depth"]
+           "ptb_bsdf_sample", "ptb_lambert_eval", "ptb_lambert_sample", "ptb_camera_rays", "ptb_trace_closest_device", "ptb_read_nodes", "ptb_stack_depth",
+           "ptb_render_pass", "ptb_read_output_rgba8_from", "ptb_snapshot_output", "ptb_read_snapshot_rgba8", "ptb_host_alloc", "ptb_host_free",
+           "ptb_mgpu_create", "ptb_mgpu_destroy", "ptb_mgpu_num_devices", "ptb_mgpu_context", "ptb_mgpu_set_options", "ptb_mgpu_set_camera", "ptb_mgpu_set_cull",
+           "ptb_mgpu_update_instances", "ptb_mgpu_update_envmap", "ptb_mgpu_reset_accum", "ptb_mgpu_render_samples", "ptb_mgpu_read_output_rgba8",
+           "ptb_mgpu_read_accum_f32", "ptb_mgpu_get_stats", "ptb_mgpu_synchronize", "ptb_mgpu_render_pass", "ptb_mgpu_snapshot_output", "ptb_mgpu_read_snapshot_rgba8",
+           "ptb_snapshot_output_from", "ptb_set_snapshot_float", "ptb_read_snapshot_rgb32f"]
 
 _lib = None
 
@@ -89,7 +94,17 @@ def load():
         "ptb_synchronize": [vp], "ptb_set_cull": [vp, i32], "ptb_trace_closest": [vp, vp, i64, i32, vp], "ptb_trace_any": [vp, vp, vp, i64, vp],
         "ptb_bsdf_eval": [vp, vp, i64, vp], "ptb_bsdf_sample": [vp, vp, i64, vp], "ptb_lambert_eval": [vp, vp, i64, vp], "ptb_lambert_sample": [vp, vp, i64, vp], "ptb_camera_rays": [vp, i32, vp],
         "ptb_trace_closest_device": [vp, vp, i64, i32, vp], "ptb_read_nodes": [vp, vp, i32], "ptb_stack_depth": [vp, C.POINTER(i32)],
+        "ptb_render_pass": [vp, i32, i32, i32], "ptb_snapshot_output_from": [vp, vp, f32], "ptb_set_snapshot_float": [vp, i32], "ptb_read_snapshot_rgb32f": [vp, vp], "ptb_mgpu_render_pass": [vp, i32, i32],
+        "ptb_mgpu_snapshot_output": [vp, f32], "ptb_mgpu_read_snapshot_rgba8": [vp, vp], "ptb_read_output_rgba8_from": [vp, vp, f32, vp], "ptb_snapshot_output": [vp, f32], "ptb_read_snapshot_rgba8": [vp, vp],
+        "ptb_host_alloc": [C.c_uint64, C.POINTER(vp)], "ptb_host_free": [vp],
+        "ptb_mgpu_create": [C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions), C.POINTER(i32), i32, C.POINTER(vp)], "ptb_mgpu_destroy": [vp],
+        "ptb_mgpu_num_devices": [vp], "ptb_mgpu_set_options": [vp, C.POINTER(PtbOptions)], "ptb_mgpu_set_camera": [vp, C.POINTER(PtbCamera)],
+        "ptb_mgpu_set_cull": [vp, i32], "ptb_mgpu_update_instances": [vp, vp, i32, vp, i32, vp, i32], "ptb_mgpu_update_envmap": [vp, vp, vp, i32, i32, f32],
+        "ptb_mgpu_reset_accum": [vp], "ptb_mgpu_render_samples": [vp, i32, i32], "ptb_mgpu_read_output_rgba8": [vp, f32, vp],
+        "ptb_mgpu_read_accum_f32": [vp, vp], "ptb_mgpu_get_stats": [vp, C.POINTER(PtbStats)], "ptb_mgpu_synchronize": [vp],
     }
+    L.ptb_mgpu_context.restype = vp
+    L.ptb_mgpu_context.argtypes = [vp, i32]
     for name, args in protos.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -170,11 +185,16 @@ def make_camera(cam) -> PtbCamera:
 class Context:
     """One PtbCtx (one GPU).  Methods map 1:1 onto the C ABI."""
 
-    def __init__(self, scene, device=0, features=None, samples_per_wave=0):
+    def __init__(self, scene, device=0, features=None, samples_per_wave=0, _borrowed=None):
         L = load()
         self.scene = scene
-        d, self._keep = scene_desc(scene)
+        self._pinned = None
+        self._owned = _borrowed is None
         self.opts = make_options(scene, features, samples_per_wave)
+        if _borrowed is not None:           # a per-GPU context owned by an Mgpu handle
+            self.h = C.c_void_p(_borrowed)
+            return
+        d, self._keep = scene_desc(scene)
         h = C.c_void_p()
         check(L.ptb_create(C.byref(d), C.byref(self.opts), device, C.byref(h)))
         self.h = h
@@ -182,9 +202,23 @@ class Context:
 
     # -- lifetime
     def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            load().ptb_host_free(self._pinned[0])
+            self._pinned = None
         if getattr(self, "h", None):
-            load().ptb_destroy(self.h)
+            if self._owned:
+                load().ptb_destroy(self.h)
             self.h = None
+
+    def _pinned_out(self, nbytes):
+        """page-locked readback target (one per context, reused): numpy view over ptb_host_alloc memory"""
+        if self._pinned is None or self._pinned[1] < nbytes:
+            if self._pinned is not None:
+                load().ptb_host_free(self._pinned[0])
+            p = C.c_void_p()
+            check(load().ptb_host_alloc(nbytes, C.byref(p)))
+            self._pinned = (p, nbytes, (C.c_uint8 * nbytes).from_address(p.value))
+        return self._pinned
 
     def __del__(self):
         try:
@@ -260,10 +294,29 @@ class Context:
         check(load().ptb_accum_device_ptr(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def read_output(self, inv_sample_counter):
+    def render_pass(self, sample, max_lookahead=0, stride=1):
+        check(load().ptb_render_pass(self.h, sample, stride, max_lookahead))
+
+    def read_output(self, inv_sample_counter, dev_accum=None, pinned=False):
+        """tonemapped RGBA8 [h, w, 4], bottom row first.  dev_accum: device pointer of another float4[w*h] sum to tonemap (reduced
+        multi-GPU sum).  pinned=True: the copy lands in the context's page-locked buffer and a VIEW of it is returned (valid until
+        the next pinned read); default is a fresh pageable array."""
+        w, h = self.size
+        if pinned:
+            p, _, raw = self._pinned_out(w * h * 4)
+            check(load().ptb_read_output_rgba8_from(self.h, dev_accum, inv_sample_counter, p))
+            return np.frombuffer(raw, np.uint8, w * h * 4).reshape(h, w, 4)
+        out = np.zeros((h, w, 4), np.uint8)
+        check(load().ptb_read_output_rgba8_from(self.h, dev_accum, inv_sample_counter, out.ctypes.data))
+        return out
+
+    def snapshot_output(self, inv_sample_counter):
+        check(load().ptb_snapshot_output(self.h, inv_sample_counter))
+
+    def read_snapshot(self):
         w, h = self.size
         out = np.zeros((h, w, 4), np.uint8)
-        check(load().ptb_read_output_rgba8(self.h, inv_sample_counter, out.ctypes.data))
+        check(load().ptb_read_snapshot_rgba8(self.h, out.ctypes.data))
         return out
 
     def stats(self):
@@ -318,3 +371,88 @@ class Context:
         v = C.c_int32()
         check(load().ptb_stack_depth(self.h, C.byref(v)))
         return v.value
+
+
+class Mgpu:
+    """PtbMgpu: N per-GPU contexts of one box behind one handle (one host thread), NCCL reduce into a scratch buffer per readback."""
+
+    def __init__(self, scene, devices=None, num_devices=None, features=None, samples_per_wave=0):
+        L = load()
+        self.scene = scene
+        d, self._keep = scene_desc(scene)
+        self.opts = make_options(scene, features, samples_per_wave)
+        if devices is None:
+            devices = list(range(num_devices or 1))
+        arr = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        check(L.ptb_mgpu_create(C.byref(d), C.byref(self.opts), arr, len(devices), C.byref(h)))
+        self.h = h
+        self.n = len(devices)
+        self.contexts = [Context(scene, features=self.opts.features, samples_per_wave=samples_per_wave, _borrowed=L.ptb_mgpu_context(h, i)) for i in range(self.n)]
+        self.set_camera(scene.camera)
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.contexts:
+                c.close()
+            load().ptb_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return self.opts.renderW, self.opts.renderH
+
+    def set_camera(self, cam):
+        self._cam = make_camera(cam)
+        check(load().ptb_mgpu_set_camera(self.h, C.byref(self._cam)))
+
+    def set_options(self, opts):
+        self.opts = opts
+        check(load().ptb_mgpu_set_options(self.h, C.byref(opts)))
+
+    def set_cull(self, on):
+        check(load().ptb_mgpu_set_cull(self.h, int(on)))
+
+    def reset_accum(self):
+        check(load().ptb_mgpu_reset_accum(self.h))
+
+    def render_samples(self, first, n):
+        check(load().ptb_mgpu_render_samples(self.h, first, n))
+
+    def read_output(self, inv_sample_counter):
+        w, h = self.size
+        out = np.zeros((h, w, 4), np.uint8)
+        check(load().ptb_mgpu_read_output_rgba8(self.h, inv_sample_counter, out.ctypes.data))
+        return out
+
+    def read_accum(self):
+        w, h = self.size
+        out = np.zeros((h, w, 4), np.float32)
+        check(load().ptb_mgpu_read_accum_f32(self.h, out.ctypes.data))
+        return out
+
+    def render_pass(self, sample, max_lookahead=0):
+        check(load().ptb_mgpu_render_pass(self.h, sample, max_lookahead))
+
+    def snapshot_output(self, inv_sample_counter):
+        check(load().ptb_mgpu_snapshot_output(self.h, inv_sample_counter))
+
+    def read_snapshot(self):
+        w, h = self.size
+        out = np.zeros((h, w, 4), np.uint8)
+        check(load().ptb_mgpu_read_snapshot_rgba8(self.h, out.ctypes.data))
+        return out
+
+    def stats(self):
+        s = PtbStats()
+        check(load().ptb_mgpu_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in PtbStats._fields_}
+
+    def synchronize(self):
+        check(load().ptb_mgpu_synchronize(self.h))

@@ -18,6 +18,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* ptb_last_error(void) { return g_err.c_str(); }
+extern "C" __attribute__((visibility("hidden"))) void ptb_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }      // for ptb_mgpu.cpp
 
 #define CK(call)                                                                                           \
     do {                                                                                                   \
@@ -129,16 +130,38 @@ struct PtbCtx
     DevBuf<DevStats> dstats;
     uint32_t* hCount = nullptr;   // pinned
 
-    uint64_t samplesRendered = 0, launchesAtCreate = 0;
+    // ptb_render_pass: a wave of several consecutive sample passes is traced at the first of them; the later ones are added to the
+    // running sum when the host asks for them, provided nothing the passes depend on has changed in between
+    struct Pending { bool valid = false; int first = 0, n = 0, consumed = 0, stride = 1; uint64_t sceneVersion = 0; FrameParams F{}; WaveParams W{}; } pending;
+    uint64_t sceneVersion = 0;                // bumped by every delta upload
+    DevBuf<uchar4> snapshot;                  // ptb_snapshot_output: tonemapped image kept on the device until it is asked for
+    DevBuf<float4> snapshotF; bool snapshotFloat = false;   // + its RGBA32F form when a denoiser hook wants it (ptb_set_snapshot_float)
+
+    uint64_t samplesRendered = 0;
+    unsigned long long launches = 0;          // kernels launched through this context
+    int traceBlocks = 1, shadeBlocks[3] = {1, 1, 1}, configuredDepth = -1;   // per-device launch configuration (ptbk_configure_device)
     uint64_t lastTraceRays = 0;
     bool timingValid = false;
 };
 
 namespace {
 
-LaunchCfg cfg(PtbCtx* c) { return LaunchCfg{c->numSMs, (void*)c->stream}; }
+LaunchCfg cfg(PtbCtx* c)
+{
+    return LaunchCfg{c->numSMs, (void*)c->stream, c->traceBlocks, {c->shadeBlocks[0], c->shadeBlocks[1], c->shadeBlocks[2]}, &c->launches};
+}
 
-uint32_t metaOf(const float* nodes, int idx, std::string& err)
+// kernel attributes / occupancy of this context's device for the current stack depth (the device must be current)
+int configureDevice(PtbCtx* c)
+{
+    if (c->configuredDepth == c->S.stackDepth) return PTB_OK;
+    cudaError_t e = (cudaError_t)ptbk_configure_device(c->S, &c->traceBlocks, c->shadeBlocks);
+    if (e != cudaSuccess) { g_err = std::string("ptbk_configure_device: ") + cudaGetErrorString(e); return PTB_ERR_CUDA; }
+    c->configuredDepth = c->S.stackDepth;
+    return PTB_OK;
+}
+
+uint32_t metaOf(const float* nodes, int idx, int numIndices, std::string& err)
 {
     const float* n = nodes + (size_t)idx * 9;
     int leaf = (int)n[8];
@@ -146,7 +169,8 @@ uint32_t metaOf(const float* nodes, int idx, std::string& err)
     if (leaf > 0)
     {
         int first = (int)n[6], cnt = (int)n[7];
-        if (cnt > PTB_MAX_LEAF_TRIS || first < 0 || (uint32_t)first > PTB_MAX_LEAF_SLOT) { err = "leaf exceeds encoding limits"; return PTB_META_NONE; }
+        if (cnt > PTB_MAX_LEAF_TRIS || cnt < 0 || first < 0 || (uint32_t)first > PTB_MAX_LEAF_SLOT) { err = "leaf exceeds encoding limits"; return PTB_META_NONE; }
+        if ((long long)first + cnt > (long long)numIndices) { err = "leaf references triangles past the end of vertIndices"; return PTB_META_NONE; }
         return (PTB_K_LEAF << 30) | ((uint32_t)cnt << 26) | (uint32_t)first;
     }
     return (PTB_K_INST << 30) | (uint32_t)(-leaf - 1);
@@ -182,8 +206,8 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
         int l = (int)n[6], r = (int)n[7];
         REQUIRE(l >= 0 && l < c->numNodes && r >= 0 && r < c->numNodes, PTB_ERR_INVALID_ARGUMENT, "child index out of range");
         const float* L = N + (size_t)l * 9; const float* R = N + (size_t)r * 9;
-        uint32_t lm = metaOf(N, l, err), rm = metaOf(N, r, err);
-        REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+        uint32_t lm = metaOf(N, l, c->S.numIndices, err), rm = metaOf(N, r, c->S.numIndices, err);
+        REQUIRE(err.empty(), err.find("past the end") != std::string::npos ? PTB_ERR_INVALID_ARGUMENT : PTB_ERR_UNSUPPORTED, err);
 #if PTB_PACKED_SLAB
         // pairs for the packed (f32x2) slab test: {Lmin.xy | Lmax.xy}, {Lmin.z Lmax.z | Rmin.z Rmax.z}, {Rmin.xy | Rmax.xy}
         q[0] = make_float4(L[0], L[1], L[3], L[4]);
@@ -213,8 +237,9 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
             if (k >= ni) continue;
             int root = (int)n[6];
             REQUIRE(root >= 0 && root < c->numNodes, PTB_ERR_INVALID_ARGUMENT, "BLAS root out of range");
-            rootMeta[k] = metaOf(N, root, err); matID[k] = (int)n[7]; blasRoot[k] = root;
-            REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
+            rootMeta[k] = metaOf(N, root, c->S.numIndices, err); matID[k] = (int)n[7]; blasRoot[k] = root;
+            REQUIRE(err.empty(), err.find("past the end") != std::string::npos ? PTB_ERR_INVALID_ARGUMENT : PTB_ERR_UNSUPPORTED, err);
+            REQUIRE(matID[k] >= 0 && matID[k] < c->S.numMaterials, PTB_ERR_INVALID_ARGUMENT, "TLAS leaf material id out of range");
         }
     }
     int maxBlas = 0;
@@ -245,11 +270,11 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
     CK(c->instShade.upload(is.data(), is.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));   // staging vectors die at scope exit
 
-    c->S.rootMeta = metaOf(N, c->topLevelIndex, err);
+    c->S.rootMeta = metaOf(N, c->topLevelIndex, c->S.numIndices, err);
     REQUIRE(err.empty(), PTB_ERR_UNSUPPORTED, err);
     c->S.inner = c->inner.p; c->S.instTrav = c->instTrav.p; c->S.instShade = c->instShade.p;
     (void)all;
-    return PTB_OK;
+    return configureDevice(c);
 }
 
 void refreshDerivedFlags(PtbCtx* c)
@@ -425,8 +450,9 @@ cudaEvent_t nextTraceEvent(PtbCtx* c)
 }
 
 // One wavefront: camera -> (trace, shade, shadow)* -> accumulate.
-int renderWave(PtbCtx* c, const FrameParams& F, WaveParams W, float4* previewOut)
+int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOut)
 {
+    c->pending.valid = false;                 // the wave state is about to be overwritten
     W.vw = (W.rw + 7) & ~7; W.vh = (W.rh + 3) & ~3;
     W.nSlots = (uint32_t)((size_t)W.vw * W.vh * W.nSamples);
     int rc = ensureWaveState(c, W.nSlots);
@@ -504,6 +530,9 @@ int allocFrameBuffers(PtbCtx* c)
 }
 
 } // namespace
+
+static void beginTiming(PtbCtx* c) { c->traceEventsUsed = 0; cudaEventRecord(c->evStart, c->stream); }
+static void endTiming(PtbCtx* c) { cudaEventRecord(c->evStop, c->stream); c->timingValid = true; }
 
 extern "C" {
 
@@ -595,7 +624,6 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     CK(c->dstats.alloc(1));
     CK(cudaMemsetAsync(c->dstats.p, 0, sizeof(DevStats), s));
     CK(cudaStreamSynchronize(s));
-    c->launchesAtCreate = (uint64_t)ptbk_kernel_launch_count();
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
     if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
@@ -610,7 +638,7 @@ int ptb_destroy(PtbCtx* c)
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
-    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release();
+    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
     c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->slotKeys.release(); c->slotSorted.release();
@@ -634,7 +662,7 @@ int ptb_set_options(PtbCtx* c, const PtbOptions* o)
     int cull = c->F.cullBoxes;
     refreshFrameParams(c);
     c->F.cullBoxes = cull;
-    if (resized) return allocFrameBuffers(c);
+    if (resized) { c->snapshot.release(); c->snapshotF.release(); c->pending.valid = false; return allocFrameBuffers(c); }
     return PTB_OK;
 }
 
@@ -664,6 +692,12 @@ int ptb_update_instances(PtbCtx* c, const float* transforms, int32_t numInstance
     REQUIRE(c && transforms && materials && tlasNodes, PTB_ERR_INVALID_ARGUMENT, "null argument");
     REQUIRE(numInstances == c->S.numInstances, PTB_ERR_INVALID_ARGUMENT, "instance count changed (the reference re-uploads the same-sized arrays)");
     REQUIRE(numTlasNodes == c->numNodes - c->topLevelIndex, PTB_ERR_INVALID_ARGUMENT, "TLAS slice size mismatch");
+    REQUIRE(numMaterials > 0, PTB_ERR_INVALID_ARGUMENT, "no materials");
+    for (int i = 0; i < numTlasNodes; i++)
+    {   // validate before anything is modified: a TLAS leaf must keep pointing at an existing material
+        const float* n = tlasNodes + (size_t)i * 9;
+        if ((int)n[8] < 0) REQUIRE((int)n[7] >= 0 && (int)n[7] < numMaterials, PTB_ERR_INVALID_ARGUMENT, "TLAS leaf material id out of range");
+    }
     CK(cudaSetDevice(c->device));
     c->hTransforms.assign(transforms, transforms + (size_t)numInstances * 16);
     c->hMaterials.assign(materials, materials + (size_t)numMaterials * 32);
@@ -673,6 +707,7 @@ int ptb_update_instances(PtbCtx* c, const float* transforms, int32_t numInstance
     CK(cudaMemcpyAsync(c->nodes.p + (size_t)c->topLevelIndex * 9, tlasNodes, (size_t)numTlasNodes * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->S.materials = c->materials.p; c->S.transforms = c->transforms.p; c->S.numMaterials = numMaterials;
+    c->sceneVersion++;
     int rc = deriveHierarchy(c, c->topLevelIndex, c->numNodes, false);
     if (rc) return rc;
     refreshDerivedFlags(c);
@@ -689,6 +724,7 @@ int ptb_update_envmap(PtbCtx* c, const float* img, const float* cdf, int32_t w, 
     CK(c->envCdf.upload(cdf, (size_t)w * h, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->S.envImg = c->envImg.p; c->S.envCdf = c->envCdf.p; c->S.envW = w; c->S.envH = h; c->S.envTotalSum = totalSum;
+    c->sceneVersion++;
     int cull = c->F.cullBoxes;
     refreshFrameParams(c);
     c->F.cullBoxes = cull;
@@ -703,8 +739,6 @@ int ptb_reset_accum(PtbCtx* c)
     return PTB_OK;
 }
 
-static void beginTiming(PtbCtx* c) { c->traceEventsUsed = 0; cudaEventRecord(c->evStart, c->stream); }
-static void endTiming(PtbCtx* c) { cudaEventRecord(c->evStop, c->stream); c->timingValid = true; }
 
 int ptb_render_tile(PtbCtx* c, int32_t tx, int32_t ty, int32_t frameNum)
 {
@@ -722,17 +756,55 @@ int ptb_render_tile(PtbCtx* c, int32_t tx, int32_t ty, int32_t frameNum)
     return rc;
 }
 
+static int samplesPerWave(const PtbCtx* c)
+{
+    int spw = c->opts.samplesPerWave;
+    if (spw <= 0)
+    {   // auto: keep ~16 M paths in flight (amortises the launch tails of the deep bounces; ~3 GB of path state)
+        size_t px = (size_t)c->F.renderW * c->F.renderH;
+        spw = (int)std::max<size_t>(1, std::min<size_t>(16, ((16u << 20) + px / 2) / std::max<size_t>(px, 1)));
+    }
+    return spw;
+}
+
+int ptb_render_pass(PtbCtx* c, int32_t sample, int32_t sampleStride, int32_t maxLookahead)
+{
+    REQUIRE(c && sample >= 1 && sampleStride >= 1, PTB_ERR_INVALID_ARGUMENT, "bad sample pass");
+    CK(cudaSetDevice(c->device));
+    PtbCtx::Pending& pd = c->pending;
+    if (pd.valid && sample == pd.first + pd.consumed * pd.stride && sampleStride == pd.stride && pd.consumed < pd.n && pd.sceneVersion == c->sceneVersion &&
+        memcmp(&pd.F, &c->F, sizeof(FrameParams)) == 0)
+    {   // this pass was traced with the wave of an earlier call under the same uniforms: add it to the running sum now
+        WaveParams W = pd.W;
+        W.accFirst = pd.consumed; W.accCount = 1;
+        ptbk_accumulate(cfg(c), pd.F, W, pathState(c), c->accum.p, nullptr);
+        CK(cudaGetLastError());
+        if (++pd.consumed == pd.n) pd.valid = false;
+        c->samplesRendered++;
+        return PTB_OK;
+    }
+    int n = samplesPerWave(c);
+    if (maxLookahead > 0) n = std::min(n, (int)maxLookahead);
+    const FrameParams F = c->F;
+    WaveParams W{};
+    W.x0 = 0; W.y0 = 0; W.rw = F.renderW; W.rh = F.renderH;
+    W.nSamples = n; W.firstSample = sample; W.sampleStride = sampleStride; W.fixedFrame = -1; W.previewMode = 0;
+    W.accFirst = 0; W.accCount = 1;
+    beginTiming(c);
+    int rc = renderWave(c, F, W, nullptr);
+    endTiming(c);
+    if (rc) return rc;
+    c->samplesRendered++;
+    if (n > 1) { pd.valid = true; pd.first = sample; pd.n = n; pd.consumed = 1; pd.stride = sampleStride; pd.sceneVersion = c->sceneVersion; pd.F = F; pd.W = W; }
+    return PTB_OK;
+}
+
 int ptb_render_samples(PtbCtx* c, int32_t firstSample, int32_t nSamples, int32_t sampleStride)
 {
     REQUIRE(c && firstSample >= 1 && nSamples >= 0 && sampleStride >= 1, PTB_ERR_INVALID_ARGUMENT, "bad sample range");
     CK(cudaSetDevice(c->device));
     const FrameParams& F = c->F;
-    int spw = c->opts.samplesPerWave;
-    if (spw <= 0)
-    {   // auto: keep ~16 M paths in flight (amortises the launch tails of the deep bounces; ~3 GB of path state)
-        size_t px = (size_t)F.renderW * F.renderH;
-        spw = (int)std::max<size_t>(1, std::min<size_t>(16, ((16u << 20) + px / 2) / std::max<size_t>(px, 1)));
-    }
+    const int spw = samplesPerWave(c);
     beginTiming(c);
     int done = 0;
     while (done < nSamples)
@@ -792,15 +864,72 @@ int ptb_accum_device_ptr(PtbCtx* c, void** p, uint64_t* nbytes)
     return PTB_OK;
 }
 
-int ptb_read_output_rgba8(PtbCtx* c, float invSampleCounter, uint8_t* out)
+int ptb_read_output_rgba8_from(PtbCtx* c, const void* devAccum, float invSampleCounter, uint8_t* out)
 {
     REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument");
     CK(cudaSetDevice(c->device));
     const PtbOptions& o = c->opts;
-    ptbk_tonemap(cfg(c), c->accum.p, o.renderW, o.renderH, invSampleCounter, o.enableTonemap, o.enableAces, o.simpleAcesFit, o.backgroundCol, c->F.features, c->out8.p);
+    ptbk_tonemap(cfg(c), devAccum ? (const float4*)devAccum : c->accum.p, o.renderW, o.renderH, invSampleCounter, o.enableTonemap, o.enableAces, o.simpleAcesFit,
+                 o.backgroundCol, c->F.features, c->out8.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, c->out8.p, (size_t)o.renderW * o.renderH * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_read_output_rgba8(PtbCtx* c, float invSampleCounter, uint8_t* out) { return ptb_read_output_rgba8_from(c, nullptr, invSampleCounter, out); }
+
+int ptb_snapshot_output(PtbCtx* c, float invSampleCounter) { return ptb_snapshot_output_from(c, nullptr, invSampleCounter); }
+
+int ptb_snapshot_output_from(PtbCtx* c, const void* devAccum, float invSampleCounter)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
+    const PtbOptions& o = c->opts;
+    CK(c->snapshot.alloc((size_t)o.renderW * o.renderH));
+    if (c->snapshotFloat) CK(c->snapshotF.alloc((size_t)o.renderW * o.renderH));
+    ptbk_tonemap(cfg(c), devAccum ? (const float4*)devAccum : c->accum.p, o.renderW, o.renderH, invSampleCounter, o.enableTonemap, o.enableAces, o.simpleAcesFit, o.backgroundCol, c->F.features,
+                 c->snapshot.p, c->snapshotFloat ? c->snapshotF.p : nullptr);
+    CK(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_read_snapshot_rgba8(PtbCtx* c, uint8_t* out)
+{
+    REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->opts.renderW * c->opts.renderH;
+    if (!c->snapshot.p || c->snapshot.n < n) { memset(out, 0, n * 4); return PTB_OK; }      // nothing completed yet: the cleared texture
+    CK(cudaMemcpyAsync(out, c->snapshot.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_set_snapshot_float(PtbCtx* c, int32_t enable) { REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context"); c->snapshotFloat = enable != 0; return PTB_OK; }
+
+int ptb_read_snapshot_rgb32f(PtbCtx* c, float* outRgb)
+{
+    REQUIRE(c && outRgb, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->opts.renderW * c->opts.renderH;
+    if (!c->snapshotF.p || c->snapshotF.n < n) { memset(outRgb, 0, n * 12); return PTB_OK; }
+    std::vector<float> tmp(n * 4);
+    CK(cudaMemcpyAsync(tmp.data(), c->snapshotF.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) { outRgb[i * 3] = tmp[i * 4]; outRgb[i * 3 + 1] = tmp[i * 4 + 1]; outRgb[i * 3 + 2] = tmp[i * 4 + 2]; }   // GL_RGB, GL_FLOAT
+    return PTB_OK;
+}
+
+int ptb_host_alloc(uint64_t nbytes, void** out)
+{
+    REQUIRE(out && nbytes > 0, PTB_ERR_INVALID_ARGUMENT, "bad argument");
+    CK(cudaMallocHost(out, (size_t)nbytes));
+    return PTB_OK;
+}
+
+int ptb_host_free(void* p)
+{
+    if (p) CK(cudaFreeHost(p));
     return PTB_OK;
 }
 
@@ -813,7 +942,7 @@ int ptb_get_stats(PtbCtx* c, PtbStats* out)
     CK(cudaMemcpy(&ds, c->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->pathSegments = ds.pathSegments; out->shadowRays = ds.shadowRays; out->samplesRendered = c->samplesRendered;
-    out->kernelLaunches = (uint64_t)ptbk_kernel_launch_count() - c->launchesAtCreate;
+    out->kernelLaunches = (uint64_t)c->launches;
     if (c->timingValid) cudaEventElapsedTime(&out->lastRenderMs, c->evStart, c->evStop);
     if (c->profiling)
     {
@@ -838,6 +967,7 @@ int ptb_set_profiling(PtbCtx* c, int32_t enable) { REQUIRE(c, PTB_ERR_INVALID_AR
 int ptb_set_stream(PtbCtx* c, void* s)
 {
     REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->ownStream;
     return PTB_OK;

@@ -82,6 +82,7 @@ struct WaveParams
     int fixedFrame;            // >= 0: use this frameNum for every pixel (ptb_render_tile); < 0: reference schedule
     int previewMode;           // preview.glsl: InitRNG(gl_FragCoord, 1), TexCoords over the whole image, depth 2
     uint32_t nSlots;           // vw*vh*nSamples
+    int accFirst, accCount;    // k_accumulate adds the wave's passes [accFirst, accFirst+accCount) to the running sum (accCount 0 = all of them)
 };
 
 // Path state fields are addressed as base + slot * stride.  stride = sizeof(T) gives SoA arrays; a common 128-byte (lights-only)
@@ -127,7 +128,13 @@ enum { CTR_NPATHS = 0, CTR_NSHA = 1, CTR_NSHB = 2, CTR_FETCH_TRACE = 3, CTR_FETC
 struct DevStats { unsigned long long pathSegments, shadowRays; };
 
 // ---- launchers implemented in ptb_kernels.cu ------------------------------------------------------------------
-struct LaunchCfg { int numSMs; void* stream; };
+struct LaunchCfg
+{
+    int numSMs; void* stream;
+    int traceBlocks;            // resident k_trace / k_shadow blocks per SM on this context's device (ptbk_configure_device)
+    int shadeBlocks[3];         // same for the three k_shade specialisations
+    unsigned long long* launches;   // per-context count of kernel launches (may be null)
+};
 
 void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
 void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
@@ -141,9 +148,9 @@ void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const Pa
                  uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);
 void ptbk_tonemap(const LaunchCfg&, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
-                  int simpleAcesFit, const float* backgroundCol3, uint32_t features, uchar4* out);
+                  int simpleAcesFit, const float* backgroundCol3, uint32_t features, uchar4* out, float4* outF = nullptr);
 void ptbk_trace_closest_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, long long n, int depth, void* hitsOut);
 void ptbk_trace_any_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, const float* maxDist, long long n, int* out);
 void ptbk_bsdf_batch(const LaunchCfg&, const void* queries, long long n, void* results, int sample);
 void ptbk_camera_rays(const LaunchCfg&, const FrameParams&, const WaveParams&, float* outRays);
-int  ptbk_kernel_launch_count();   // kernels launched so far by this process through the launchers above
+int  ptbk_configure_device(const DevScene&, int* traceBlocks, int shadeBlocks[3]);   // per-device attributes; returns a cudaError_t value

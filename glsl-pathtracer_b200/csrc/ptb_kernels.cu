@@ -15,8 +15,9 @@
 
 using namespace ptb;
 
-static int g_launches = 0;
-int ptbk_kernel_launch_count() { return g_launches; }
+// Launch bookkeeping is per context (LaunchCfg::launches) and the occupancy / shared-memory attributes are per device
+// (ptbk_configure_device): one process may hold one context per GPU.
+#define COUNT_LAUNCH(c, n) do { if ((c).launches) *(c).launches += (n); } while (0)
 
 #define OPT(F, bit) (((F).features & (bit)) != 0u)
 enum {
@@ -560,7 +561,9 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
         if (visible)
         {
             float3 f; float pdf;
-            if (isSurface) f = DisneyEvalFr(mat, eta, fr, lightDir, pdf);
+            // the phase function is only used by the OPT_MEDIUM && OPT_VOL_MIS branch (pathtrace.glsl:178-186); the binary-AnyHit
+            // branch evaluates DisneyEval with the boundary surface's material even for a medium scatter (:200)
+            if (isSurface || !volMis) f = DisneyEvalFr(mat, eta, fr, lightDir, pdf);
             else { float ph = PhaseHG(dot(-rd, lightDir), medAniso); f = f3(ph); pdf = ph; }
             if (pdf > 0.0f)
             {
@@ -591,7 +594,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
             if (visible)
             {
                 float3 f; float pdf;
-                if (isSurface) f = DisneyEvalFr(mat, eta, fr, ls.direction, pdf);
+                if (isSurface || !volMis) f = DisneyEvalFr(mat, eta, fr, ls.direction, pdf);        // pathtrace.glsl:246-254 vs :268
                 else { float ph = PhaseHG(dot(-rd, ls.direction), medAniso); f = f3(ph); pdf = ph; }
                 float misWeight = 1.0f;
                 if (area > 0.0f) misWeight = PowerHeuristic(ls.pdf, pdf);
@@ -705,8 +708,9 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
                         thr *= mcol;
                         ro += rd * scatterDist;
                         sf.fhp = ro;
-                        ShadeFrame noFrame;
-                        rad += directLight<MODE>(S, F, rd, sf, mat, eta, noFrame, false, aniso, thr, rng, sa, sb, ic, sink) * thr;
+                        ShadeFrame mfr;
+                        if (!OPT(F, O_VOLMIS)) frameSetup(mat, eta, -rd, sf.ffnormal, mfr);      // DisneyEval(state, ...) of the non-VOL_MIS branch
+                        rad += directLight<MODE>(S, F, rd, sf, mat, eta, mfr, false, aniso, thr, rng, sa, sb, ic, sink) * thr;
                         float hr1 = rng.rand(), hr2 = rng.rand();
                         float3 scatterDir = SampleHG(-rd, aniso, hr1, hr2);
                         prevPdf = PhaseHG(dot(-rd, scatterDir), aniso);
@@ -936,7 +940,8 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W,
         }
         float4* dst = accum + (size_t)(W.y0 + py) * F.renderW + (W.x0 + px);
         float4 a = *dst;
-        for (int k = 0; k < W.nSamples; k++)
+        const int k0 = W.accCount > 0 ? W.accFirst : 0, k1 = W.accCount > 0 ? W.accFirst + W.accCount : W.nSamples;
+        for (int k = k0; k < k1; k++)
         {
             const float4 r = P.rad[idx + (uint32_t)k * perSample];
             a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
@@ -947,7 +952,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W,
 
 // tonemap.glsl:44-133 + float->unorm8 of glGetTexImage (Renderer.cpp:633)
 __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
-                                                  int simpleAcesFit, float bgr, float bgg, float bgb, uint32_t features, uchar4* __restrict__ out)
+                                                  int simpleAcesFit, float bgr, float bgg, float bgb, uint32_t features, uchar4* __restrict__ out, float4* __restrict__ outF)
 {
     const int n = w * h;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -992,6 +997,7 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accu
         float4 o;
         if (features & (O_BG | O_TRANSPBG)) { float3 m = mix(bgCol, color, alpha); o = make_float4(m.x, m.y, m.z, outAlpha); }
         else o = make_float4(color.x, color.y, color.z, 1.0f);
+        if (outF) outF[i] = o;                  // the RGBA32F texel of tileOutputTexture before glGetTexImage's unorm8 conversion
         float v[4] = {o.x, o.y, o.z, o.w};
         unsigned char b[4];
 #pragma unroll
@@ -1087,42 +1093,47 @@ __global__ void k_camera_rays(FrameParams F, WaveParams W, float* out)
 static inline cudaStream_t st(const LaunchCfg& c) { return (cudaStream_t)c.stream; }
 static inline size_t stackBytes(const DevScene& S, int threads) { return (size_t)S.stackDepth * threads * sizeof(uint32_t); }
 
-static int traceBlocksPerSM(const DevScene& S)
+// Per-device kernel attributes for the current device: dynamic shared memory of the stack-carrying kernels (the default limit is 48 KB) and the
+// resident blocks per SM the persistent grids are sized with.  Called by the host side after cudaSetDevice whenever a context is created
+// or its stack depth changes; the results live in the context, not in process-wide statics.
+int ptbk_configure_device(const DevScene& S, int* traceBlocks, int shadeBlocks[3])
 {
-    static int cachedDepth = -1, cached = 0;
-    if (cachedDepth != S.stackDepth)
-    {
-        size_t smem = stackBytes(S, TRACE_THREADS);
-        cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace, TRACE_THREADS, smem);
-        cached = nb > 0 ? nb : 1; cachedDepth = S.stackDepth;
-    }
-    return cached;
+    const size_t smem = stackBytes(S, TRACE_THREADS);
+    cudaError_t e = cudaSuccess;
+    auto upd = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    upd(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace, TRACE_THREADS, smem));
+    *traceBlocks = nb > 0 ? nb : 1;
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[0], k_shade<0, 4>, SHADE_THREADS, 0));
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[1], k_shade<1, 5>, SHADE_THREADS, 0));
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[2], k_shade<2, 4>, SHADE_THREADS, 0));
+    for (int k = 0; k < 3; k++) if (shadeBlocks[k] < 1) shadeBlocks[k] = 1;
+    return (int)e;
 }
 
 void ptbk_camera(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, uint32_t* ctr0)
 {
     int blocks = c.numSMs * 8;
     k_camera<<<blocks, 256, 0, st(c)>>>(S, F, W, P, ctr0);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
                 const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey)
 {
-    int bps = traceBlocksPerSM(S);
+    const int bps = c.traceBlocks;
     k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist, nOverride, holeKey);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_sort_tile_local(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey, uint32_t nOverride)
 {
     k_sort_tile_local<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys, holeKey, nOverride);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
@@ -1131,68 +1142,61 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
     k_sort_scan<<<1, 32, 0, st(c)>>>(hist, cursor, numKeys);
     if (numKeys <= 4096) k_sort_scatter<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, cursor, sorted, numKeys);
     else k_sort_scatter_global<<<c.numSMs * 8, 256, 0, st(c)>>>(queue, keys, countPtr, cursor, sorted);
-    g_launches += 2;
+    COUNT_LAUNCH(c, 2);
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride)
 {
-    static int bps[3] = {0, 0, 0};
-    if (!bps[0])
-    {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], k_shade<0, 4>, SHADE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], k_shade<1, 5>, SHADE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[2], k_shade<2, 4>, SHADE_THREADS, 0);
-        for (int k = 0; k < 3; k++) if (bps[k] < 1) bps[k] = 1;
-    }
+    const int* bps = c.shadeBlocks;
     if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats)
 {
-    int bps = traceBlocksPerSM(S);
+    const int bps = c.traceBlocks;
     k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_accumulate(const LaunchCfg& c, const FrameParams& F, const WaveParams& W, const PathState& P, float4* accum, float4* previewOut)
 {
     k_accumulate<<<c.numSMs * 8, 256, 0, st(c)>>>(F, W, P, accum, previewOut);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_tonemap(const LaunchCfg& c, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
-                  int simpleAcesFit, const float* bg, uint32_t features, uchar4* out)
+                  int simpleAcesFit, const float* bg, uint32_t features, uchar4* out, float4* outF)
 {
-    k_tonemap<<<c.numSMs * 8, 256, 0, st(c)>>>(accum, w, h, invSampleCounter, enableTonemap, enableAces, simpleAcesFit, bg[0], bg[1], bg[2], features, out);
-    g_launches++;
+    k_tonemap<<<c.numSMs * 8, 256, 0, st(c)>>>(accum, w, h, invSampleCounter, enableTonemap, enableAces, simpleAcesFit, bg[0], bg[1], bg[2], features, out, outF);
+    COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_trace_closest_batch(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const float* rays, long long n, int depth, void* hitsOut)
 {
-    int bps = traceBlocksPerSM(S);
+    const int bps = c.traceBlocks;
     k_trace_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, rays, n, depth, (HitOut*)hitsOut);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 void ptbk_trace_any_batch(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const float* rays, const float* maxDist, long long n, int* out)
 {
-    int bps = traceBlocksPerSM(S);
+    const int bps = c.traceBlocks;
     k_any_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, rays, maxDist, n, out);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 void ptbk_bsdf_batch(const LaunchCfg& c, const void* queries, long long n, void* results, int sample)
 {
     if (n <= 0) return;
     k_bsdf_batch<<<(unsigned)((n + 127) / 128), 128, 0, st(c)>>>((const BsdfQuery*)queries, n, (BsdfResult*)results, sample);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }
 void ptbk_camera_rays(const LaunchCfg& c, const FrameParams& F, const WaveParams& W, float* outRays)
 {
     int n = F.renderW * F.renderH;
     k_camera_rays<<<(n + 255) / 256, 256, 0, st(c)>>>(F, W, outRays);
-    g_launches++;
+    COUNT_LAUNCH(c, 1);
 }

@@ -2,8 +2,20 @@
 #pragma once
 #include "Renderer.h"
 struct PtbCtx;
+struct PtbMgpu;
 namespace GLSLPT
 {
+    // GPUs a Renderer constructed afterwards will use (CUDA ordinals; default: PTB_DEVICES="0,1,..", else PTB_DEVICE, else 0).  With
+    // more than one, sample passes are sharded over the GPUs and GetOutputBuffer sees their NCCL-reduced sum.
+    void SetDevicesB200(const int* devices, int n);
+    // Denoiser hook in place of the reference's OIDN block (Renderer.cpp:695-728): called from Update() with the tonemapped image of
+    // the last completed pass (w*h*3 floats, GL_RGB/GL_FLOAT as the reference reads it) whenever the reference would run its filter
+    // (renderOptions.enableDenoiser, sampleCounter > 1, every denoiserFrameCnt passes).  nullptr (default) = no denoiser linked.
+    typedef void (*DenoiseFnB200)(const float* rgbIn, float* rgbOut, int w, int h, void* user);
+    void SetDenoiserB200(DenoiseFnB200 fn, void* user);
+    const float* DenoisedImageB200(Renderer& r);          // what the reference uploads to denoisedTexture (nullptr before the first run)
+    PtbMgpu* MgpuOfB200(Renderer& r);
+
     // Equivalent to n * numTiles.x * numTiles.y Update()+Render() pairs on a non-dirty scene, as ONE wavefront per batch of passes.
     void RenderSamplesB200(Renderer& r, Scene* scene, int n);
     // The C-ABI context behind a Renderer (stats, profiling).

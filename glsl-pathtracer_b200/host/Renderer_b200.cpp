@@ -16,6 +16,7 @@
 #include "RendererB200Ext.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -27,13 +28,33 @@ namespace GLSLPT
     {
         struct Side
         {
-            PtbCtx* ctx = nullptr;
+            PtbMgpu* m = nullptr;                          // one context per configured GPU (default: one, device PTB_DEVICE or 0)
+            PtbCtx* ctx0 = nullptr;                        // context of the first GPU: previews, single tiles, the frozen output image
             float invSampleCounter = 1.0f;                 // tonemap uniform (Renderer.cpp:806)
-            std::vector<unsigned char> completed;          // tileOutputTexture[1 - currentBuffer]
             std::vector<float> preview;                    // pathTraceTextureLowRes
             int samplesPerWave = 0;
+            uint32_t features = 0;                         // OPT_* set of the last InitShaders / ReloadShaders (Renderer.cpp:401-459)
+            bool coalesce = true;                          // a whole sample pass per first-tile Render() (PTB_COALESCE=0: one wave per tile)
+            bool passCoalesced = false;                    // the pass being walked was rendered at its first tile
+            std::vector<float> denoiseIn, denoiseOut;      // denoiserInputFramePtr / frameOutputPtr (Renderer.cpp:347-348)
         };
         std::map<const Renderer*, Side>& table() { static std::map<const Renderer*, Side> t; return t; }
+
+        // process-wide configuration set before a Renderer is constructed (RendererB200Ext.h)
+        std::vector<int>& configuredDevices() { static std::vector<int> d; return d; }
+        DenoiseFnB200& denoiser() { static DenoiseFnB200 f = nullptr; return f; }
+        void*& denoiserUser() { static void* u = nullptr; return u; }
+
+        std::vector<int> devicesFromEnv()
+        {   // SetDevicesB200() > PTB_DEVICES="0,1,2,3" > PTB_DEVICE="1" > device 0
+            if (!configuredDevices().empty()) return configuredDevices();
+            std::vector<int> d;
+            if (const char* e = getenv("PTB_DEVICES"))
+                for (const char* p = e; *p;) { d.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p == ',') p++; }
+            else if (const char* e1 = getenv("PTB_DEVICE")) d.push_back(atoi(e1));
+            if (d.empty()) d.push_back(0);
+            return d;
+        }
 
         void check(int rc, const char* what)
         {
@@ -61,23 +82,31 @@ namespace GLSLPT
             return d;
         }
 
-        PtbOptions options(Scene* s, int samplesPerWave)
-        {   // the #defines of InitShaders (Renderer.cpp:401-459) and the uniforms of Update (Renderer.cpp:776-782, 806-810)
+        uint32_t deriveFeatures(Scene* s);
+
+        PtbOptions options(Scene* s, int samplesPerWave, uint32_t features)
+        {   // the uniforms of Update (Renderer.cpp:776-782, 806-810) + the feature set the shaders were last compiled with
             const RenderOptions& ro = s->renderOptions;
             PtbOptions o; memset(&o, 0, sizeof(o));
             o.renderW = ro.renderResolution.x; o.renderH = ro.renderResolution.y; o.tileW = ro.tileWidth; o.tileH = ro.tileHeight;
             o.maxDepth = ro.maxDepth; o.rrDepth = ro.RRDepth;
-            uint32_t bools = (ro.enableEnvMap ? 1u : 0u) | (ro.enableRR ? 2u : 0u) | (ro.enableUniformLight ? 4u : 0u) | (ro.openglNormalMap ? 8u : 0u) |
-                             (ro.hideEmitters ? 16u : 0u) | (ro.enableBackground ? 32u : 0u) | (ro.transparentBackground ? 64u : 0u) |
-                             (ro.enableRoughnessMollification ? 128u : 0u) | (ro.enableVolumeMIS ? 256u : 0u);
-            PtbSceneDesc d = describe(s);
-            o.features = ptb_derive_features(&d, bools);
+            o.features = features;
             o.envMapIntensity = ro.envMapIntensity; o.envMapRot = ro.envMapRot; o.roughnessMollificationAmt = ro.roughnessMollificationAmt;
             o.uniformLightCol[0] = ro.uniformLightCol.x; o.uniformLightCol[1] = ro.uniformLightCol.y; o.uniformLightCol[2] = ro.uniformLightCol.z;
             o.backgroundCol[0] = ro.backgroundCol.x; o.backgroundCol[1] = ro.backgroundCol.y; o.backgroundCol[2] = ro.backgroundCol.z;
             o.enableTonemap = ro.enableTonemap; o.enableAces = ro.enableAces; o.simpleAcesFit = ro.simpleAcesFit;
             o.samplesPerWave = samplesPerWave;
             return o;
+        }
+
+        uint32_t deriveFeatures(Scene* s)
+        {   // the #defines of InitShaders (Renderer.cpp:401-459): evaluated where the reference compiles shaders, not per frame
+            const RenderOptions& ro = s->renderOptions;
+            uint32_t bools = (ro.enableEnvMap ? 1u : 0u) | (ro.enableRR ? 2u : 0u) | (ro.enableUniformLight ? 4u : 0u) | (ro.openglNormalMap ? 8u : 0u) |
+                             (ro.hideEmitters ? 16u : 0u) | (ro.enableBackground ? 32u : 0u) | (ro.transparentBackground ? 64u : 0u) |
+                             (ro.enableRoughnessMollification ? 128u : 0u) | (ro.enableVolumeMIS ? 256u : 0u);
+            PtbSceneDesc d = describe(s);
+            return ptb_derive_features(&d, bools);
         }
 
         PtbCamera camera(Scene* s)
@@ -110,8 +139,12 @@ namespace GLSLPT
 
         Side& sd = table()[this];
         PtbSceneDesc d = describe(scene);                    // InitGPUDataBuffers
-        PtbOptions o = options(scene, sd.samplesPerWave);    // InitShaders: feature selection instead of GLSL compilation
-        check(ptb_create(&d, &o, 0, &sd.ctx), "ptb_create");
+        sd.features = deriveFeatures(scene);                 // InitShaders: feature selection instead of GLSL compilation
+        PtbOptions o = options(scene, sd.samplesPerWave, sd.features);
+        std::vector<int> devs = devicesFromEnv();
+        check(ptb_mgpu_create(&d, &o, devs.data(), (int)devs.size(), &sd.m), "ptb_mgpu_create");
+        sd.ctx0 = ptb_mgpu_context(sd.m, 0);
+        if (const char* e = getenv("PTB_COALESCE")) sd.coalesce = atoi(e) != 0;
         pixelRatio = 0.25f;
         InitFBOs();
         initialized = true;
@@ -120,7 +153,7 @@ namespace GLSLPT
     Renderer::~Renderer()
     {
         auto it = table().find(this);
-        if (it != table().end()) { ptb_destroy(it->second.ctx); table().erase(it); }
+        if (it != table().end()) { ptb_mgpu_destroy(it->second.m); table().erase(it); }
     }
 
     void Renderer::InitGPUDataBuffers() {}                   // done by ptb_create
@@ -135,8 +168,7 @@ namespace GLSLPT
         numTiles.x = ceil((float)renderSize.x / tileWidth); numTiles.y = ceil((float)renderSize.y / tileHeight);
         tile.x = -1; tile.y = numTiles.y - 1;
         Side& sd = table()[this];
-        sd.completed.assign((size_t)renderSize.x * renderSize.y * 4, 0);
-        sd.invSampleCounter = 1.0f;
+        sd.invSampleCounter = 1.0f; sd.passCoalesced = false;
         printf("Window Resolution : %d %d\n", windowSize.x, windowSize.y);
         printf("Render Resolution : %d %d\n", renderSize.x, renderSize.y);
         printf("Preview Resolution : %d %d\n", (int)((float)windowSize.x * pixelRatio), (int)((float)windowSize.y * pixelRatio));
@@ -146,17 +178,18 @@ namespace GLSLPT
     void Renderer::ResizeRenderer()
     {   // Renderer.cpp:251-279
         Side& sd = table()[this];
-        PtbOptions o = options(scene, sd.samplesPerWave);
-        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
-        check(ptb_resize(sd.ctx, o.renderW, o.renderH, o.tileW, o.tileH), "ptb_resize");
+        PtbOptions o = options(scene, sd.samplesPerWave, sd.features);
+        check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");     // new size: buffers reallocated, frozen image dropped
+        check(ptb_mgpu_reset_accum(sd.m), "ptb_reset_accum");         // the reference re-creates (clears) every FBO texture
         InitFBOs();
     }
 
     void Renderer::ReloadShaders()
     {   // Renderer.cpp:381-390: re-derive the OPT_* set
         Side& sd = table()[this];
-        PtbOptions o = options(scene, sd.samplesPerWave);
-        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
+        sd.features = deriveFeatures(scene);
+        PtbOptions o = options(scene, sd.samplesPerWave, sd.features);
+        check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");
     }
 
     void Renderer::Render()
@@ -168,13 +201,31 @@ namespace GLSLPT
         {
             int w = (int)(windowSize.x * pixelRatio), h = (int)(windowSize.y * pixelRatio);
             sd.preview.resize((size_t)w * h * 4);
-            check(ptb_render_preview(sd.ctx, w, h, sd.preview.data()), "ptb_render_preview");
+            check(ptb_render_preview(sd.ctx0, w, h, sd.preview.data()), "ptb_render_preview");
             scene->instancesModified = false;
             scene->dirty = false;
             scene->envMapModified = false;
+            return;
         }
-        else
-            check(ptb_render_tile(sd.ctx, tile.x, tile.y, frameCounter), "ptb_render_tile");
+        // Only the buffer of a COMPLETED pass is observable (GetOutputBuffer reads tileOutputTexture[1-currentBuffer],
+        // Renderer.cpp:628-633), so the numTiles draws of a pass are coalesced: the whole pass is rendered as one wavefront when its
+        // first tile is drawn — same frameNum per tile and same tile-local seeds as the tile walk would use (ptb_render_pass) — and
+        // the remaining tiles of the pass draw nothing.  A pass that does not start on the regular schedule falls back to one wave per tile.
+        const int T = numTiles.x * numTiles.y;
+        const bool firstTile = tile.x == 0 && tile.y == numTiles.y - 1;
+        if (firstTile)
+        {
+            sd.passCoalesced = sd.coalesce && frameCounter == 2 + (sampleCounter - 1) * T;
+            if (sd.passCoalesced)
+            {
+                const int maxSpp = scene->renderOptions.maxSpp;
+                const int N = ptb_mgpu_num_devices(sd.m);
+                const int remaining = maxSpp == -1 ? 0 : (maxSpp - sampleCounter + N - 1) / N;      // passes this GPU still has to render (Q1: maxSpp-1 in total)
+                check(ptb_mgpu_render_pass(sd.m, sampleCounter, remaining), "ptb_render_pass");
+            }
+        }
+        if (!sd.passCoalesced)
+            check(ptb_render_tile(sd.ctx0, tile.x, tile.y, frameCounter), "ptb_render_tile");
     }
 
     void Renderer::Present() {}                              // Renderer.cpp:592-611 draws to the window: nothing to do headless
@@ -190,7 +241,7 @@ namespace GLSLPT
         w = renderSize.x; h = renderSize.y;
         *data = new unsigned char[w * h * 4];
         Side& sd = table()[this];
-        memcpy(*data, sd.completed.data(), (size_t)w * h * 4);
+        check(ptb_mgpu_read_snapshot_rgba8(sd.m, *data), "ptb_read_snapshot_rgba8");     // the glGetTexImage: the only host copy of the image
     }
 
     int Renderer::GetSampleCount() { return sampleCounter; }
@@ -204,19 +255,33 @@ namespace GLSLPT
         if (scene->instancesModified)
         {
             int top = scene->bvhTranslator.topLevelIndex;
-            check(ptb_update_instances(sd.ctx, (const float*)scene->transforms.data(), (int)scene->transforms.size(), (const float*)scene->materials.data(),
+            check(ptb_mgpu_update_instances(sd.m, (const float*)scene->transforms.data(), (int)scene->transforms.size(), (const float*)scene->materials.data(),
                                        (int)scene->materials.size(), (const float*)&scene->bvhTranslator.nodes[top],
                                        (int)scene->bvhTranslator.nodes.size() - top), "ptb_update_instances");
         }
         if (scene->envMapModified && scene->envMap != nullptr)
-            check(ptb_update_envmap(sd.ctx, scene->envMap->img, scene->envMap->cdf, scene->envMap->width, scene->envMap->height, scene->envMap->totalSum),
+            check(ptb_mgpu_update_envmap(sd.m, scene->envMap->img, scene->envMap->cdf, scene->envMap->width, scene->envMap->height, scene->envMap->totalSum),
                   "ptb_update_envmap");
-        denoised = false;                                    // OIDN (Renderer.cpp:695-730) stays out of the hot path
+        // Denoiser hook (Renderer.cpp:695-730): same trigger and cadence as the reference; the filter itself (OIDN there) is whatever
+        // the host registered with SetDenoiserB200 — without one the branch leaves `denoised` false, as a build without OIDN would.
+        if (scene->renderOptions.enableDenoiser && sampleCounter > 1 && denoiser())
+        {
+            if (!denoised || (frameCounter % (scene->renderOptions.denoiserFrameCnt * (numTiles.x * numTiles.y)) == 0))
+            {
+                const size_t n = (size_t)renderSize.x * renderSize.y * 3;
+                sd.denoiseIn.resize(n); sd.denoiseOut.resize(n);
+                check(ptb_read_snapshot_rgb32f(sd.ctx0, sd.denoiseIn.data()), "ptb_read_snapshot_rgb32f");    // glGetTexImage(GL_RGB, GL_FLOAT)
+                denoiser()(sd.denoiseIn.data(), sd.denoiseOut.data(), renderSize.x, renderSize.y, denoiserUser());
+                denoised = true;
+            }
+        }
+        else
+            denoised = false;
         if (scene->dirty)
         {
             tile.x = -1; tile.y = numTiles.y - 1;
             sampleCounter = 1; denoised = false; frameCounter = 1;
-            check(ptb_reset_accum(sd.ctx), "ptb_reset_accum");
+            check(ptb_mgpu_reset_accum(sd.m), "ptb_reset_accum");
         }
         else
         {
@@ -231,16 +296,18 @@ namespace GLSLPT
                     tile.x = 0;
                     tile.y = numTiles.y - 1;
                     // the buffer tonemapped with the finished pass's uniform becomes the displayed one (Renderer.cpp:584-588,758)
-                    check(ptb_read_output_rgba8(sd.ctx, sd.invSampleCounter, sd.completed.data()), "ptb_read_output_rgba8");
+                    // Frozen on the device (asynchronous; with several GPUs: one NCCL reduce into a scratch sum first); copied to the host only
+                    // when GetOutputBuffer asks.
+                    check(ptb_mgpu_snapshot_output(sd.m, sd.invSampleCounter), "ptb_snapshot_output");
                     sampleCounter++;
                     currentBuffer = 1 - currentBuffer;
                 }
             }
         }
         PtbCamera cam = camera(scene);
-        check(ptb_set_camera(sd.ctx, &cam), "ptb_set_camera");
-        PtbOptions o = options(scene, sd.samplesPerWave);
-        check(ptb_set_options(sd.ctx, &o), "ptb_set_options");
+        check(ptb_mgpu_set_camera(sd.m, &cam), "ptb_set_camera");
+        PtbOptions o = options(scene, sd.samplesPerWave, sd.features);      // uniforms only: the OPT_* set changes in ReloadShaders, as in the reference
+        check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");
         sd.invSampleCounter = 1.0f / (sampleCounter);
     }
 
@@ -249,11 +316,15 @@ namespace GLSLPT
     {
         Side& sd = table()[&r];
         PtbCamera cam = camera(scene);
-        check(ptb_set_camera(sd.ctx, &cam), "ptb_set_camera");
+        check(ptb_mgpu_set_camera(sd.m, &cam), "ptb_set_camera");
         int first = r.GetSampleCount();
-        check(ptb_render_samples(sd.ctx, first, n, 1), "ptb_render_samples");
+        check(ptb_mgpu_render_samples(sd.m, first, n), "ptb_render_samples");
         RendererB200Access::advance(r, n);
-        check(ptb_read_output_rgba8(sd.ctx, 1.0f / (float)(first + n - 1), sd.completed.data()), "ptb_read_output_rgba8");
+        check(ptb_mgpu_snapshot_output(sd.m, 1.0f / (float)(first + n - 1)), "ptb_snapshot_output");
     }
-    PtbCtx* ContextOfB200(Renderer& r) { return table()[&r].ctx; }
+    PtbCtx* ContextOfB200(Renderer& r) { return table()[&r].ctx0; }
+    PtbMgpu* MgpuOfB200(Renderer& r) { return table()[&r].m; }
+    void SetDevicesB200(const int* devices, int n) { configuredDevices().assign(devices, devices + (n > 0 ? n : 0)); }
+    void SetDenoiserB200(DenoiseFnB200 fn, void* user) { denoiser() = fn; denoiserUser() = user; }
+    const float* DenoisedImageB200(Renderer& r) { Side& sd = table()[&r]; return sd.denoiseOut.empty() ? nullptr : sd.denoiseOut.data(); }
 }

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <chrono>
+#include <vector>
 #include "Scene.h"
 #include "Loader.h"
 #include "GLTFLoader.h"
@@ -18,7 +19,8 @@ using namespace GLSLPT;
 int main(int argc, char** argv)
 {
     std::string sceneFile, out = "out.png", accumOut;
-    int spp = 16, w = 0, h = 0, depth = -1; bool whole = false;
+    int spp = 16, w = 0, h = 0, depth = -1, warmup = 0, denoiseEvery = 0; bool whole = false;
+    static int denoiseCalls = 0;
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i];
@@ -29,7 +31,12 @@ int main(int argc, char** argv)
         else if (a == "--depth" && i + 1 < argc) depth = atoi(argv[++i]);
         else if (a == "--accum" && i + 1 < argc) accumOut = argv[++i];
         else if (a == "--whole-frame") whole = true;
-        else { printf("usage: ptb_headless -s file.scene [-o out.png] [--spp N] [--res W H] [--depth D] [--whole-frame] [--accum file.f32]\n"); return 2; }
+        else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);          // passes rendered before the clock starts (same loop)
+        else if (a == "--no-coalesce") setenv("PTB_COALESCE", "0", 1);               // one wavefront per Render() tile, as the reference draws
+        else if (a == "--devices" && i + 1 < argc) setenv("PTB_DEVICES", argv[++i], 1);   // "0,1,2,3"
+        else if (a == "--denoise-every" && i + 1 < argc) denoiseEvery = atoi(argv[++i]);  // exercise the denoiser hook with a stand-in filter
+        else { printf("usage: ptb_headless -s file.scene [-o out.png] [--spp N] [--warmup N] [--res W H] [--depth D] [--whole-frame] [--no-coalesce] "
+                      "[--devices 0,1,..] [--denoise-every N] [--accum file.f32]\n"); return 2; }
     }
     if (sceneFile.empty()) { printf("no scene\n"); return 2; }
 
@@ -47,32 +54,53 @@ int main(int argc, char** argv)
     }
     if (w > 0) { renderOptions.renderResolution = iVec2(w, h); renderOptions.windowResolution = iVec2(w, h); }
     if (depth >= 0) renderOptions.maxDepth = depth;
-    renderOptions.maxSpp = spp + 1;                      // Q1: maxSpp = M renders M-1 passes
+    renderOptions.maxSpp = warmup + spp + 1;             // Q1: maxSpp = M renders M-1 passes
+    if (denoiseEvery > 0) { renderOptions.enableDenoiser = true; renderOptions.denoiserFrameCnt = denoiseEvery; }
     scene->renderOptions = renderOptions;                // Main.cpp:154
+    if (denoiseEvery > 0)      // stand-in for OIDN: the hook, its trigger and its cadence are the deliverable, not the filter
+        SetDenoiserB200([](const float* in, float* out, int w_, int h_, void*) { denoiseCalls++; memcpy(out, in, (size_t)w_ * h_ * 12); }, nullptr);
 
     Renderer* renderer = new Renderer(scene, "shaders/");
     auto t0 = std::chrono::steady_clock::now();
+    unsigned char* data = nullptr; int ow, oh;
+    PtbStats st0{}; long long updates = 0;
     if (whole)
     {
         renderer->Update(0.f); renderer->Render();       // the dirty / preview frame
+        if (warmup > 0) { RenderSamplesB200(*renderer, scene, warmup); ptb_mgpu_synchronize(MgpuOfB200(*renderer)); ptb_mgpu_get_stats(MgpuOfB200(*renderer), &st0); t0 = std::chrono::steady_clock::now(); }
         RenderSamplesB200(*renderer, scene, spp);
     }
     else
-        while (renderer->GetSampleCount() < renderOptions.maxSpp) { renderer->Update(0.016f); renderer->Render(); renderer->Present(); }
-    PtbStats st; ptb_get_stats(ContextOfB200(*renderer), &st);
+    {   // the application loop of Main.cpp:175-213, 263: one Update + one Render (one tile) + Present per iteration
+        bool clockStarted = warmup == 0;
+        while (renderer->GetSampleCount() < renderOptions.maxSpp)
+        {
+            if (!clockStarted && renderer->GetSampleCount() >= warmup + 1)
+            {
+                renderer->GetOutputBuffer(&data, ow, oh); delete[] data;      // drains the GPU: the timed region starts idle
+                ptb_mgpu_get_stats(MgpuOfB200(*renderer), &st0);
+                t0 = std::chrono::steady_clock::now(); clockStarted = true;
+            }
+            renderer->Update(0.016f); renderer->Render(); renderer->Present(); updates++;
+        }
+    }
+    renderer->GetOutputBuffer(&data, ow, oh);            // SaveFrame, Main.cpp:164-173: the one device->host copy (inside the timed region)
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    PtbStats st; ptb_mgpu_get_stats(MgpuOfB200(*renderer), &st);
     printf("rendered %d spp in %.3f s (%.1f spp/s), %llu path segments, %llu shadow rays, %llu kernel launches\n", spp, sec, spp / sec,
-           (unsigned long long)st.pathSegments, (unsigned long long)st.shadowRays, (unsigned long long)st.kernelLaunches);
+           (unsigned long long)(st.pathSegments - st0.pathSegments), (unsigned long long)(st.shadowRays - st0.shadowRays), (unsigned long long)(st.kernelLaunches - st0.kernelLaunches));
+    printf("BENCH {\"spp\": %d, \"seconds\": %.6f, \"path_segments\": %llu, \"shadow_rays\": %llu, \"kernel_launches\": %llu, \"updates\": %lld, \"gpus\": %d, "
+           "\"coalesced\": %s, \"whole_frame\": %s, \"denoiser_calls\": %d}\n", spp, sec, (unsigned long long)(st.pathSegments - st0.pathSegments),
+           (unsigned long long)(st.shadowRays - st0.shadowRays), (unsigned long long)(st.kernelLaunches - st0.kernelLaunches), updates, ptb_mgpu_num_devices(MgpuOfB200(*renderer)),
+           (getenv("PTB_COALESCE") && atoi(getenv("PTB_COALESCE")) == 0) ? "false" : "true", whole ? "true" : "false", denoiseCalls);
 
-    unsigned char* data = nullptr; int ow, oh;
-    renderer->GetOutputBuffer(&data, ow, oh);            // SaveFrame, Main.cpp:164-173
     stbi_flip_vertically_on_write(true);
     stbi_write_png(out.c_str(), ow, oh, 4, data, ow * 4);
     delete[] data;
     if (!accumOut.empty())
     {
         std::vector<float> acc((size_t)ow * oh * 4);
-        ptb_read_accum_f32(ContextOfB200(*renderer), acc.data());
+        ptb_mgpu_read_accum_f32(MgpuOfB200(*renderer), acc.data());
         FILE* f = fopen(accumOut.c_str(), "wb"); fwrite(acc.data(), 4, acc.size(), f); fclose(f);
     }
     printf("wrote %s (%dx%d)\n", out.c_str(), ow, oh);

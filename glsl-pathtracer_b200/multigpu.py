@@ -22,13 +22,20 @@ def passes_of(first: int, total: int, rank: int, world: int):
     return [f + i * s for i in range(c)]
 
 
-def reduce_accum(accum_tensor, dst: int = 0, group=None):
-    """Sum the per-rank running sums onto rank `dst` (in place).  `accum_tensor` is a torch tensor viewing the accumulation
-    buffer: a CUDA tensor over `ptb_accum_device_ptr` with the nccl backend, a CPU tensor with gloo."""
+def reduce_accum(accum_tensor, dst: int = 0, group=None, scratch=None):
+    """Sum of the per-rank running sums, delivered on rank `dst` in a SCRATCH tensor (returned; `scratch` is reused if given).
+    The running sums themselves are never modified: each rank's buffer stays the partial sum of its own passes, so the image can be
+    read back any number of times while rendering goes on (an in-place reduce would fold the other ranks' earlier passes into rank
+    dst's buffer again at every readback).  `accum_tensor` views the accumulation buffer: a CUDA tensor over `ptb_accum_device_ptr`
+    with the nccl backend, a CPU tensor with gloo.  On ranks other than `dst` the returned tensor's content is unspecified."""
+    import torch
     import torch.distributed as dist
+    if scratch is None or scratch.shape != accum_tensor.shape or scratch.device != accum_tensor.device:
+        scratch = torch.empty_like(accum_tensor)
+    scratch.copy_(accum_tensor)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.reduce(accum_tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    return accum_tensor
+        dist.reduce(scratch, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return scratch
 
 
 class DeviceAccumView:
@@ -51,6 +58,12 @@ class ShardedRenderer:
     def __init__(self, ctx, rank: int, world: int, reduce_fn=reduce_accum):
         self.ctx, self.rank, self.world, self.reduce_fn = ctx, rank, world, reduce_fn
         self.next_pass = 1
+        self._scratch = None
+
+    def reduced(self, accum_tensor, dst: int = 0):
+        """The summed image so far on rank `dst` (scratch tensor); safe to call between render() batches."""
+        self._scratch = self.reduce_fn(accum_tensor, dst=dst, scratch=self._scratch)
+        return self._scratch
 
     def render(self, total_passes: int):
         f, c, s = shard_passes(self.next_pass, total_passes, self.rank, self.world)

@@ -11,7 +11,7 @@ from . import capi
 
 
 class Renderer:
-    def __init__(self, scene, shadersDirectory: str = "", device: int = 0, samples_per_wave: int = 0):
+    def __init__(self, scene, shadersDirectory: str = "", device: int = 0, samples_per_wave: int = 0, coalesce: bool = True):
         """Renderer::Renderer (Renderer.cpp:41-87).  `shadersDirectory` is accepted for signature parity and ignored:
         the OPT_* defines select precompiled sm_100a kernels instead of GLSL sources."""
         self.scene = scene
@@ -22,6 +22,7 @@ class Renderer:
             return
         # (scene->initialized / ProcessScene: scene blobs are always processed, Renderer.cpp:78-79)
         self.ctx = capi.Context(scene, device=device, samples_per_wave=samples_per_wave)      # InitGPUDataBuffers + InitShaders
+        self.coalesce = coalesce                         # a whole sample pass per first-tile Render() (False: one wavefront per tile)
         self.pixelRatio = 0.25                           # Renderer.cpp:83
         self._init_fbos()
 
@@ -38,8 +39,8 @@ class Renderer:
         self.numTiles = (int(math.ceil(np.float32(self.renderSize[0]) / np.float32(self.tileWidth))),
                          int(math.ceil(np.float32(self.renderSize[1]) / np.float32(self.tileHeight))))
         self.tile = [-1, self.numTiles[1] - 1]
-        self._completed = None            # tileOutputTexture[1-currentBuffer]: tonemapped image of the last completed pass
-        self._completed_inv = 1.0
+        self._have_completed = False      # tileOutputTexture[1-currentBuffer] lives on the device (ctx.snapshot_output)
+        self._pass_coalesced = False
         self._preview = None
         self._invSampleCounter = 1.0
         self._maxDepthUniform = ro.maxDepth
@@ -75,10 +76,16 @@ class Renderer:
             sc.dirty = False
             sc.envMapModified = False
         else:
-            self.ctx.render_tile(self.tile[0], self.tile[1], self.frameCounter)
-            # the tonemap pass of Render() writes tileOutputTexture[currentBuffer] after every tile; only the state after
-            # the last tile of a pass is ever read back (Renderer.cpp:584-588,628-633), so it is evaluated lazily there.
-            self._pending_inv = self._invSampleCounter
+            # Only the buffer of a completed pass is observable (Renderer.cpp:628-633): the whole pass is rendered as one wavefront at
+            # its first tile (same frameNum per tile, same tile-local seeds), the other tiles of the pass draw nothing.
+            T = self.numTiles[0] * self.numTiles[1]
+            if self.tile[0] == 0 and self.tile[1] == self.numTiles[1] - 1:
+                self._pass_coalesced = self.coalesce and self.frameCounter == 2 + (self.sampleCounter - 1) * T
+                if self._pass_coalesced:
+                    maxSpp = sc.renderOptions.maxSpp
+                    self.ctx.render_pass(self.sampleCounter, 0 if maxSpp == -1 else maxSpp - self.sampleCounter)
+            if not self._pass_coalesced:
+                self.ctx.render_tile(self.tile[0], self.tile[1], self.frameCounter)
 
     def Present(self):
         """Renderer.cpp:592-611 draws to the window; headless build: no-op."""
@@ -94,9 +101,7 @@ class Renderer:
     def GetOutputBuffer(self):
         """Renderer.cpp:619-634: tonemapped RGBA8 of the last COMPLETED pass, bottom row first.  Returns (data, w, h)."""
         w, h = self.renderSize
-        if self._completed is None:
-            return np.zeros((h, w, 4), np.uint8), w, h
-        return self._completed, w, h
+        return self.ctx.read_snapshot(), w, h            # zeros before the first completed pass (the cleared texture)
 
     def Update(self, secondsElapsed: float):
         """Renderer.cpp:641-812"""
@@ -123,7 +128,7 @@ class Renderer:
                     self.tile[0] = 0
                     self.tile[1] = self.numTiles[1] - 1
                     # all tiles of a pass done: the buffer written with the uniform of that pass becomes the displayed one
-                    self._completed = self.ctx.read_output(self._invSampleCounter)
+                    self.ctx.snapshot_output(self._invSampleCounter)      # frozen on the device; copied to the host by GetOutputBuffer
                     self.sampleCounter += 1
                     self.currentBuffer = 1 - self.currentBuffer
         # uniforms (:766-811)
@@ -140,4 +145,4 @@ class Renderer:
         T = self.numTiles[0] * self.numTiles[1]
         self.frameCounter += n * T
         self.sampleCounter += n
-        self._completed = self.ctx.read_output(float(np.float32(1.0) / np.float32(self.sampleCounter - 1)))
+        self.ctx.snapshot_output(float(np.float32(1.0) / np.float32(self.sampleCounter - 1)))

@@ -1,5 +1,5 @@
 """Scene blobs: the arrays `Renderer::InitGPUDataBuffers` uploads (reference Renderer.cpp:135-249), as dumped
-by the unmodified reference host code (oracle/ref_host/scene_dump.cpp) into a `.ptscene` file.
+by the unmodified reference host code (the `scene_dump` tool of the test infrastructure) into a `.ptscene` file.
 
 Host-side data contract only - no compute happens here.
 """
@@ -8,7 +8,7 @@ import lzma, os, struct
 from dataclasses import dataclass, field
 import numpy as np
 
-# Mirrors `struct Scalars` in oracle/ref_host/scene_dump.cpp (camera: Camera.h:46-54, options: Renderer.h:37-100).
+# Mirrors `struct Scalars` of the scene_dump tool (camera: Camera.h:46-54, options: Renderer.h:37-100).
 _SCALARS = np.dtype([
     ("topLevelIndex", "<i4"), ("numNodes", "<i4"), ("numIndices", "<i4"), ("numVertices", "<i4"), ("numMaterials", "<i4"),
     ("numInstances", "<i4"), ("numLights", "<i4"), ("numTextures", "<i4"),
@@ -170,11 +170,11 @@ def load_ptscene(path: str) -> Scene:
 
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SCENE_DIRS = [os.path.join(_ROOT, "tests", "golden", "scenes"), os.path.join(_ROOT, "oracle", "_ref", "scenes")]
+SCENE_DIRS = [d for d in os.environ.get("PTB_SCENE_DIRS", "").split(os.pathsep) if d] + [os.path.join(_ROOT, "tests", "golden", "scenes")]
 
 
 def find_scene(name: str) -> str:
-    """Locate `<name>.ptscene[.xz]` in tests/golden/scenes (committed fixtures) or oracle/_ref/scenes (built here)."""
+    """Locate `<name>.ptscene[.xz]` in $PTB_SCENE_DIRS or tests/golden/scenes (committed fixtures)."""
     for d in SCENE_DIRS:
         for ext in (".ptscene", ".ptscene.xz"):
             p = os.path.join(d, name + ext)

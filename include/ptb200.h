@@ -138,6 +138,14 @@ int  ptb_render_tile(PtbCtx* ctx, int32_t tx, int32_t ty, int32_t frameNum);
  * (Renderer.cpp:745-783, tile.glsl:45), so the sum equals nSamples x numTiles Render() calls.
  * sampleStride > 1 renders passes firstSample, firstSample+stride, ... (multi-GPU sample sharding). */
 int  ptb_render_samples(PtbCtx* ctx, int32_t firstSample, int32_t nSamples, int32_t sampleStride);
+/* One sample pass of the WHOLE frame for a host that keeps the reference's one-tile-per-Render() loop (Main.cpp:175-212,
+ * Renderer.cpp:566-589, 745-762): called at the first tile of pass `sample`, it replaces the numTiles Render() draws of that pass —
+ * only the completed buffer is observable (Renderer.cpp:628-633), so the other tiles' calls become no-ops.  The library traces a
+ * wave of up to maxLookahead passes sample, sample+sampleStride, ... at once (<= 0: its own wave size) and adds only pass `sample`
+ * to the running sum; the following calls (sample+sampleStride, ...) add their pass from the resident wave, unless camera, options
+ * or scene arrays changed in between — then the wave is discarded and traced again.  Sum, seeds and frameNum schedule equal
+ * ptb_render_samples(sample, 1, 1).  sampleStride > 1: the other passes belong to other GPUs (ptb_mgpu_render_pass). */
+int  ptb_render_pass(PtbCtx* ctx, int32_t sample, int32_t sampleStride, int32_t maxLookahead);
 /* preview.glsl:41-71 + Renderer.cpp:555-565,798: quarter-resolution 1-spp depth-2 render, no accumulation.
  * out = (w*h*4) floats, w = windowW*0.25, h = windowH*0.25. */
 int  ptb_render_preview(PtbCtx* ctx, int32_t w, int32_t h, float* outRgba);
@@ -151,6 +159,23 @@ int  ptb_accum_device_ptr(PtbCtx* ctx, void** devPtr, uint64_t* nbytes);
 /* tonemap.glsl:97-133 with invSampleCounter (Renderer.cpp:806) + glGetTexImage(GL_RGBA, GL_UNSIGNED_BYTE)
  * (Renderer.cpp:619-634): tonemapped gamma-2.2 RGBA8, bottom row first, w*h*4 bytes. */
 int  ptb_read_output_rgba8(PtbCtx* ctx, float invSampleCounter, uint8_t* outRgba8);
+/* Same, tonemapping a caller-provided device buffer (float4[w*h], e.g. the NCCL-reduced sum of several contexts' running sums)
+ * instead of the context's own; devAccum = NULL is ptb_read_output_rgba8. */
+int  ptb_read_output_rgba8_from(PtbCtx* ctx, const void* devAccum, float invSampleCounter, uint8_t* outRgba8);
+/* The tonemap pass Render() runs after a tile (Renderer.cpp:584-588) into tileOutputTexture[currentBuffer], kept on the DEVICE:
+ * ptb_snapshot_output freezes the tonemapped image of the pass just completed (asynchronous, no host copy);
+ * ptb_read_snapshot_rgba8 is the glGetTexImage of GetOutputBuffer (Renderer.cpp:619-634) on that frozen image (zeros before
+ * the first snapshot). */
+int  ptb_snapshot_output(PtbCtx* ctx, float invSampleCounter);
+int  ptb_snapshot_output_from(PtbCtx* ctx, const void* devAccum, float invSampleCounter);   /* ... of a caller-provided device sum */
+int  ptb_read_snapshot_rgba8(PtbCtx* ctx, uint8_t* outRgba8);
+/* Denoiser hook support (Renderer.cpp:695-728 reads tileOutputTexture[1-currentBuffer] as GL_RGB / GL_FLOAT): when enabled, a
+ * snapshot also keeps the RGBA32F form of the tonemapped image; ptb_read_snapshot_rgb32f copies its rgb to the host (w*h*3 floats). */
+int  ptb_set_snapshot_float(PtbCtx* ctx, int32_t enable);
+int  ptb_read_snapshot_rgb32f(PtbCtx* ctx, float* outRgb);
+/* Page-locked host memory for readback targets (a pageable target costs ~3 % of the end-to-end rate at 1080p). */
+int  ptb_host_alloc(uint64_t nbytes, void** out);
+int  ptb_host_free(void* p);
 
 int  ptb_get_stats(PtbCtx* ctx, PtbStats* out);
 int  ptb_reset_stats(PtbCtx* ctx);
@@ -185,6 +210,35 @@ int  ptb_trace_closest_device(PtbCtx* ctx, const void* devRays, int64_t n, int32
 int  ptb_read_nodes(PtbCtx* ctx, float* outNodes, int32_t numNodes);
 /* Required traversal stack depth computed from the uploaded hierarchy (TLAS height + marker + max BLAS height). */
 int  ptb_stack_depth(PtbCtx* ctx, int32_t* out);
+
+/* ---- several GPUs of one box behind one handle -------------------------------------------------------
+ * For a host that is one process and one thread, as the reference's Renderer is (Renderer.h:169-179 knows no device): N contexts
+ * (one scene replica per GPU) + one NCCL communicator.  Sample passes are sharded round-robin (context r renders passes
+ * first+r, first+r+N, ... with the seeds a 1-GPU run would use); there is no data-path collective.  A readback combines the N
+ * running sums with ONE ncclReduce over NVLink into a scratch buffer on devices[0] — the per-GPU sums stay untouched, so
+ * progressive readbacks are correct — and tonemaps there.  NCCL is bound at run time (dlopen) and only when numDevices > 1.
+ * devices = NULL means ordinals 0..numDevices-1.  One process per GPU with torch.distributed (bench.py) is the other supported
+ * arrangement; it uses ptb_accum_device_ptr + ptb_read_output_rgba8_from. */
+typedef struct PtbMgpu PtbMgpu;
+int  ptb_mgpu_create(const PtbSceneDesc* scene, const PtbOptions* opts, const int32_t* devices, int32_t numDevices, PtbMgpu** out);
+int  ptb_mgpu_destroy(PtbMgpu* m);
+int  ptb_mgpu_num_devices(PtbMgpu* m);
+PtbCtx* ptb_mgpu_context(PtbMgpu* m, int32_t i);                                    /* the i-th per-GPU context (stats, parity entry points) */
+int  ptb_mgpu_set_options(PtbMgpu* m, const PtbOptions* opts);                      /* ptb_set_options on every context */
+int  ptb_mgpu_set_camera(PtbMgpu* m, const PtbCamera* cam);
+int  ptb_mgpu_set_cull(PtbMgpu* m, int32_t enable);
+int  ptb_mgpu_update_instances(PtbMgpu* m, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
+                               const float* tlasNodes, int32_t numTlasNodes);
+int  ptb_mgpu_update_envmap(PtbMgpu* m, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum);
+int  ptb_mgpu_reset_accum(PtbMgpu* m);
+int  ptb_mgpu_render_samples(PtbMgpu* m, int32_t firstSample, int32_t nSamples);    /* passes [first, first+n) over all GPUs, asynchronous */
+int  ptb_mgpu_render_pass(PtbMgpu* m, int32_t sample, int32_t maxLookahead);         /* ptb_render_pass on GPU (sample-1) mod N, stride N */
+int  ptb_mgpu_read_output_rgba8(PtbMgpu* m, float invSampleCounter, uint8_t* outRgba8);   /* reduce -> tonemap -> host (GetOutputBuffer) */
+int  ptb_mgpu_snapshot_output(PtbMgpu* m, float invSampleCounter);                  /* reduce -> tonemap, kept on devices[0] (asynchronous) */
+int  ptb_mgpu_read_snapshot_rgba8(PtbMgpu* m, uint8_t* outRgba8);
+int  ptb_mgpu_read_accum_f32(PtbMgpu* m, float* outRgba);                           /* reduced linear sum (parity) */
+int  ptb_mgpu_get_stats(PtbMgpu* m, PtbStats* out);                                 /* counters summed, lastRenderMs = max over GPUs */
+int  ptb_mgpu_synchronize(PtbMgpu* m);
 
 #ifdef __cplusplus
 }

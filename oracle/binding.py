@@ -76,6 +76,7 @@ def lib():
         L.orc_get_stats.argtypes = [C.c_void_p, C.POINTER(OrcStats)]
         L.orc_reset_stats.argtypes = [C.c_void_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]; L.orc_set_num_threads.restype = None
     return _LIB
 
 

@@ -1436,6 +1436,14 @@ OrcCtx* orc_create(const OrcSceneDesc* d, const OrcOptions* opts)
 }
 void orc_destroy(OrcCtx* h) { delete h; }
 void orc_set_options(OrcCtx* h, const OrcOptions* opts) { h->o = *opts; }
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);      // overrides OMP_NUM_THREADS (torchrun exports 1) for every OpenMP region of this process
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

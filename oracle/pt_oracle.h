@@ -121,6 +121,7 @@ void orc_tonemap(const float* accum, int32_t w, int32_t h, float invSampleCounte
 void orc_get_stats(OrcCtx*, OrcStats* out);
 void orc_reset_stats(OrcCtx*);
 int  orc_num_threads(void);
+void orc_set_num_threads(int n);   /* OpenMP threads of the CPU arms (process-wide) */
 
 #ifdef __cplusplus
 }

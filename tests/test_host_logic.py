@@ -19,7 +19,7 @@ class FakeCtx:
     def __getattr__(self, name):
         def rec(*a, **k):
             self.calls.append((name, a))
-            if name == "read_output":
+            if name in ("read_output", "read_snapshot"):
                 return np.zeros((self.opts.renderH, self.opts.renderW, 4), np.uint8)
             if name == "render_preview":
                 return np.zeros((a[1], a[0], 4), np.float32)
@@ -48,7 +48,7 @@ def test_tile_schedule_and_frame_numbers(fake):
     """First Update is the dirty one (preview); afterwards tiles run x-fastest from the TOP row and frameNum increments per tile:
     frameNum = 2 + (s-1)*T + j  (SURVEY §8(b) state machine)."""
     sc = scene_at("cornell_box_orig", 100, 72, 48, 32)          # 3 x 3 tiles
-    r = R.Renderer(sc, "")
+    r = R.Renderer(sc, "", coalesce=False)                      # one wavefront per Render() tile, as the reference draws
     seen = []
     for _ in range(1 + 2 * 9 + 1):
         r.Update(0.0)
@@ -61,15 +61,36 @@ def test_tile_schedule_and_frame_numbers(fake):
         s, j = k // 9 + 1, k % 9
         assert (tx, ty) == (j % 3, 2 - j // 3) and frame == 2 + (s - 1) * 9 + j
     assert r.GetSampleCount() == 3                             # two passes complete, third in progress
-    outs = [c for c in r.ctx.calls if c[0] == "read_output"]
+    outs = [c for c in r.ctx.calls if c[0] == "snapshot_output"]
     assert [round(1 / o[1][0]) for o in outs] == [1, 2]        # tonemap uniform invSampleCounter = 1/sampleCounter of the finished pass
+    assert not [c for c in r.ctx.calls if c[0] in ("read_output", "read_snapshot")]     # no host copy until GetOutputBuffer
+    r.GetOutputBuffer()
+    assert r.ctx.calls[-1][0] == "read_snapshot"
+
+
+def test_coalesced_passes_keep_the_tile_walk_and_render_once_per_pass(fake):
+    """Default mode: the whole pass is rendered at its first tile (render_pass(sample, remaining passes)); the other tiles' Render() calls
+    draw nothing, counters / tile walk / tonemap uniforms are those of the reference's loop; a dirty scene restarts at pass 1."""
+    sc = scene_at("cornell_box_orig", 100, 72, 48, 32)          # 3 x 3 tiles
+    sc.renderOptions.maxSpp = 5
+    r = R.Renderer(sc, "")
+    walk = []
+    for _ in range(1 + 2 * 9 + 4):
+        r.Update(0.0); walk.append((tuple(r.tile), r.frameCounter)); r.Render()
+    assert [c[0] for c in r.ctx.calls if c[0] in ("render_tile", "render_pass", "render_preview")] == ["render_preview", "render_pass", "render_pass", "render_pass"]
+    assert [c[1] for c in r.ctx.calls if c[0] == "render_pass"] == [(1, 4), (2, 3), (3, 2)]      # (sample, passes left before maxSpp stops the loop)
+    assert walk[1] == ((0, 2), 2) and walk[9] == ((2, 0), 10) and walk[10] == ((0, 2), 11)
+    assert [round(1 / c[1][0]) for c in r.ctx.calls if c[0] == "snapshot_output"] == [1, 2]
+    sc.dirty = True
+    r.Update(0.0); r.Render(); r.Update(0.0); r.Render()
+    assert [c[1] for c in r.ctx.calls if c[0] == "render_pass"][-1] == (1, 4) and r.sampleCounter == 1
 
 
 def test_maxspp_renders_maxspp_minus_one_passes(fake):
     """Render/Update return early once sampleCounter >= maxSpp."""
     sc = scene_at("cornell_box_orig", 96, 64, 48, 32)
     sc.renderOptions.maxSpp = 4
-    r = R.Renderer(sc, "")
+    r = R.Renderer(sc, "", coalesce=False)
     for _ in range(200):
         r.Update(0.0); r.Render()
     assert r.GetSampleCount() == 4 and r.GetProgress() == 100.0

@@ -1,6 +1,7 @@
 """N>1 host path on CPU: two processes over gloo shard the sample passes (multigpu.shard_passes), each renders its share with
-the oracle standing in for the GPU context (same render_samples(first, n, stride) contract), and ONE reduce(SUM) of the
-per-rank running sums reproduces the single-process image.  The GPU version of the same test is tests/test_gpu_render.py::
+the oracle standing in for the GPU context (same render_samples(first, n, stride) contract), and a reduce(SUM) of the
+per-rank running sums into a scratch buffer reproduces the single-process image — also on a SECOND readback after more passes
+(the running sums are not modified by a readback).  The GPU version of the same test is tests/test_gpu_render.py::
 test_sample_stride_sharding_sums_to_single; the NCCL reduce itself is exercised by `bench.py --gpus N`."""
 import os, subprocess, sys, textwrap
 import numpy as np
@@ -26,13 +27,20 @@ WORKER = textwrap.dedent("""
     sc = scene_at('cornell_box_orig', 48, 32, 24, 16, 3)
     ctx = OracleCtx(sc)
     drv = multigpu.ShardedRenderer(ctx, rank, 2)
-    drv.render(5); drv.render(4)          # two batches: 9 passes in total, odd split
     t = torch.from_numpy(ctx.acc)
-    multigpu.reduce_accum(t, dst=0)
+    drv.render(5)
+    first = drv.reduced(t).numpy().copy()     # progressive readback after the first batch ...
+    drv.render(4)                             # ... rendering goes on: 9 passes in total, odd split
+    second = drv.reduced(t).numpy().copy()    # ... and a second readback: must not count the first batch twice
     if rank == 0:
-        ref = ob.Oracle(sc).render(1, 9)
+        o = ob.Oracle(sc)
+        ref5 = o.render(1, 5).copy(); ref9 = o.render(6, 4, accum=ref5.copy())
         assert drv.samples_total() == 9
-        np.testing.assert_allclose(ctx.acc, ref, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(first, ref5, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(second, ref9, rtol=1e-5, atol=1e-5)
+        own = ob.Oracle(sc); mine = np.zeros_like(ref9)
+        for p in multigpu.passes_of(1, 5, 0, 2) + multigpu.passes_of(6, 4, 0, 2): own.render(p, 1, accum=mine)
+        np.testing.assert_array_equal(ctx.acc, mine)      # rank 0's running sum still holds only its own passes
         print('GLOO_OK')
     dist.barrier(); dist.destroy_process_group()
 """)
