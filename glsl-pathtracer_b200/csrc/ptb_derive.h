@@ -1,0 +1,23 @@
+// ptb_derive.h — host-side derivation of the traversal layout from the canonical arrays (no CUDA calls): what ptb_create /
+// ptb_update_instances compute before they upload.  Kept apart from ptb_api.cpp so that the derivation and the device headers can
+// also be compiled for the host by the test harness (tests/host_harness), which checks them against the oracle without a GPU.
+#pragma once
+#include "ptb_internal.h"
+#include <string>
+#include <vector>
+
+struct PtbDerivedHierarchy
+{
+    std::vector<float4> inner;        // rows for canonical nodes [begin, end): 4 float4 each
+    std::vector<float4> instTrav;     // 4 float4 / instance
+    std::vector<float4> instShade;    // 8 float4 / instance
+    uint32_t rootMeta = PTB_META_NONE;
+    int stackDepth = 4;
+};
+struct PtbDerivedLights { std::vector<float4> lightsPre, lightGroups; int numGroups = 0; };
+
+// status codes: 0 ok, 1 invalid argument, 4 unsupported (same values as PtbStatus)
+int ptbd_derive_hierarchy(const float* nodes, int numNodes, int topLevelIndex, int numIndices, int numMaterials, const float* transforms, int numInstances,
+                          int begin, int end, PtbDerivedHierarchy& out, std::string& err);
+int ptbd_build_tris(const int32_t* vertIndices, int numIndices, const float* verticesUVX, int numVertices, std::vector<float4>& tris, std::string& err);
+void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);

@@ -43,66 +43,6 @@ __device__ __forceinline__ bool slotToPixel(const WaveParams& W, uint32_t slot, 
     return px < W.rw && py < W.rh;
 }
 
-// tile.glsl:41-68 / preview.glsl:41-67.  (x,y) absolute pixel; returns the ray and leaves rng advanced by 4 draws.
-__device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass, Rng& rng, float3& ro, float3& rd)
-{
-    float cx, cy;
-    if (W.previewMode)
-    {
-        cx = __fdiv_rn((float)x + 0.5f, (float)W.rw); cy = __fdiv_rn((float)y + 0.5f, (float)W.rh);     // TexCoords over the whole low-res target
-        rng.init((uint32_t)x, (uint32_t)y, 1u);                                         // preview.glsl:43
-    }
-    else
-    {
-        int tx = x / F.tileW, ty = y / F.tileH, lx = x - tx * F.tileW, ly = y - ty * F.tileH;
-        float tcx = __fdiv_rn((float)lx + 0.5f, (float)F.tileW), tcy = __fdiv_rn((float)ly + 0.5f, (float)F.tileH);
-        float offx = (float)tx * F.invNumTilesX, offy = (float)ty * F.invNumTilesY;        // Renderer.cpp:780
-        // mix(tileOffset, tileOffset + invNumTiles, TexCoords)  (tile.glsl:43)
-        cx = __fadd_rn(__fmul_rn(offx, __fsub_rn(1.0f, tcx)), __fmul_rn(__fadd_rn(offx, F.invNumTilesX), tcx));
-        cy = __fadd_rn(__fmul_rn(offy, __fsub_rn(1.0f, tcy)), __fmul_rn(__fadd_rn(offy, F.invNumTilesY), tcy));
-        int frame;
-        if (W.fixedFrame >= 0) frame = W.fixedFrame;
-        else
-        {   // frameNum of pass s, tile j: first Update is the dirty one, tiles run x-fastest from the top row (Renderer.cpp:745-762)
-            int T = F.numTilesX * F.numTilesY;
-            int j = (F.numTilesY - 1 - ty) * F.numTilesX + tx;
-            frame = 2 + (samplePass - 1) * T + j;
-        }
-        rng.init((uint32_t)lx, (uint32_t)ly, (uint32_t)frame);                            // gl_FragCoord is tile-local (tile.glsl:45)
-    }
-    float r1 = __fmul_rn(2.0f, rng.rand());
-    float r2 = __fmul_rn(2.0f, rng.rand());
-    float jx = r1 < 1.0f ? __fsub_rn(__fsqrt_rn(r1), 1.0f) : __fsub_rn(1.0f, __fsqrt_rn(__fsub_rn(2.0f, r1)));
-    float jy = r2 < 1.0f ? __fsub_rn(__fsqrt_rn(r2), 1.0f) : __fsub_rn(1.0f, __fsqrt_rn(__fsub_rn(2.0f, r2)));
-    jx = __fdiv_rn(jx, __fmul_rn((float)F.renderW, 0.5f));
-    jy = __fdiv_rn(jy, __fmul_rn((float)F.renderH, 0.5f));
-    float dx = __fadd_rn(__fsub_rn(__fmul_rn(cx, 2.0f), 1.0f), jx);
-    float dy = __fadd_rn(__fsub_rn(__fmul_rn(cy, 2.0f), 1.0f), jy);
-    float scale = F.camScale;
-    dy = __fmul_rn(dy, __fmul_rn(F.aspect, scale));     // aspect = float(renderH) / float(renderW), one IEEE division on the host
-    dx = __fmul_rn(dx, scale);
-    float3 right = f3(F.camRight[0], F.camRight[1], F.camRight[2]), up = f3(F.camUp[0], F.camUp[1], F.camUp[2]),
-           fwd = f3(F.camFwd[0], F.camFwd[1], F.camFwd[2]), pos = f3(F.camPos[0], F.camPos[1], F.camPos[2]);
-    // exact-op evaluation keeps pinhole primary rays bit-identical to the oracle's (aperture 0 => no sin/cos influence)
-    float3 v = f3(xa(xa(xm(dx, right.x), xm(dy, up.x)), fwd.x), xa(xa(xm(dx, right.y), xm(dy, up.y)), fwd.y), xa(xa(xm(dx, right.z), xm(dy, up.z)), fwd.z));
-    float vl = __fsqrt_rn(xdot(v, v));
-    float3 rayDir = f3(xd(v.x, vl), xd(v.y, vl), xd(v.z, vl));
-    float3 focalPoint = f3(xm(F.camFocalDist, rayDir.x), xm(F.camFocalDist, rayDir.y), xm(F.camFocalDist, rayDir.z));
-    float cam_r1 = __fmul_rn(rng.rand(), PTB_TWO_PI);
-    float cam_r2 = __fmul_rn(rng.rand(), F.camAperture);
-    float sr = __fsqrt_rn(cam_r2);
-    float3 ap = f3(0.f);
-    if (F.camAperture != 0.0f)       // pinhole: the lens offset is (cos,sin)*sqrt(0) = 0, skip the sincos (the two draws above are still consumed)
-    {
-        float s1, c1; sincosf(cam_r1, &s1, &c1);
-        ap = f3(xm(xa(xm(c1, right.x), xm(s1, up.x)), sr), xm(xa(xm(c1, right.y), xm(s1, up.y)), sr), xm(xa(xm(c1, right.z), xm(s1, up.z)), sr));
-    }
-    float3 fd = xsub(focalPoint, ap);
-    float fl = __fsqrt_rn(xdot(fd, fd));
-    rd = f3(xd(fd.x, fl), xd(fd.y, fl), xd(fd.z, fl));
-    ro = f3(xa(pos.x, ap.x), xa(pos.y, ap.y), xa(pos.z, ap.z));
-}
-
 __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0)
 {
     const uint32_t lane = threadIdx.x & 31u;

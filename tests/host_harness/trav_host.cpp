@@ -1,0 +1,112 @@
+// trav_host.cpp — TEST INFRASTRUCTURE (see ptb_host_shim.h): the product's traversal / light-test / camera-ray source
+// (csrc/ptb_device.cuh) and its host-side layout derivation (csrc/ptb_derive.cpp), compiled for the host and exposed through a small
+// C interface with the same record layouts as the C ABI's parity entry points (PtbHit).  Used only by tests/test_host_traversal.py.
+#define PTB_HOST_HARNESS 1
+#include "ptb_device.cuh"
+#include "ptb_derive.h"
+#include <string>
+#include <vector>
+
+using namespace ptb;
+
+struct HHScene
+{
+    DevScene S{};
+    PtbDerivedHierarchy dh; PtbDerivedLights dl; std::vector<float4> tris;
+    std::vector<float> nodes, transforms; std::vector<int> vertIndices; std::vector<float4> verticesUVX;
+};
+struct HHHit { float t; int kind, instance, matID, primSlot, triIDx; float bary[3]; int lightIdx; };
+
+extern "C" {
+
+HHScene* hh_create(const float* nodes, int numNodes, int topLevelIndex, const int32_t* vertIndices, int numIndices, const float* verticesUVX, int numVertices,
+                   const float* transforms, int numInstances, int numMaterials, const float* lights, int numLights, char* errOut, int errCap)
+{
+    HHScene* h = new HHScene();
+    std::string err;
+    h->nodes.assign(nodes, nodes + (size_t)numNodes * 9); h->transforms.assign(transforms, transforms + (size_t)numInstances * 16);
+    h->vertIndices.assign(vertIndices, vertIndices + (size_t)numIndices * 3);
+    int rc = ptbd_build_tris(vertIndices, numIndices, verticesUVX, numVertices, h->tris, err);
+    if (!rc) rc = ptbd_derive_hierarchy(nodes, numNodes, topLevelIndex, numIndices, numMaterials, transforms, numInstances, 0, numNodes, h->dh, err);
+    if (rc) { if (errOut) { strncpy(errOut, err.c_str(), errCap - 1); errOut[errCap - 1] = 0; } delete h; return nullptr; }
+    ptbd_build_lights(lights, numLights, h->dl);
+    DevScene& S = h->S;
+    S.nodes = h->nodes.data(); S.vertIndices = h->vertIndices.data();
+    S.inner = h->dh.inner.data(); S.tris = h->tris.data(); S.instTrav = h->dh.instTrav.data(); S.instShade = h->dh.instShade.data();
+    S.lightsPre = h->dl.lightsPre.data(); S.lightGroups = h->dl.lightGroups.data(); S.numLightGroups = h->dl.numGroups;
+    S.rootMeta = h->dh.rootMeta; S.stackDepth = h->dh.stackDepth;
+    S.numNodes = numNodes; S.topLevelIndex = topLevelIndex; S.numIndices = numIndices; S.numVertices = numVertices; S.numMaterials = numMaterials;
+    S.numInstances = numInstances; S.numLights = numLights;
+    return h;
+}
+void hh_destroy(HHScene* h) { delete h; }
+int hh_stack_depth(HHScene* h) { return h->S.stackDepth; }
+
+// k_trace_batch of ptb_kernels.cu, one ray after the other
+void hh_trace_closest(HHScene* h, const float* rays, long long n, int lights, int cull, HHHit* out)
+{
+    const DevScene& S = h->S;
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (long long i = 0; i < n; i++)
+    {
+        LocalStack stk;
+        const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+        HitRec hr; hr.t = PTB_INF; hr.prim = -1; hr.inst = -1; hr.light = -1; hr.bu = hr.bv = 0.f;
+        float t = PTB_INF;
+        if (lights) closestLights(S, o, d, t, hr.light);
+        if (cull) traverse<false, false, true>(S, o, d, t, stk, hr, NoAlpha());
+        else traverse<false, false, false>(S, o, d, t, stk, hr, NoAlpha());
+        HHHit r;
+        r.t = hr.t;
+        if (hr.t == PTB_INF) { r.kind = 0; r.instance = r.matID = r.primSlot = r.triIDx = r.lightIdx = -1; r.bary[0] = r.bary[1] = r.bary[2] = 0.f; }
+        else if (hr.inst >= 0)
+        {
+            r.kind = 1; r.instance = hr.inst; r.matID = __float_as_int(S.instTrav[(size_t)hr.inst * 4 + 1].w); r.primSlot = hr.prim;
+            r.triIDx = S.vertIndices[(size_t)hr.prim * 3];
+            r.bary[0] = xs(xs(1.0f, hr.bu), hr.bv); r.bary[1] = hr.bu; r.bary[2] = hr.bv; r.lightIdx = -1;
+        }
+        else { r.kind = 2; r.instance = r.matID = r.primSlot = r.triIDx = -1; r.bary[0] = r.bary[1] = r.bary[2] = 0.f; r.lightIdx = hr.light; }
+        out[i] = r;
+    }
+}
+
+void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long n, int lights, int cull, int* out)
+{
+    const DevScene& S = h->S;
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (long long i = 0; i < n; i++)
+    {
+        LocalStack stk;
+        const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+        bool occ = lights && anyLights(S, o, d, maxDist[i]);
+        if (!occ)
+        {
+            HitRec hr;
+            occ = cull ? traverse<true, false, true>(S, o, d, maxDist[i], stk, hr, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, hr, NoAlpha());
+        }
+        out[i] = occ ? 1 : 0;
+    }
+}
+
+// uniforms as refreshFrameParams (ptb_api.cpp) derives them from PtbOptions / PtbCamera
+void hh_camera_rays(int renderW, int renderH, int tileW, int tileH, const float* pos, const float* right, const float* up, const float* fwd, float fov, float focalDist,
+                    float aperture, int sample, float* out)
+{
+    FrameParams F{};
+    F.renderW = renderW; F.renderH = renderH; F.tileW = tileW; F.tileH = tileH;
+    F.invNumTilesX = (float)tileW / renderW; F.invNumTilesY = (float)tileH / renderH;
+    F.numTilesX = (int)ceilf((float)renderW / tileW); F.numTilesY = (int)ceilf((float)renderH / tileH);
+    memcpy(F.camPos, pos, 12); memcpy(F.camRight, right, 12); memcpy(F.camUp, up, 12); memcpy(F.camFwd, fwd, 12);
+    F.aspect = (float)renderH / (float)renderW;
+    F.camScale = tanf(fov * 0.5f); F.camFocalDist = focalDist; F.camAperture = aperture;
+    WaveParams W{}; W.rw = renderW; W.rh = renderH; W.firstSample = sample; W.sampleStride = 1; W.fixedFrame = -1; W.nSamples = 1;
+    for (int i = 0; i < renderW * renderH; i++)
+    {
+        int x = i % renderW, y = i / renderW;
+        Rng rng; float3 ro, rd;
+        cameraRay(F, W, x, y, sample, rng, ro, rd);
+        out[i * 6 + 0] = ro.x; out[i * 6 + 1] = ro.y; out[i * 6 + 2] = ro.z; out[i * 6 + 3] = rd.x; out[i * 6 + 4] = rd.y; out[i * 6 + 5] = rd.z;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,53 @@
+"""Ray sets and hit-record comparisons shared by the G1 tests on the GPU (test_gpu_trace.py) and the host-compiled traversal check
+(test_host_traversal.py)."""
+import numpy as np
+
+
+def random_rays(sc, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array(sc.sceneBounds[0], np.float32), np.array(sc.sceneBounds[1], np.float32)
+    ext = hi - lo
+    o = (lo - 0.25 * ext + rng.random((n, 3), dtype=np.float32) * 1.5 * ext).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # a share of exactly axis-parallel rays: 0*inf NaNs in the slab test
+    k = n // 16
+    d[:k] = 0; d[np.arange(k), rng.integers(0, 3, k)] = rng.choice([-1.0, 1.0], k)
+    return np.concatenate([o, d.astype(np.float32)], axis=1)
+
+
+def bounce_rays(rays, hits, seed=11):
+    """bounce-like rays: start on the surfaces found by `hits`, random directions, offset by EPS along the direction"""
+    hit = hits["kind"] == 1
+    p = rays[hit, :3] + rays[hit, 3:] * hits["t"][hit, None]
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=p.shape).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([(p + d * np.float32(0.0003)).astype(np.float32), d], axis=1)
+
+
+def any_hit_distances(sc, n, seed=9):
+    rng = np.random.default_rng(seed)
+    ext = float(np.linalg.norm(np.array(sc.sceneBounds[1]) - np.array(sc.sceneBounds[0])))
+    md = (rng.random(n, dtype=np.float32) * ext).astype(np.float32)
+    md[::3] = np.float32(1e6 - 0.0003)
+    return md
+
+
+def assert_hits_nearly_equal(a, b, max_frac=2e-5):
+    """Culled traversal: identical except for exact-tie edge cases (two triangles sharing an edge, t equal to a few ulp)."""
+    bad = np.nonzero((a["primSlot"] != b["primSlot"]) | (a["kind"] != b["kind"]) | (a["lightIdx"] != b["lightIdx"]))[0]
+    assert bad.size <= max(1, int(max_frac * len(a))), f"{bad.size} mismatches"
+    assert np.all(np.abs(a["t"] - b["t"]) <= 1e-5 * np.abs(b["t"]))
+    good = np.ones(len(a), bool); good[bad] = False
+    assert np.array_equal(a["t"][good].view(np.uint32), b["t"][good].view(np.uint32))
+
+
+def assert_hits_equal(a, b):
+    for f in ("kind", "instance", "matID", "primSlot", "triIDx", "lightIdx"):
+        bad = np.nonzero(a[f] != b[f])[0]
+        assert bad.size == 0, f"{f}: {bad.size} mismatches, first ray {bad[:5]}: {a[f][bad[:5]]} vs {b[f][bad[:5]]}"
+    ta, tb = a["t"], b["t"]
+    assert np.all(np.abs(ta - tb) <= 1e-5 * np.abs(tb)), "t beyond 1e-5 relative"
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32)), "t not bit-identical"
+    hit = a["kind"] == 1
+    assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32)), "barycentrics not bit-identical"

@@ -351,3 +351,73 @@ def test_full_size_hyperion_1080p(oracle_mod):
     assert ta[1008:, 1792:].tobytes() == s1.read_accum()[1008:, 1792:].tobytes() and not ta[:1008].any()
     for c in (ctx, s1, s2, t): c.close()
     orc.close(); orc_c.close()
+
+
+# ---------------------------------------------------------------- converged gates (G3 as the survey words it) ---------------------
+def _signed_bias(g, o):
+    """mean signed per-pixel difference of the rgb means, and the mean radiance"""
+    d = (g[..., :3].astype(np.float64) - o[..., :3].astype(np.float64)).mean(axis=-1).ravel()
+    return float(d.mean()), float(o[..., :3].mean())
+
+
+@pytest.mark.parametrize("name,spp", [("hyperion_sphere_light", 256), ("hyperion_rect_lights", 128)])
+def test_converged_image_is_unbiased_against_the_oracle(name, spp, oracle_mod):
+    """480x270 at 256 / 128 spp.  hyperion_sphere_light is the scene where only a minority of the pixels stays RNG-matched
+    (the reference's sphere light shadows its own grazing NEE rays within rounding of EPS, anyhit.glsl:56-61): "equal in expectation" is
+    tested here — relMSE <= 1e-3 at equal spp AND the mean signed difference (a) within 3 sigma of the Monte-Carlo noise of the converged
+    mean itself (sigma from two independent halves of the oracle's own passes) and (b) below 1e-4 of the mean radiance.
+    hyperion_rect_lights (glass, clearcoat, near-mirror metal) bounds the bias of the 2-ulp shading arithmetic the same way.
+    (With div.approx / rsqrt in the sphere-light sample geometry this test measured -0.5 % on hyperion_sphere_light; see SampleOneLight.)"""
+    sc = scene_at(name, 480, 270, 256, 144)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc)
+    ctx.render_samples(1, spp)
+    g = np.nan_to_num(ctx.read_accum() / spp)
+    h = spp // 2
+    o1 = np.nan_to_num(orc.render(1, h) / h); o2 = np.nan_to_num(orc.render(1 + h, h) / h)
+    o = (o1 + o2) / 2
+    r = rel_mse(o, g)
+    mean, level = _signed_bias(g, o)
+    half = (o1[..., :3].astype(np.float64) - o2[..., :3].astype(np.float64)).mean(axis=-1).ravel()
+    sigma = float(half.std(ddof=1) / 2 / np.sqrt(half.size))          # standard error of the converged image's mean radiance
+    print(f"{name}: relMSE {r:.3e}, signed bias {mean:+.3e} = {mean / level:+.2e} of the mean radiance {level:.4f}; MC sigma of that mean {sigma:.3e}; matched pixels "
+          f"{np.isclose(g[..., :3], o[..., :3], rtol=1e-3, atol=1e-4).all(axis=-1).mean():.3f}")
+    assert r <= 1e-3, f"relMSE {r}"
+    assert abs(mean) <= 3.0 * sigma, f"signed bias {mean} exceeds 3 sigma ({sigma})"
+    assert abs(mean) <= 1e-4 * level
+    ctx.close(); orc.close()
+
+
+# ---------------------------------------------------------------- the other BASELINE configs at their full sizes -------------------
+@pytest.mark.parametrize("name,w,h,minfrac", [("volume_cube", 1920, 1080, 0.97), ("ibl_spheres", 1920, 1080, 0.95), ("hyperion_sphere_light", 1920, 1080, 0.85),
+                                             ("instancing", 3840, 2160, 0.93)])
+def test_full_size_other_baseline_configs(name, w, h, minfrac, oracle_mod):
+    """BASELINE configs[1], [3], [4] (and the sphere-light variant of [2]) at the sizes they are quoted on: every primary ray bit-exact in
+    both traversal variants (tile.glsl:41-68 + closest_hit.glsl), and a 1-spp RNG-matched image of the whole frame against the oracle.
+    The 4K instancing frame is 8.3 M pixels x depth 8: 66 M path slots per default wave (auto wave split, uint32 slot indices)."""
+    sc = scene_at(name, w, h)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc); orc_c = oracle_mod.Oracle(sc, cull=True)
+    rays = orc.camera_rays(1)
+    assert np.array_equal(ctx.camera_rays(1).view(np.uint32), rays.view(np.uint32))
+    g, o = ctx.trace_closest(rays), orc_c.trace_closest(rays)
+    for f in ("kind", "instance", "matID", "primSlot", "triIDx", "lightIdx"):
+        assert np.array_equal(g[f], o[f]), f
+    assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+    ctx.set_cull(False)
+    assert ctx.trace_closest(rays).tobytes() == orc.trace_closest(rays).tobytes()
+    ctx.set_cull(True)
+    ctx.render_samples(1, 1)
+    a = np.nan_to_num(ctx.read_accum()); ref = np.nan_to_num(orc.render(1, 1))
+    close = np.isclose(a[..., :3], ref[..., :3], rtol=1e-3, atol=1e-4).all(axis=-1).mean()
+    r = rel_mse(ref, a)
+    print(f"{name} {w}x{h}: 1-spp relMSE {r:.3e}, RNG-matched pixels {close:.4f}")
+    assert close > minfrac, close
+    # ONE sample per pixel is not a converged image: a pixel whose path diverged differs by O(1), and the error of a k-spp mean of RNG-matched
+    # paths falls as 1/k.  The relMSE <= 1e-3 gate is held at 8 spp by test_image_matches_oracle_rng_matched and at 128/256 spp by the
+    # converged test above; here the same gate is scaled to one sample (8 x 1e-3).
+    assert r <= 8e-3, r
+    # size-independent property at the full size: two strided shards sum to a two-pass render
+    ctx.render_samples(2, 1)
+    s1 = _ctx(sc); s1.render_samples(1, 1, 2); s1.render_samples(2, 1, 2)
+    np.testing.assert_allclose(np.nan_to_num(s1.read_accum()), np.nan_to_num(ctx.read_accum()), rtol=1e-6, atol=1e-6)
+    for c in (ctx, s1): c.close()
+    orc.close(); orc_c.close()

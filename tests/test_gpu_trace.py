@@ -4,6 +4,7 @@ reference-faithful host traversal of the same flattened BVH, on primary, random 
 import numpy as np
 import pytest
 from conftest import scene_at
+from raysets import random_rays, assert_hits_equal, assert_hits_nearly_equal
 
 pytestmark = pytest.mark.gpu
 SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
@@ -12,39 +13,6 @@ SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyp
 def _ctx(sc):
     from glsl_pathtracer_b200 import capi
     return capi.Context(sc)
-
-
-def random_rays(sc, n, seed):
-    rng = np.random.default_rng(seed)
-    lo, hi = np.array(sc.sceneBounds[0], np.float32), np.array(sc.sceneBounds[1], np.float32)
-    ext = hi - lo
-    o = (lo - 0.25 * ext + rng.random((n, 3), dtype=np.float32) * 1.5 * ext).astype(np.float32)
-    d = rng.normal(size=(n, 3)).astype(np.float32)
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    # a share of exactly axis-parallel rays: 0*inf NaNs in the slab test
-    k = n // 16
-    d[:k] = 0; d[np.arange(k), rng.integers(0, 3, k)] = rng.choice([-1.0, 1.0], k)
-    return np.concatenate([o, d.astype(np.float32)], axis=1)
-
-
-def assert_hits_nearly_equal(a, b, max_frac=2e-5):
-    """Culled traversal: identical except for exact-tie edge cases (two triangles sharing an edge, t equal to a few ulp)."""
-    bad = np.nonzero((a["primSlot"] != b["primSlot"]) | (a["kind"] != b["kind"]) | (a["lightIdx"] != b["lightIdx"]))[0]
-    assert bad.size <= max(1, int(max_frac * len(a))), f"{bad.size} mismatches"
-    assert np.all(np.abs(a["t"] - b["t"]) <= 1e-5 * np.abs(b["t"]))
-    good = np.ones(len(a), bool); good[bad] = False
-    assert np.array_equal(a["t"][good].view(np.uint32), b["t"][good].view(np.uint32))
-
-
-def assert_hits_equal(a, b):
-    for f in ("kind", "instance", "matID", "primSlot", "triIDx", "lightIdx"):
-        bad = np.nonzero(a[f] != b[f])[0]
-        assert bad.size == 0, f"{f}: {bad.size} mismatches, first ray {bad[:5]}: {a[f][bad[:5]]} vs {b[f][bad[:5]]}"
-    ta, tb = a["t"], b["t"]
-    assert np.all(np.abs(ta - tb) <= 1e-5 * np.abs(tb)), "t beyond 1e-5 relative"
-    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32)), "t not bit-identical"
-    hit = a["kind"] == 1
-    assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32)), "barycentrics not bit-identical"
 
 
 @pytest.mark.parametrize("name", SCENES)

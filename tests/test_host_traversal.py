@@ -1,0 +1,42 @@
+"""The product's hit-deciding SOURCE — csrc/ptb_device.cuh (two-level traversal state machine, analytic-light tests, camera rays) and
+csrc/ptb_derive.cpp (derived 64-byte node / 48-byte triangle / instance / light-group layout) — compiled for the HOST
+(tests/host_harness) and compared with the oracle bit for bit.  Every operation in that code is an IEEE round-to-nearest intrinsic that
+ptxas cannot contract, so the host build executes the same arithmetic as the sm_100a build; this catches logic errors in traversal
+changes where no GPU exists.  The G1 gate proper (tests/test_gpu_trace.py) runs the CUDA build through the C ABI on the B200."""
+import numpy as np
+import pytest
+from conftest import scene_at
+from raysets import random_rays, bounce_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
+from host_harness.binding import HostTrav
+
+SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_host_compiled_traversal_equals_oracle(name, oracle_mod):
+    sc = scene_at(name, 160, 90, 80, 45)
+    ht = HostTrav(sc); orc = oracle_mod.Oracle(sc); orc_c = oracle_mod.Oracle(sc, cull=True)
+    prim = orc.camera_rays(1)
+    assert np.array_equal(ht.camera_rays(1).view(np.uint32), prim.view(np.uint32)), "camera rays"
+    rays = np.concatenate([prim, random_rays(sc, 30_000, 7)])
+    for depth in (0, 1):
+        ht.set_cull(False)
+        faithful = orc.trace_closest(rays, depth)
+        assert_hits_equal(ht.trace_closest(rays, depth), faithful)
+        ht.set_cull(True)
+        got = ht.trace_closest(rays, depth)
+        assert_hits_equal(got, orc_c.trace_closest(rays, depth))
+        assert_hits_nearly_equal(got, faithful, max_frac=1e-4)
+    b = bounce_rays(rays, faithful)
+    ht.set_cull(False); assert_hits_equal(ht.trace_closest(b, 1), orc.trace_closest(b, 1))
+    ht.set_cull(True); assert_hits_equal(ht.trace_closest(b, 1), orc_c.trace_closest(b, 1))
+    # any-hit: occlusion is the same boolean in both variants
+    ar = np.concatenate([random_rays(sc, 30_000, 5), b[:20_000]])
+    md = any_hit_distances(sc, len(ar))
+    want = orc.trace_any(ar, md)
+    for cull in (False, True):
+        ht.set_cull(cull)
+        got = ht.trace_any(ar, md)
+        assert np.array_equal(got, want), f"cull={cull}: {np.count_nonzero(got != want)} occlusion mismatches"
+    assert ht.stack_depth() <= 64
+    ht.close(); orc.close(); orc_c.close()
