@@ -139,21 +139,35 @@ int ptbd_derive_hierarchy(const float* N, int numNodes, int topLevelIndex, int n
     out.stackDepth = std::max(4, 1 + tlasDepth + 1 + maxBlas + 1);
     DREQ(out.stackDepth <= 64, 4, "BVH deeper than the 64-entry traversal stack of the reference shader");
 
+    std::vector<char> transOnly(ni, 0);
     for (int k = 0; k < ni; k++)
     {
         const float* D = transforms + (size_t)k * 16;
         float inv[16], inv3[9];
         inverse4(D, inv); inverse3(D, inv3);
         float4* it = &out.instTrav[(size_t)k * 4]; float4* is = &out.instShade[(size_t)k * 8];
-        it[0] = make_float4(inv[0], inv[1], inv[2], u2f(rootMeta[k]));
+        it[0] = make_float4(inv[0], inv[1], inv[2], 0.f);
         it[1] = make_float4(inv[4], inv[5], inv[6], u2f((uint32_t)matID[k]));
         it[2] = make_float4(inv[8], inv[9], inv[10], 0.f);
-        it[3] = make_float4(inv[12], inv[13], inv[14], 0.f);
+        it[3] = make_float4(inv[12], inv[13], inv[14], u2f(rootMeta[k]));
+        // translation-only: the linear part of the computed inverse is the identity bit for bit (off-diagonals +-0), so the traversal may
+        // take the short instance entry (Trav::round) — the flag travels in the TLAS-leaf metas patched below
+        transOnly[k] = inv[0] == 1.f && inv[5] == 1.f && inv[10] == 1.f && inv[1] == 0.f && inv[2] == 0.f && inv[4] == 0.f && inv[6] == 0.f &&
+                       inv[8] == 0.f && inv[9] == 0.f && std::isfinite(inv[12]) && std::isfinite(inv[13]) && std::isfinite(inv[14]);
         for (int r = 0; r < 4; r++) is[r] = make_float4(D[r * 4 + 0], D[r * 4 + 1], D[r * 4 + 2], D[r * 4 + 3]);
         for (int r = 0; r < 3; r++) is[4 + r] = make_float4(inv3[r * 3 + 0], inv3[r * 3 + 1], inv3[r * 3 + 2], 0.f);
     }
     out.rootMeta = metaOf(N, topLevelIndex, numIndices, merr);
     DREQ(merr.empty(), metaCode(), merr);
+    DREQ((uint32_t)ni <= PTB_INST_INDEX_MASK, 4, "too many instances for the meta encoding");
+    auto flagInst = [&](uint32_t m) { return ((m >> 30) == PTB_K_INST && (m & PTB_INST_INDEX_MASK) < (uint32_t)ni && transOnly[m & PTB_INST_INDEX_MASK]) ? (m | PTB_INST_TRANSLATION_ONLY) : m; };
+    out.rootMeta = flagInst(out.rootMeta);
+    for (int i = std::max(begin, topLevelIndex); i < end; i++)
+    {   // child metas of the TLAS nodes in the derived range
+        float4& q3 = out.inner[(size_t)(i - begin) * 4 + 3];
+        if ((int)N[(size_t)i * 9 + 8] != 0) continue;
+        q3.x = u2f(flagInst(f2u(q3.x))); q3.y = u2f(flagInst(f2u(q3.y)));
+    }
     return 0;
 }
 

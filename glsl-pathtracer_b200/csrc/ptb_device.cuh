@@ -285,7 +285,7 @@ struct NoAlpha { };
 //   inner[i]   = { lmin.xyz lmax.x | lmax.yz rmin.xy | rmin.z rmax.xyz | lmeta rmeta - - }   (one 64-byte fetch per step;
 //                the reference reads LRLeaf of the node and then both children's boxes from two other nodes)
 //   tris[slot] = { v0.xyz e0.x | e0.yz e1.xy | e1.z vertIndex.x - - }
-//   instTrav[k]= rows of inverse(transform) + {rootMeta, matID}
+//   instTrav[k]= rows of inverse(transform) (xyz) + .w = {-, matID, -, rootMeta}; translation-only instances are flagged in the TLAS-leaf meta
 // Visiting order, near/far rule (left first on ties), strict-< acceptance and the un-normalised transformed direction are the
 // reference's, so primitive/instance IDs and t are identical to a host traversal of the canonical array.
 // Control flow is "while-while": every lane keeps descending internal nodes until it holds a leaf / instance / sentinel, then
@@ -308,6 +308,7 @@ struct Trav
     uint32_t cur;
     int curInst;
     bool inBlas;
+    bool generic;       // no zero / non-finite component in origin or direction: translation-only instances may take the short entry
     bool occluded;      // ANY result
     HitRec h;           // closest result (t filled by finish())
 
@@ -323,8 +324,31 @@ struct Trav
         inv = f3(xd(1.0f, d_.x), xd(1.0f, d_.y), xd(1.0f, d_.z)); invW = inv;
 #endif
         t = tmax; cur = S.rootMeta; curInst = -1; inBlas = false; occluded = false;
+        // |x| in (0, inf) for all six components (false for NaN too)
+        generic = fabsf(o_.x) > 0.f && fabsf(o_.y) > 0.f && fabsf(o_.z) > 0.f && fabsf(d_.x) > 0.f && fabsf(d_.y) > 0.f && fabsf(d_.z) > 0.f &&
+                  fabsf(o_.x) < CUDART_INF_F && fabsf(o_.y) < CUDART_INF_F && fabsf(o_.z) < CUDART_INF_F &&
+                  fabsf(d_.x) < CUDART_INF_F && fabsf(d_.y) < CUDART_INF_F && fabsf(d_.z) < CUDART_INF_F;
         stk.reset();
         stk.push(PTB_META_NONE);
+    }
+
+    // back in the TLAS: the world-space ray again (closest_hit.glsl:206-216); 1/direction of the world ray was computed once in begin()
+    __device__ __forceinline__ void leaveBlas()
+    {
+        inBlas = false;
+#if PTB_PACKED_SLAB
+        rd = d; rp = packRay(o, invW);
+#else
+        ro = o; rd = d; inv = invW;
+#endif
+    }
+    // Pop the next item; a BLAS marker is consumed on the spot (restore the world ray, pop again) instead of costing the warp another round.
+    template <class Stack>
+    __device__ __forceinline__ uint32_t popNext(Stack& stk)
+    {
+        uint32_t v = stk.pop();
+        if (v == PTB_META_NONE && inBlas) { leaveBlas(); v = stk.pop(); }
+        return v;
     }
 
     // One round: descend to the next non-internal item and process it.  Returns true when the traversal is finished.
@@ -358,7 +382,7 @@ struct Trav
             }
             else if (hl) cur = lm;
             else if (hr) cur = rm;
-            else cur = stk.pop();
+            else cur = popNext(stk);
         }
         const uint32_t kind = cur >> 30;
         if (kind == PTB_K_LEAF)                               // closest_hit.glsl:118-153
@@ -369,15 +393,31 @@ struct Trav
                 const float4* tp = S.tris + (size_t)(first + i) * 3;
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 const float3 v0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x);
-                // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard)
-                float3 pv = xcross(rd, e1);
-                float det = xdot(e0, pv);
-                float3 tv = xsub(roNow(), v0);
-                float3 qv = xcross(tv, e0);
-                float ux = xd(xdot(tv, pv), det);
-                float uy = xd(xdot(rd, qv), det);
-                float uz = xd(xdot(e1, qv), det);
-                float uw = xs(xs(1.0f, ux), uy);
+                // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard).  The acceptance test is
+                //   ux >= 0 && uy >= 0 && uz >= 0 && uw >= 0 && uz < t   with   u* = numerator / det,  uw = (1 - ux) - uy.
+                // Most tests are misses, and most misses can be decided from the numerators without dividing, with the SAME outcome:
+                //  * numerator and det of strictly opposite sign, |numerator| >= 1e-18 and |det| <= 1e18: the IEEE quotient is a negative number
+                //    of magnitude >= 1e-36 (it cannot round to -0, which would pass `>= 0`), or -inf for det = +-0;
+                //  * both numerators share det's sign and |a| + |b| > 1.001 |det|: ux + uy > 1.0007, so (1 - ux) - uy is below -7e-4 whatever the
+                //    rounding (or -inf when a quotient overflows).
+                // NaNs and everything near a boundary take the full path below, which is the reference's arithmetic unchanged.
+                const float3 pv = xcross(rd, e1);
+                const float det = xdot(e0, pv);
+                const float3 tv = xsub(roNow(), v0);
+                const float na = xdot(tv, pv);
+                const int sd = __float_as_int(det);
+                const bool detSmall = fabsf(det) <= 1e18f;
+                if (((__float_as_int(na) ^ sd) < 0) && fabsf(na) >= 1e-18f && detSmall) continue;
+                const float3 qv = xcross(tv, e0);
+                const float nb = xdot(rd, qv);
+                if (((__float_as_int(nb) ^ sd) < 0) && fabsf(nb) >= 1e-18f && detSmall) continue;
+                if (((__float_as_int(na) ^ sd) >= 0) && ((__float_as_int(nb) ^ sd) >= 0) && xa(fabsf(na), fabsf(nb)) > xm(1.001f, fabsf(det))) continue;
+                const float nc = xdot(e1, qv);
+                if (((__float_as_int(nc) ^ sd) < 0) && fabsf(nc) >= 1e-18f && detSmall) continue;
+                const float ux = xd(na, det);
+                const float uy = xd(nb, det);
+                const float uz = xd(nc, det);
+                const float uw = xs(xs(1.0f, ux), uy);
                 if (ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < t)
                 {
                     if constexpr (ANY)
@@ -388,42 +428,48 @@ struct Trav
                     else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
                 }
             }
-            cur = stk.pop();
+            cur = popNext(stk);
         }
         else if (kind == PTB_K_INST)                          // closest_hit.glsl:154-172
         {
-            curInst = (int)(cur & 0x3FFFFFFFu);
+            curInst = (int)(cur & PTB_INST_INDEX_MASK);
             const float4* ip = S.instTrav + (size_t)curInst * 4;
-            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-            // rTrans = inverse(transform) * (origin,1) / (direction,0); the inverse is precomputed at upload
-            const float3 roI = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
-                    xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
-                    xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
-            rd = f3(xa(xa(xa(xm(d.x, r0.x), xm(d.y, r1.x)), xm(d.z, r2.x)), xm(0.0f, r3.x)),
-                    xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
-                    xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
+            const float4 r3 = __ldg(ip + 3);
+            if ((cur & PTB_INST_TRANSLATION_ONLY) && generic)
+            {   // inverse(transform) is [I | -translation] bit for bit (checked at upload): the general formula below then reduces, for a ray without
+                // zero components, to origin + r3 (x*1 = x, x + (+-0) = x for x != 0) and an unchanged direction, whose reciprocal is invW
 #if PTB_PACKED_SLAB
-            rp = packRay(roI, f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z)));
+                rp = packRay(f3(xa(o.x, r3.x), xa(o.y, r3.y), xa(o.z, r3.z)), invW);
 #else
-            ro = roI;
-            inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
+                ro = f3(xa(o.x, r3.x), xa(o.y, r3.y), xa(o.z, r3.z));
 #endif
+            }
+            else
+            {
+                const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+                // rTrans = inverse(transform) * (origin,1) / (direction,0); the inverse is precomputed at upload
+                const float3 roI = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
+                        xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
+                        xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
+                rd = f3(xa(xa(xa(xm(d.x, r0.x), xm(d.y, r1.x)), xm(d.z, r2.x)), xm(0.0f, r3.x)),
+                        xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
+                        xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
+#if PTB_PACKED_SLAB
+                rp = packRay(roI, f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z)));
+#else
+                ro = roI;
+                inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
+#endif
+            }
             stk.push(PTB_META_NONE);                          // marker: back to the TLAS when it is popped
-            cur = __float_as_uint(r0.w);                      // BLAS root meta
+            cur = __float_as_uint(r3.w);                      // BLAS root meta
             inBlas = true;
         }
         else                                                  // sentinel / marker (closest_hit.glsl:206-216)
         {
             if (!inBlas) { h.t = t; return true; }
-            inBlas = false;
+            leaveBlas();                                      // (markers are normally consumed by popNext; this handles a marker reached directly)
             cur = stk.pop();
-#if PTB_PACKED_SLAB
-            rd = d;
-            rp = packRay(o, invW);                           // 1/direction of the world-space ray, computed once in begin()
-#else
-            ro = o; rd = d;
-            inv = invW;                                      // 1/direction of the world-space ray, computed once in begin()
-#endif
         }
         return false;
     }

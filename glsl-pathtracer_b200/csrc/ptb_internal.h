@@ -17,9 +17,12 @@
 
 // ---- child / node "meta" word of the derived traversal layout -------------------------------------------------
 // bits 31..30 kind; INNER: canonical node index (30 bits); LEAF: count (4 bits, 29..26) | first leaf-ref slot (26 bits);
-// INST: instance index (30 bits); NONE: stack sentinel / BLAS marker (the reference's -1, closest_hit.glsl:91,166).
+// INST: bit 29 = translation-only transform, instance index (29 bits); NONE: stack sentinel / BLAS marker (the reference's -1,
+// closest_hit.glsl:91,166).
 enum : uint32_t { PTB_K_INNER = 0u, PTB_K_LEAF = 1u, PTB_K_INST = 2u, PTB_K_NONE = 3u };
 #define PTB_META_NONE 0xFFFFFFFFu
+#define PTB_INST_TRANSLATION_ONLY (1u << 29)
+#define PTB_INST_INDEX_MASK ((1u << 29) - 1)
 #define PTB_MAX_LEAF_TRIS 15
 #define PTB_MAX_LEAF_SLOT ((1u << 26) - 1)
 
@@ -41,7 +44,7 @@ struct DevScene
     // derived
     const float4* inner;        // 4 float4 / canonical node index: child boxes + child metas (valid for internal nodes)
     const float4* tris;         // 3 float4 / leaf-ref slot: v0, e0, e1, vertIndices.x
-    const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {rootMeta, matID, 0, 0} in .w
+    const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {0, matID, 0, rootMeta} in .w
     const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
     const float4* lightsPre;    // 8 float4 / light (see buildLightsPre in ptb_api.cpp)
     const float4* lightGroups;  // 3 float4 / group of consecutive lights (shared plane + padded bounds)
