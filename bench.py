@@ -408,6 +408,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     ctx.set_profiling(False)
     trace_ms_last = st["lastTraceMs"]                 # closest-hit launches of the LAST step (events recorded in-stream)
+    kernel_ms = {k[4:-2].lower(): st[k] for k in ("lastCameraMs", "lastTraceMs", "lastSortMs", "lastShadeMs", "lastShadowMs", "lastAccumMs")}
     e2e_steps = max(2, min(args.steps, 5))
     e2e_ms, e2e_segs, _, _ = rig.timed(e2e_steps, SPP_PER_STEP, True)
 
@@ -488,6 +489,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": C.sizeof(capi.PtbCamera) + C.sizeof(capi.PtbOptions), "d2h_bytes_per_step": W * H * 4,
                     "what": "Context.set_camera + set_options (host uniforms) + render_samples + (N>1: NCCL reduce) + tonemapped RGBA8 readback into page-locked host memory, per step"},
             "gpu_launches": int(launches),
+            "kernel_ms_per_step": kernel_ms,       # CUDA events between the launches of the last timed step, by kernel class
             "clocks": clk,
             "roofline": roof,
         }

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptb200.so")
+LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(_HERE, "libptb200.so")     # PTB200_LIB: an A/B build of the same library (scripts/ab_build.sh)
 
 PTB_OK, PTB_ERR_INVALID_ARGUMENT, PTB_ERR_NO_DEVICE, PTB_ERR_CUDA, PTB_ERR_UNSUPPORTED, PTB_ERR_OUT_OF_MEMORY = range(6)
 
@@ -46,7 +46,9 @@ class PtbCamera(C.Structure):
 
 class PtbStats(C.Structure):
     _fields_ = [("pathSegments", C.c_uint64), ("shadowRays", C.c_uint64), ("samplesRendered", C.c_uint64), ("kernelLaunches", C.c_uint64),
-                ("lastRenderMs", C.c_float), ("lastTraceMs", C.c_float), ("lastTraceRays", C.c_uint64)]
+                ("lastRenderMs", C.c_float), ("lastTraceMs", C.c_float), ("lastTraceRays", C.c_uint64),
+                ("lastCameraMs", C.c_float), ("lastSortMs", C.c_float), ("lastShadeMs", C.c_float), ("lastShadowMs", C.c_float), ("lastAccumMs", C.c_float),
+                ("reserved_", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("t", "<f4"), ("kind", "<i4"), ("instance", "<i4"), ("matID", "<i4"), ("primSlot", "<i4"),

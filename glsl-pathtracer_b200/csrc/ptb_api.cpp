@@ -68,7 +68,8 @@ struct PtbCtx
     int device = 0, numSMs = 148;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
-    std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool profiling = false;
+    // profiling: one event between consecutive launches of a render call, each interval attributed to the kernel class that runs in it
+    std::vector<cudaEvent_t> traceEvents; std::vector<int> eventKind; size_t traceEventsUsed = 0; bool profiling = false;
 
     // host copies needed for re-derivation
     std::vector<float> hNodes, hTransforms, hMaterials;
@@ -85,6 +86,7 @@ struct PtbCtx
     FrameParams F{};
 
     DevBuf<float4> accum, preview;
+    DevBuf<float2> pixTabX, pixTabY; int tabW = 0, tabH = 0, tabTW = 0, tabTH = 0;     // pixel tables of the current resolution / tile size
     DevBuf<uchar4> out8;
 
     // wave state
@@ -92,6 +94,7 @@ struct PtbCtx
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
+    int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
                                //    tiles of 2048 slots, instead of over the compacted arrival-order queue (PTB_SLOT_ORDER)
     int sortMode = 3;          // 0 off, 1 global sort of bounces >= 1, 2 global sort of every bounce, 3 tile-local sort of bounces >= 1 (default: +3 % over 1)
@@ -165,9 +168,29 @@ void refreshDerivedFlags(PtbCtx* c)
     F.inlineShadow = (((f & PTB_OPT_ALPHA_TEST) && !(f & PTB_OPT_MEDIUM) && anyBlend) || ((f & PTB_OPT_MEDIUM) && (f & PTB_OPT_VOL_MIS))) ? 1 : 0;
 }
 
+// (re)build the per-column / per-row pixel tables when the resolution or the tile size changed
+int refreshPixelTables(PtbCtx* c)
+{
+    const PtbOptions& o = c->opts;
+    if (c->pixTabX.p && c->tabW == o.renderW && c->tabH == o.renderH && c->tabTW == o.tileW && c->tabTH == o.tileH) return PTB_OK;
+    std::vector<float2> tx, ty; std::string err;
+    if (ptbd_build_pixel_tables(o.renderW, o.renderH, o.tileW, o.tileH, tx, ty, err) != 0)
+    {   // sizes beyond the table encoding: the kernels evaluate the mapping per pixel
+        c->pixTabX.release(); c->pixTabY.release(); c->tabW = 0;
+        return PTB_OK;
+    }
+    CK(cudaStreamSynchronize(c->stream));           // a wave in flight may still read the old tables
+    CK(c->pixTabX.upload(tx.data(), tx.size(), c->stream));
+    CK(c->pixTabY.upload(ty.data(), ty.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->tabW = o.renderW; c->tabH = o.renderH; c->tabTW = o.tileW; c->tabTH = o.tileH;
+    return PTB_OK;
+}
+
 void refreshFrameParams(PtbCtx* c)
 {
     FrameParams& F = c->F; const PtbOptions& o = c->opts; const PtbCamera& cam = c->cam;
+    F.pixTabX = c->pixTabX.p; F.pixTabY = c->pixTabY.p;
     F.features = o.features;
     if (!(c->S.envImg && c->S.envW > 0)) F.features &= ~(uint32_t)PTB_OPT_ENVMAP;       // Renderer.cpp:404 needs scene->envMap
     if (c->S.numLights == 0) F.features &= ~(uint32_t)PTB_OPT_LIGHTS;
@@ -246,13 +269,18 @@ PathState pathState(PtbCtx* c)
     return P;
 }
 
-cudaEvent_t nextTraceEvent(PtbCtx* c)
+enum { KIND_NONE = -1, KIND_CAMERA = 0, KIND_TRACE = 1, KIND_SORT = 2, KIND_SHADE = 3, KIND_SHADOW = 4, KIND_ACCUM = 5, KIND_COUNT = 6 };
+
+// profiling only: an event in front of the launch(es) of class `kind`; the time up to the next mark is attributed to that class
+void mark(PtbCtx* c, int kind)
 {
+    if (!c->profiling) return;
     if (c->traceEventsUsed == c->traceEvents.size())
     {
-        cudaEvent_t e; cudaEventCreate(&e); c->traceEvents.push_back(e);
+        cudaEvent_t e; cudaEventCreate(&e); c->traceEvents.push_back(e); c->eventKind.push_back(KIND_NONE);
     }
-    return c->traceEvents[c->traceEventsUsed++];
+    c->eventKind[c->traceEventsUsed] = kind;
+    cudaEventRecord(c->traceEvents[c->traceEventsUsed++], c->stream);
 }
 
 // One wavefront: camera -> (trace, shade, shadow)* -> accumulate.
@@ -270,7 +298,13 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     const int numKeys = c->S.numMaterials + 2;
     CK(c->sortHist.alloc((size_t)numKeys * 2));
     CK(cudaMemsetAsync(c->sortHist.p, 0, (size_t)numKeys * 2 * sizeof(uint32_t), c->stream));
-    ptbk_camera(L, c->S, F, W, P, ctr);
+    // the camera rays of a render wave are generated inside the first closest-hit launch (k_trace_primary); the preview target keeps k_camera
+    const bool fusedCamera = c->fuseCamera && !W.previewMode && (W.nSlots & 31u) == 0;
+    if (!fusedCamera)
+    {
+        mark(c, KIND_CAMERA);
+        ptbk_camera(L, c->S, F, W, P, ctr);
+    }
     const int lightsFromDepth = (F.features & PTB_OPT_HIDE_EMITTERS) ? 1 : 0;
     const bool alphaScene = (F.features & PTB_OPT_ALPHA_TEST) != 0u;
     const int nominal = F.maxDepth + 1;
@@ -282,31 +316,38 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     {
         uint32_t* ci = ctr + (size_t)it * PTB_CTR_STRIDE;
         uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
-        if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
         const bool sortThis = c->sortMode == 2 || ((c->sortMode == 1 || c->sortMode == 3) && it >= 1);
         // bounce 1 over the slots in screen order (95 % of them still alive there): see slotOrder
         const bool slotIter = useSlotOrder && it == 1;
-        const uint32_t nOv = slotIter ? W.nSlots : 0u;
+        const uint32_t nOv = (slotIter || (it == 0 && fusedCamera)) ? W.nSlots : 0u;      // queue length = slot count (holes inside)
         const uint32_t* traceQueue = P.queue[it & 1];
         if (slotIter)
         {
+            mark(c, KIND_SORT);
             ptbk_sort_tile_local(L, nullptr, c->slotKeys.p, ci + CTR_NPATHS, 8, c->slotSorted.p, 7, W.nSlots);
             traceQueue = c->slotSorted.p;
         }
-        ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
-                   sortThis ? c->sortKeys.p : nullptr, c->sortHist.p, nOv, (uint32_t)numKeys);
-        if (c->profiling) cudaEventRecord(nextTraceEvent(c), c->stream);
+        mark(c, KIND_TRACE);
+        if (it == 0 && fusedCamera)
+            ptbk_trace_primary(L, c->S, F, W, P, ctr, lightsFromDepth, c->dstats.p, sortThis ? c->sortKeys.p : nullptr, c->sortHist.p,
+                               (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys);
+        else
+            ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
+                       sortThis ? c->sortKeys.p : nullptr, c->sortHist.p, nOv, (uint32_t)numKeys);
         const uint32_t* shadeQueue = traceQueue;
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)
-            if (slotIter) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys + 1, c->sortedQueue.p, numKeys, W.nSlots);
+            mark(c, KIND_SORT);
+            if (nOv) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys + 1, c->sortedQueue.p, numKeys, W.nSlots);     // queue with holes
             else if (c->sortMode == 3 && numKeys <= 4096) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys, c->sortedQueue.p);
             else ptbk_sort(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
             shadeQueue = c->sortedQueue.p;
         }
+        mark(c, KIND_SHADE);
         ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0, (useSlotOrder && it == 0) ? c->slotKeys.p : nullptr, nOv);
         if (!F.inlineShadow)
         {
+            mark(c, KIND_SHADOW);
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
                 ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
             if (F.features & PTB_OPT_LIGHTS)
@@ -322,7 +363,9 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
             if (*c->hCount == 0) break;
         }
     }
+    mark(c, KIND_ACCUM);
     ptbk_accumulate(L, F, W, P, c->accum.p, previewOut);
+    mark(c, KIND_NONE);
     CK(cudaGetLastError());
     return PTB_OK;
 }
@@ -424,6 +467,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     c->opts = *o;
     // default camera: looking down -z from the origin (the caller sets the real one with ptb_set_camera)
     c->cam = PtbCamera{{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, 1.0f, 1.0f, 0.0f};
+    if ((rc = refreshPixelTables(c)) != PTB_OK) { ptb_destroy(c); return rc; }
     refreshFrameParams(c);
     c->F.cullBoxes = 1;      // t-culled traversal by default; ptb_set_cull(0) = the reference's unculled visit order, see ptb200.h
     if ((rc = allocFrameBuffers(c)) != PTB_OK) { ptb_destroy(c); return rc; }
@@ -433,6 +477,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_SORT")) c->sortMode = atoi(e);
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
     if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
+    if (const char* e = getenv("PTB_FUSE_CAMERA")) c->fuseCamera = atoi(e);
     *out = c;
     return PTB_OK;
 }
@@ -444,7 +489,7 @@ int ptb_destroy(PtbCtx* c)
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
-    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release();
+    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
     c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->slotKeys.release(); c->slotSorted.release();
@@ -466,6 +511,7 @@ int ptb_set_options(PtbCtx* c, const PtbOptions* o)
     REQUIRE(o->renderW > 0 && o->renderH > 0 && o->tileW > 0 && o->tileH > 0, PTB_ERR_INVALID_ARGUMENT, "bad resolution");
     c->opts = *o;
     int cull = c->F.cullBoxes;
+    { int rc = refreshPixelTables(c); if (rc) return rc; }
     refreshFrameParams(c);
     c->F.cullBoxes = cull;
     if (resized) { c->snapshot.release(); c->snapshotF.release(); c->pending.valid = false; return allocFrameBuffers(c); }
@@ -753,9 +799,15 @@ int ptb_get_stats(PtbCtx* c, PtbStats* out)
     if (c->timingValid) cudaEventElapsedTime(&out->lastRenderMs, c->evStart, c->evStop);
     if (c->profiling)
     {
-        float tot = 0.f;
-        for (size_t i = 0; i + 1 < c->traceEventsUsed; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, c->traceEvents[i], c->traceEvents[i + 1]); tot += ms; }
-        out->lastTraceMs = tot;
+        float tot[KIND_COUNT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (size_t i = 0; i + 1 < c->traceEventsUsed; i++)
+        {
+            const int k = c->eventKind[i];
+            if (k < 0) continue;
+            float ms = 0.f; cudaEventElapsedTime(&ms, c->traceEvents[i], c->traceEvents[i + 1]); tot[k] += ms;
+        }
+        out->lastTraceMs = tot[KIND_TRACE]; out->lastCameraMs = tot[KIND_CAMERA]; out->lastSortMs = tot[KIND_SORT]; out->lastShadeMs = tot[KIND_SHADE];
+        out->lastShadowMs = tot[KIND_SHADOW]; out->lastAccumMs = tot[KIND_ACCUM];
     }
     return PTB_OK;
 }

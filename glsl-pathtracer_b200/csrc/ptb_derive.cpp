@@ -249,3 +249,26 @@ void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out)
     }
     out.numGroups = (int)(groups.size() / 3);
 }
+
+int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err)
+{
+    DREQ(renderW > 0 && renderH > 0 && tileW > 0 && tileH > 0 && tileW < 65536 && tileH < 65536 && renderW / tileW < 65536 && renderH / tileH < 65536, 4,
+         "resolution / tile size beyond the pixel-table encoding");
+    // the arithmetic of pixelSeed() in ptb_device.cuh (tile.glsl:43 with the uniforms of Renderer.cpp:293-294,780), one IEEE operation per step
+    auto fill = [](int n, int tile, int res, std::vector<float2>& tab)
+    {
+        const float invNumTiles = (float)tile / res;
+        tab.resize((size_t)n);
+        for (int x = 0; x < n; x++)
+        {
+            const int t = x / tile, l = x - t * tile;
+            const float tc = ((float)l + 0.5f) / (float)tile;
+            const float off = (float)t * invNumTiles;
+            const float a = off * (1.0f - tc), b = (off + invNumTiles) * tc;
+            tab[(size_t)x] = make_float2(a + b, u2f((uint32_t)l | ((uint32_t)t << 16)));
+        }
+    };
+    fill(renderW, tileW, renderW, tabX);
+    fill(renderH, tileH, renderH, tabY);
+    return 0;
+}

@@ -21,3 +21,5 @@ int ptbd_derive_hierarchy(const float* nodes, int numNodes, int topLevelIndex, i
                           int begin, int end, PtbDerivedHierarchy& out, std::string& err);
 int ptbd_build_tris(const int32_t* vertIndices, int numIndices, const float* verticesUVX, int numVertices, std::vector<float4>& tris, std::string& err);
 void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);
+// per-column / per-row pixel tables: {frame texture coordinate of the pixel centre (tile.glsl:43), bits(tile-local coordinate | tile index << 16)}
+int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err);

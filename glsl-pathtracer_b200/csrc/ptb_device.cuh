@@ -23,6 +23,17 @@
 #define PTB_EPS        0.0003f
 #define PTB_INF        1000000.0f
 
+// Traversal variants kept switchable for same-box A/B measurements (results are bit-identical either way)
+#ifndef PTB_TRI_EARLYOUT
+#define PTB_TRI_EARLYOUT 1      // decide triangle misses from the numerators' signs before dividing
+#endif
+#ifndef PTB_FUSED_POP
+#define PTB_FUSED_POP 0         // consume BLAS markers at the pop instead of in a round of their own (measured: -3.5 %, the restore inside the inner loop)
+#endif
+#ifndef PTB_FAST_INST
+#define PTB_FAST_INST 1         // short instance entry for translation-only transforms
+#endif
+
 namespace ptb {
 
 // ------------------------------------------------------------------ float3 helpers (contractable math) ----------
@@ -347,7 +358,9 @@ struct Trav
     __device__ __forceinline__ uint32_t popNext(Stack& stk)
     {
         uint32_t v = stk.pop();
+#if PTB_FUSED_POP
         if (v == PTB_META_NONE && inBlas) { leaveBlas(); v = stk.pop(); }
+#endif
         return v;
     }
 
@@ -407,13 +420,19 @@ struct Trav
                 const float na = xdot(tv, pv);
                 const int sd = __float_as_int(det);
                 const bool detSmall = fabsf(det) <= 1e18f;
+#if PTB_TRI_EARLYOUT
                 if (((__float_as_int(na) ^ sd) < 0) && fabsf(na) >= 1e-18f && detSmall) continue;
+#endif
                 const float3 qv = xcross(tv, e0);
                 const float nb = xdot(rd, qv);
+#if PTB_TRI_EARLYOUT
                 if (((__float_as_int(nb) ^ sd) < 0) && fabsf(nb) >= 1e-18f && detSmall) continue;
                 if (((__float_as_int(na) ^ sd) >= 0) && ((__float_as_int(nb) ^ sd) >= 0) && xa(fabsf(na), fabsf(nb)) > xm(1.001f, fabsf(det))) continue;
+#endif
                 const float nc = xdot(e1, qv);
+#if PTB_TRI_EARLYOUT
                 if (((__float_as_int(nc) ^ sd) < 0) && fabsf(nc) >= 1e-18f && detSmall) continue;
+#endif
                 const float ux = xd(na, det);
                 const float uy = xd(nb, det);
                 const float uz = xd(nc, det);
@@ -435,7 +454,7 @@ struct Trav
             curInst = (int)(cur & PTB_INST_INDEX_MASK);
             const float4* ip = S.instTrav + (size_t)curInst * 4;
             const float4 r3 = __ldg(ip + 3);
-            if ((cur & PTB_INST_TRANSLATION_ONLY) && generic)
+            if (PTB_FAST_INST && (cur & PTB_INST_TRANSLATION_ONLY) && generic)
             {   // inverse(transform) is [I | -translation] bit for bit (checked at upload): the general formula below then reduces, for a ray without
                 // zero components, to origin + r3 (x*1 = x, x + (+-0) = x for x != 0) and an unchanged direction, whose reciprocal is invW
 #if PTB_PACKED_SLAB
@@ -487,33 +506,57 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
 }
 
 // ------------------------------------------------------------------ camera ray --------------------------------------
-// tile.glsl:41-68 / preview.glsl:41-67.  (x,y) absolute pixel; returns the ray and leaves rng advanced by 4 draws.
-__device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass, Rng& rng, float3& ro, float3& rd)
+// tile.glsl:41-45 / preview.glsl:41-43: what a pixel contributes to its ray before any random number is drawn — the texture coordinate of the
+// pixel centre in the full frame (mix(tileOffset, tileOffset + invNumTiles, TexCoords)) and the RNG seed (tile-local gl_FragCoord, frameNum).
+struct PixelSeed { float cx, cy; uint32_t sx, sy, frame; };
+
+// frameNum of pass s, tile (tx,ty): first Update is the dirty one, tiles run x-fastest from the top row (Renderer.cpp:745-762)
+__device__ __forceinline__ uint32_t frameOf(const FrameParams& F, const WaveParams& W, int tx, int ty, int samplePass)
 {
-    float cx, cy;
+    if (W.fixedFrame >= 0) return (uint32_t)W.fixedFrame;
+    const int T = F.numTilesX * F.numTilesY;
+    const int j = (F.numTilesY - 1 - ty) * F.numTilesX + tx;
+    return (uint32_t)(2 + (samplePass - 1) * T + j);
+}
+
+// evaluated per pixel (preview target, parity entry points, host harness)
+__device__ __forceinline__ PixelSeed pixelSeed(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass)
+{
+    PixelSeed p;
     if (W.previewMode)
     {
-        cx = __fdiv_rn((float)x + 0.5f, (float)W.rw); cy = __fdiv_rn((float)y + 0.5f, (float)W.rh);     // TexCoords over the whole low-res target
-        rng.init((uint32_t)x, (uint32_t)y, 1u);                                         // preview.glsl:43
+        p.cx = __fdiv_rn((float)x + 0.5f, (float)W.rw); p.cy = __fdiv_rn((float)y + 0.5f, (float)W.rh);     // TexCoords over the whole low-res target
+        p.sx = (uint32_t)x; p.sy = (uint32_t)y; p.frame = 1u;                              // preview.glsl:43
+        return p;
     }
-    else
-    {
-        int tx = x / F.tileW, ty = y / F.tileH, lx = x - tx * F.tileW, ly = y - ty * F.tileH;
-        float tcx = __fdiv_rn((float)lx + 0.5f, (float)F.tileW), tcy = __fdiv_rn((float)ly + 0.5f, (float)F.tileH);
-        float offx = (float)tx * F.invNumTilesX, offy = (float)ty * F.invNumTilesY;        // Renderer.cpp:780
-        // mix(tileOffset, tileOffset + invNumTiles, TexCoords)  (tile.glsl:43)
-        cx = __fadd_rn(__fmul_rn(offx, __fsub_rn(1.0f, tcx)), __fmul_rn(__fadd_rn(offx, F.invNumTilesX), tcx));
-        cy = __fadd_rn(__fmul_rn(offy, __fsub_rn(1.0f, tcy)), __fmul_rn(__fadd_rn(offy, F.invNumTilesY), tcy));
-        int frame;
-        if (W.fixedFrame >= 0) frame = W.fixedFrame;
-        else
-        {   // frameNum of pass s, tile j: first Update is the dirty one, tiles run x-fastest from the top row (Renderer.cpp:745-762)
-            int T = F.numTilesX * F.numTilesY;
-            int j = (F.numTilesY - 1 - ty) * F.numTilesX + tx;
-            frame = 2 + (samplePass - 1) * T + j;
-        }
-        rng.init((uint32_t)lx, (uint32_t)ly, (uint32_t)frame);                            // gl_FragCoord is tile-local (tile.glsl:45)
-    }
+    int tx = x / F.tileW, ty = y / F.tileH, lx = x - tx * F.tileW, ly = y - ty * F.tileH;
+    float tcx = __fdiv_rn((float)lx + 0.5f, (float)F.tileW), tcy = __fdiv_rn((float)ly + 0.5f, (float)F.tileH);
+    float offx = __fmul_rn((float)tx, F.invNumTilesX), offy = __fmul_rn((float)ty, F.invNumTilesY);        // Renderer.cpp:780
+    // mix(tileOffset, tileOffset + invNumTiles, TexCoords)  (tile.glsl:43)
+    p.cx = __fadd_rn(__fmul_rn(offx, __fsub_rn(1.0f, tcx)), __fmul_rn(__fadd_rn(offx, F.invNumTilesX), tcx));
+    p.cy = __fadd_rn(__fmul_rn(offy, __fsub_rn(1.0f, tcy)), __fmul_rn(__fadd_rn(offy, F.invNumTilesY), tcy));
+    p.sx = (uint32_t)lx; p.sy = (uint32_t)ly;                                              // gl_FragCoord is tile-local (tile.glsl:45)
+    p.frame = frameOf(F, W, tx, ty, samplePass);
+    return p;
+}
+
+// The same from the per-column / per-row tables the host builds once per (resolution, tile size) with the arithmetic above
+// (ptbd_build_pixel_tables: {coordinate, bits(local | tile << 16)}): two 8-byte loads instead of two integer and two IEEE divisions per pixel.
+__device__ __forceinline__ PixelSeed pixelSeedFromTables(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass)
+{
+    const float2 ex = __ldg(F.pixTabX + x), ey = __ldg(F.pixTabY + y);
+    const uint32_t ux = __float_as_uint(ex.y), uy = __float_as_uint(ey.y);
+    PixelSeed p;
+    p.cx = ex.x; p.cy = ey.x; p.sx = ux & 0xffffu; p.sy = uy & 0xffffu;
+    p.frame = frameOf(F, W, (int)(ux >> 16), (int)(uy >> 16), samplePass);
+    return p;
+}
+
+// tile.glsl:45-68 / preview.glsl:43-67: RNG seeding, tent-filter jitter, pinhole / thin-lens ray.  Leaves rng advanced by 4 draws.
+__device__ __forceinline__ void cameraRayFromSeed(const FrameParams& F, const PixelSeed& ps, Rng& rng, float3& ro, float3& rd)
+{
+    const float cx = ps.cx, cy = ps.cy;
+    rng.init(ps.sx, ps.sy, ps.frame);
     float r1 = __fmul_rn(2.0f, rng.rand());
     float r2 = __fmul_rn(2.0f, rng.rand());
     float jx = r1 < 1.0f ? __fsub_rn(__fsqrt_rn(r1), 1.0f) : __fsub_rn(1.0f, __fsqrt_rn(__fsub_rn(2.0f, r1)));
@@ -545,6 +588,12 @@ __device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams
     float fl = __fsqrt_rn(xdot(fd, fd));
     rd = f3(xd(fd.x, fl), xd(fd.y, fl), xd(fd.z, fl));
     ro = f3(xa(pos.x, ap.x), xa(pos.y, ap.y), xa(pos.z, ap.z));
+}
+// (x,y) absolute pixel
+__device__ __forceinline__ void cameraRay(const FrameParams& F, const WaveParams& W, int x, int y, int samplePass, Rng& rng, float3& ro, float3& rd)
+{
+    const PixelSeed ps = (F.pixTabX && !W.previewMode) ? pixelSeedFromTables(F, W, x, y, samplePass) : pixelSeed(F, W, x, y, samplePass);
+    cameraRayFromSeed(F, ps, rng, ro, rd);
 }
 
 

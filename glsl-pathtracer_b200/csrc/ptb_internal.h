@@ -73,6 +73,8 @@ struct FrameParams
     int cullBoxes;       // cull child boxes whose entry distance exceeds the current hit distance
     int inlineShadow;    // shadow rays consume path RNG draws (BLEND alpha in AnyHit / EvalTransmittance) -> traced inside shade
     int general;         // shade kernel specialisation: 0 lights only, 1 + env/textures/emission, 2 + media/alpha/inline shadows
+    // per-column / per-row tables of the pixel -> (frame texture coordinate, tile-local coordinate, tile) mapping (ptbd_build_pixel_tables); null = evaluate per pixel
+    const float2* pixTabX; const float2* pixTabY;
 };
 
 // One wavefront: S sample passes of a pixel rectangle.
@@ -142,6 +144,8 @@ struct LaunchCfg
 void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
 void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
                 const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride = 0, uint32_t holeKey = 0);
+void ptbk_trace_primary(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0, int depthForLights, DevStats* stats,
+                        uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey);
 void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
                uint32_t* sorted);
 void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey = -1, uint32_t nOverride = 0);

@@ -94,13 +94,18 @@ __device__ __forceinline__ uint32_t shadeKey(const DevScene& S, int hitInst)
 // Persistent warps fetch 32 consecutive queue entries at a time (one atomic per fetch).  A lane-granular refill of finished
 // lanes was measured and rejected: it breaks the screen-space coherence of the warp (primary rays 0.68 -> 1.17 ms per 8.3 M rays)
 // and did not help the incoherent bounces (1.33 -> 1.35 ms), see DESIGN.md.
-template <bool CULL>
-__device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* __restrict__ queue, uint32_t n,
+// CAM: first bounce of a wave.  There is no queue yet: the 32 entries of a fetch are the path slots of one 8x4 pixel block, the camera
+// ray (tile.glsl:41-68) is generated in registers and traced at once; the ray, the RNG state and the initial queue (slot, or a hole
+// for the off-image pixels of a padded block) are written once from here, for the first shade pass.
+template <bool CULL, bool CAM>
+__device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, const uint32_t* __restrict__ queue, uint32_t n,
                                           uint32_t* fetchCtr, int lightsFromDepth, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t holeKey)
 {
     const uint32_t lane = threadIdx.x & 31u;
     SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     const bool lights = OPT(F, O_LIGHTS);
+    uint32_t blocksX = 1, blocksPerSample = 1;
+    if (CAM) { blocksX = (uint32_t)W.vw >> 3; blocksPerSample = blocksX * ((uint32_t)W.vh >> 2); }
     while (true)
     {
         uint32_t base = 0;
@@ -108,20 +113,49 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
-        const uint32_t pq = i < n ? queue[i] : 0xffffffffu;
-        if (i < n && pq == 0xffffffffu) { if (keys) keys[i] = holeKey; }      // hole of a slot-ordered queue (dead path): nothing to trace
+        uint32_t pq;
+        float3 o, d; int depth = 0;
+        if (CAM)
+        {   // slot -> (sample, 8x4 block, pixel): the divisions are per fetch, not per pixel (n is a multiple of 32)
+            const uint32_t b = base >> 5;
+            const uint32_t s = b / blocksPerSample, bb = b - s * blocksPerSample;
+            const uint32_t by = bb / blocksX, bx = bb - by * blocksX;
+            const int px = (int)(bx * 8u + (lane & 7u)), py = (int)(by * 4u + (lane >> 3));
+            const bool live = px < W.rw && py < W.rh;
+            pq = live ? i : 0xffffffffu;
+            P.queue[0][i] = pq;
+            if (live)
+            {
+                Rng rng;
+                cameraRay(F, W, W.x0 + px, W.y0 + py, W.firstSample + (int)s * W.sampleStride, rng, o, d);
+                P.rayO[i] = make_float4(o.x, o.y, o.z, 0.0f);
+                P.rayD[i] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+                P.rng[i] = rng.s;             // throughput (1) / radiance (0) / alpha (1) are implied in the first shade iteration
+                if (F.general)
+                {
+                    P.med[i] = make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(0));
+                    P.medCol[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    P.prevUV[i] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        else
+        {
+            pq = i < n ? queue[i] : 0xffffffffu;
+            if (pq != 0xffffffffu)
+            {
+                const float4 o4 = P.rayO[pq], d4 = P.rayD[pq];
+                o = f3(o4); d = f3(d4);
+                depth = (int)(short)(__float_as_uint(d4.w) & 0xffffu);
+            }
+        }
+        if (i < n && pq == 0xffffffffu) { if (keys) keys[i] = holeKey; }      // hole (dead path of a slot-ordered queue / off-image pixel): nothing to trace
         else if (i < n)
         {
             const uint32_t p = pq;
-            const float4 o4 = P.rayO[p], d4 = P.rayD[p];
-            const float3 o = f3(o4), d = f3(d4);
             HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
             float t = PTB_INF;
-            if (lights)
-            {
-                int depth = (int)(short)(__float_as_uint(d4.w) & 0xffffu);
-                if (depth >= lightsFromDepth) closestLights(S, o, d, t, h.light);         // OPT_HIDE_EMITTERS: lights only at depth > 0
-            }
+            if (lights && depth >= lightsFromDepth) closestLights(S, o, d, t, h.light);         // OPT_HIDE_EMITTERS: lights only at depth > 0
             traverse<false, false, CULL>(S, o, d, t, stk, h, NoAlpha());
             P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
             const int hi = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
@@ -144,8 +178,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     const uint32_t live = *countPtr;                     // rays actually traced (statistics)
     const uint32_t n = nOverride ? nOverride : live;     // queue length: the slot count when the queue is slot-ordered with holes
     if (blockIdx.x == 0 && threadIdx.x == 0 && live) atomicAdd(&stats->pathSegments, (unsigned long long)live);
-    if (F.cullBoxes) traceLoop<true>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
-    else traceLoop<false>(S, F, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
+    const WaveParams W{};
+    if (F.cullBoxes) traceLoop<true, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
+    else traceLoop<false, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
+}
+
+// First bounce: camera-ray generation fused into the closest-hit trace (see traceLoop<., true>).  liveCount = rays generated (host-known).
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_primary(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0, int lightsFromDepth,
+                                                                  DevStats* stats, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&stats->pathSegments, (unsigned long long)liveCount); ctr0[CTR_NPATHS] = liveCount; }
+    if (F.cullBoxes) traceLoop<true, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey);
+    else traceLoop<false, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey);
 }
 
 // Exclusive scan of the key histogram into bucket cursors (one warp); clears the histogram for the next bounce.
@@ -1042,6 +1086,7 @@ int ptbk_configure_device(const DevScene& S, int* traceBlocks, int shadeBlocks[3
     cudaError_t e = cudaSuccess;
     auto upd = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     upd(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_trace_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1067,6 +1112,14 @@ void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
 {
     const int bps = c.traceBlocks;
     k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist, nOverride, holeKey);
+    COUNT_LAUNCH(c, 1);
+}
+
+void ptbk_trace_primary(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, uint32_t* ctr0, int depthForLights,
+                        DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey)
+{
+    const int bps = c.traceBlocks;
+    k_trace_primary<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, W, P, ctr0, depthForLights, stats, keys, hist, liveCount, holeKey);
     COUNT_LAUNCH(c, 1);
 }
 

@@ -99,6 +99,8 @@ typedef struct PtbStats {
     float    lastRenderMs;     /* device time of the last ptb_render_* call (CUDA events on the context stream) */
     float    lastTraceMs;      /* device time of the closest-hit launches within it (0 unless profiling is enabled) */
     uint64_t lastTraceRays;    /* rays those launches traced */
+    float    lastCameraMs, lastSortMs, lastShadeMs, lastShadowMs, lastAccumMs;   /* the other kernel classes of that call (profiling only) */
+    float    reserved_;
 } PtbStats;
 
 typedef struct PtbCtx PtbCtx;

@@ -20,7 +20,7 @@ def lib():
         L.hh_stack_depth.argtypes = [vp]
         L.hh_trace_closest.argtypes = [vp, vp, C.c_longlong, i32, i32, vp]
         L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, vp]
-        L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, vp]
+        L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
         _LIB = L
     return _LIB
 
@@ -59,13 +59,13 @@ class HostTrav:
         lib().hh_trace_any(self.h, rays.ctypes.data, md.ctypes.data, len(rays), int(self.lights), int(self.cull), out.ctypes.data)
         return out
 
-    def camera_rays(self, sample=1):
+    def camera_rays(self, sample=1, tables=True):
         ro, cam = self.scene.renderOptions, self.scene.camera
         w, h = ro.renderResolution
         out = np.zeros((w * h, 6), np.float32)
         v = [np.ascontiguousarray(x, np.float32) for x in (cam.position, cam.right, cam.up, cam.forward)]
         lib().hh_camera_rays(w, h, ro.tileWidth, ro.tileHeight, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data, v[3].ctypes.data,
-                             float(cam.fov), float(cam.focalDist), float(cam.aperture), sample, out.ctypes.data)
+                             float(cam.fov), float(cam.focalDist), float(cam.aperture), sample, int(tables), out.ctypes.data)
         return out
 
     def stack_depth(self):

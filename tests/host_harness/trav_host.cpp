@@ -90,7 +90,7 @@ void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long
 
 // uniforms as refreshFrameParams (ptb_api.cpp) derives them from PtbOptions / PtbCamera
 void hh_camera_rays(int renderW, int renderH, int tileW, int tileH, const float* pos, const float* right, const float* up, const float* fwd, float fov, float focalDist,
-                    float aperture, int sample, float* out)
+                    float aperture, int sample, int useTables, float* out)
 {
     FrameParams F{};
     F.renderW = renderW; F.renderH = renderH; F.tileW = tileW; F.tileH = tileH;
@@ -99,6 +99,8 @@ void hh_camera_rays(int renderW, int renderH, int tileW, int tileH, const float*
     memcpy(F.camPos, pos, 12); memcpy(F.camRight, right, 12); memcpy(F.camUp, up, 12); memcpy(F.camFwd, fwd, 12);
     F.aspect = (float)renderH / (float)renderW;
     F.camScale = tanf(fov * 0.5f); F.camFocalDist = focalDist; F.camAperture = aperture;
+    std::vector<float2> tx, ty; std::string err;
+    if (useTables && ptbd_build_pixel_tables(renderW, renderH, tileW, tileH, tx, ty, err) == 0) { F.pixTabX = tx.data(); F.pixTabY = ty.data(); }
     WaveParams W{}; W.rw = renderW; W.rh = renderH; W.firstSample = sample; W.sampleStride = 1; W.fixedFrame = -1; W.nSamples = 1;
     for (int i = 0; i < renderW * renderH; i++)
     {

@@ -41,7 +41,7 @@ def test_every_entry_point_cites_the_reference():
 
 
 def test_struct_sizes_match_c_layout():
-    assert C.sizeof(capi.PtbCamera) == 60 and C.sizeof(capi.PtbStats) == 48
+    assert C.sizeof(capi.PtbCamera) == 60 and C.sizeof(capi.PtbStats) == 72
     assert capi.HIT_DTYPE.itemsize == 40 and capi.BSDF_QUERY_DTYPE.itemsize == 180 and capi.BSDF_RESULT_DTYPE.itemsize == 28
     assert C.sizeof(capi.PtbOptions) == 80
     assert C.sizeof(capi.PtbSceneDesc) == 8 * 13 + 4 * 12 if C.sizeof(capi.PtbSceneDesc) % 8 else True

@@ -14,10 +14,13 @@ SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyp
 
 @pytest.mark.parametrize("name", SCENES)
 def test_host_compiled_traversal_equals_oracle(name, oracle_mod):
-    sc = scene_at(name, 160, 90, 80, 45)
+    sc = scene_at(name, 160, 90, 48, 32)          # 4 x 3 tiles, last column and top row over-hang
     ht = HostTrav(sc); orc = oracle_mod.Oracle(sc); orc_c = oracle_mod.Oracle(sc, cull=True)
     prim = orc.camera_rays(1)
-    assert np.array_equal(ht.camera_rays(1).view(np.uint32), prim.view(np.uint32)), "camera rays"
+    for sample in (1, 5):          # per-pixel arithmetic and the per-column / per-row tables give the oracle's rays bit for bit (over-hanging tiles included)
+        want = orc.camera_rays(sample)
+        for tables in (False, True):
+            assert np.array_equal(ht.camera_rays(sample, tables).view(np.uint32), want.view(np.uint32)), f"camera rays, sample {sample}, tables {tables}"
     rays = np.concatenate([prim, random_rays(sc, 30_000, 7)])
     for depth in (0, 1):
         ht.set_cull(False)
