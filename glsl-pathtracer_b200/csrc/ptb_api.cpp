@@ -77,6 +77,7 @@ struct PtbCtx
 
     DevBuf<float> nodes, lights, envImg, envCdf;
     DevBuf<int> vertIndices;
+    DevBuf<float4> triShade;
     DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
     DevScene S{};
@@ -223,8 +224,11 @@ int buildTris(PtbCtx* c, const PtbSceneDesc* d)
     int rc = ptbd_build_tris(d->vertIndices, d->numIndices, d->verticesUVX, d->numVertices, t, err);
     REQUIRE(rc == 0, rc, err);
     CK(c->tris.upload(t.data(), t.size(), c->stream));
+    std::vector<float4> ts;
+    ptbd_build_tri_shade(d->vertIndices, d->numIndices, d->verticesUVX, d->normalsUVY, ts);
+    CK(c->triShade.upload(ts.data(), ts.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->S.tris = c->tris.p;
+    c->S.tris = c->tris.p; c->S.triShade = c->triShade.p;
     return PTB_OK;
 }
 
@@ -488,7 +492,7 @@ int ptb_destroy(PtbCtx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
-    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release();
+    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release();
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }

@@ -272,3 +272,19 @@ int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std:
     fill(renderH, tileH, renderH, tabY);
     return 0;
 }
+
+void ptbd_build_tri_shade(const int32_t* vertIndices, int numIndices, const float* verticesUVX, const float* normalsUVY, std::vector<float4>& out)
+{   // indices were validated by ptbd_build_tris
+    out.assign((size_t)numIndices * 4, make_float4(0, 0, 0, 0));
+    for (int s = 0; s < numIndices; s++)
+    {
+        const int32_t* vi = vertIndices + (size_t)s * 3;
+        const float* n0 = normalsUVY + (size_t)vi[0] * 4; const float* n1 = normalsUVY + (size_t)vi[1] * 4; const float* n2 = normalsUVY + (size_t)vi[2] * 4;
+        const float u0 = verticesUVX[(size_t)vi[0] * 4 + 3], u1 = verticesUVX[(size_t)vi[1] * 4 + 3], u2 = verticesUVX[(size_t)vi[2] * 4 + 3];
+        float4* q = &out[(size_t)s * 4];
+        q[0] = make_float4(n0[0], n0[1], n0[2], n1[0]);
+        q[1] = make_float4(n1[1], n1[2], n2[0], n2[1]);
+        q[2] = make_float4(n2[2], u0, n0[3], u1);
+        q[3] = make_float4(n1[3], u2, n2[3], 0.f);
+    }
+}

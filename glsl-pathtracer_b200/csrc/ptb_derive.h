@@ -20,6 +20,9 @@ struct PtbDerivedLights { std::vector<float4> lightsPre, lightGroups; int numGro
 int ptbd_derive_hierarchy(const float* nodes, int numNodes, int topLevelIndex, int numIndices, int numMaterials, const float* transforms, int numInstances,
                           int begin, int end, PtbDerivedHierarchy& out, std::string& err);
 int ptbd_build_tris(const int32_t* vertIndices, int numIndices, const float* verticesUVX, int numVertices, std::vector<float4>& tris, std::string& err);
+// per leaf-ref slot: the three vertex normals and texture coordinates the hit-attribute code interpolates (closest_hit.glsl:226-241), gathered
+// through vertIndices at upload: one 64-byte record instead of an index fetch followed by six scattered 16-byte fetches
+void ptbd_build_tri_shade(const int32_t* vertIndices, int numIndices, const float* verticesUVX, const float* normalsUVY, std::vector<float4>& out);
 void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);
 // per-column / per-row pixel tables: {frame texture coordinate of the pixel centre (tile.glsl:43), bits(tile-local coordinate | tile index << 16)}
 int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err);

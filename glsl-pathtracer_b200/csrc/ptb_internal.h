@@ -44,6 +44,7 @@ struct DevScene
     // derived
     const float4* inner;        // 4 float4 / canonical node index: child boxes + child metas (valid for internal nodes)
     const float4* tris;         // 3 float4 / leaf-ref slot: v0, e0, e1, vertIndices.x
+    const float4* triShade;     // 4 float4 / leaf-ref slot: n0 n1 n2 (9 floats), (u,v) x 3 (ptbd_build_tri_shade)
     const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {0, matID, 0, rootMeta} in .w
     const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
     const float4* lightsPre;    // 8 float4 / light (see buildLightsPre in ptb_api.cpp)

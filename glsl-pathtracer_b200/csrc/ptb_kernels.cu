@@ -323,10 +323,12 @@ struct Surf
 // closest_hit.glsl:220-263 for a triangle hit (slot = leaf-ref slot, inst = instance)
 __device__ __forceinline__ void triangleSurface(const DevScene& S, int slot, int inst, float bu, float bv, float3 ro, float3 rd, float t, bool needUV, bool needTangents, Surf& sf)
 {
-    const int i0 = __ldg(S.vertIndices + (size_t)slot * 3), i1 = __ldg(S.vertIndices + (size_t)slot * 3 + 1), i2 = __ldg(S.vertIndices + (size_t)slot * 3 + 2);
     const float bw = 1.0f - bu - bv;       // uvt.w; bary = uvt.wxy
-    const float4 n0 = __ldg(S.normalsUVY + i0), n1 = __ldg(S.normalsUVY + i1), n2 = __ldg(S.normalsUVY + i2);
-    float3 normal = normalize(f3(n0) * bw + f3(n1) * bu + f3(n2) * bv);
+    // the three vertex normals (and texture coordinates) of this leaf-ref slot, gathered at upload (closest_hit.glsl:226-235 reads them through vertexIndicesTex)
+    const float4* ts = S.triShade + (size_t)slot * 4;
+    const float4 s0 = __ldg(ts), s1 = __ldg(ts + 1), s2 = __ldg(ts + 2);
+    const float3 nn0 = f3(s0.x, s0.y, s0.z), nn1 = f3(s0.w, s1.x, s1.y), nn2 = f3(s1.z, s1.w, s2.x);
+    float3 normal = normalize(nn0 * bw + nn1 * bu + nn2 * bv);
     const float4* is = S.instShade + (size_t)inst * 8;
     const float4 m0 = __ldg(is + 4), m1 = __ldg(is + 5), m2 = __ldg(is + 6);       // inverse(mat3(transform)) rows
     float3 nw = f3(m0.x * normal.x + m0.y * normal.y + m0.z * normal.z, m1.x * normal.x + m1.y * normal.y + m1.z * normal.z,
@@ -340,11 +342,13 @@ __device__ __forceinline__ void triangleSurface(const DevScene& S, int slot, int
     sf.tangent = sf.bitangent = f3(0.f);
     if (needUV)
     {
-        const float4 v0 = __ldg(S.verticesUVX + i0), v1 = __ldg(S.verticesUVX + i1), v2 = __ldg(S.verticesUVX + i2);
-        float2 t0 = make_float2(v0.w, n0.w), t1 = make_float2(v1.w, n1.w), t2 = make_float2(v2.w, n2.w);
+        const float4 s3 = __ldg(ts + 3);
+        float2 t0 = make_float2(s2.y, s2.z), t1 = make_float2(s2.w, s3.x), t2 = make_float2(s3.y, s3.z);
         sf.uv = make_float2(t0.x * bw + t1.x * bu + t2.x * bv, t0.y * bw + t1.y * bu + t2.y * bv);
         if (needTangents)
         {
+            const int i0 = __ldg(S.vertIndices + (size_t)slot * 3), i1 = __ldg(S.vertIndices + (size_t)slot * 3 + 1), i2 = __ldg(S.vertIndices + (size_t)slot * 3 + 2);
+            const float4 v0 = __ldg(S.verticesUVX + i0), v1 = __ldg(S.verticesUVX + i1), v2 = __ldg(S.verticesUVX + i2);
             float3 dp1 = f3(v1) - f3(v0), dp2 = f3(v2) - f3(v0);
             float2 duv1 = make_float2(t1.x - t0.x, t1.y - t0.y), duv2 = make_float2(t2.x - t0.x, t2.y - t0.y);
             float invdet = 1.0f / (duv1.x * duv2.y - duv1.y * duv2.x);
