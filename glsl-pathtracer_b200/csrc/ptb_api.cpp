@@ -77,7 +77,8 @@ struct PtbCtx
 
     DevBuf<float> nodes, lights, envImg, envCdf;
     DevBuf<int> vertIndices;
-    DevBuf<float4> triShade;
+    DevBuf<float4> triShade, wide;
+    int wideAny = 1;           // 1: shadow rays use the 4-wide any-hit hierarchy where it is provably equivalent (PTB_WIDE_ANY)
     DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
     DevScene S{};
@@ -111,7 +112,7 @@ struct PtbCtx
 
     uint64_t samplesRendered = 0;
     unsigned long long launches = 0;          // kernels launched through this context
-    int traceBlocks = 1, shadeBlocks[3] = {1, 1, 1}, configuredDepth = -1;   // per-device launch configuration (ptbk_configure_device)
+    int traceBlocks = 1, shadowBlocks = 1, shadeBlocks[3] = {1, 1, 1}, configuredDepth = -1, configuredDepthAny = -1;   // per-device launch configuration (ptbk_configure_device)
     uint64_t lastTraceRays = 0;
     bool timingValid = false;
 };
@@ -120,16 +121,16 @@ namespace {
 
 LaunchCfg cfg(PtbCtx* c)
 {
-    return LaunchCfg{c->numSMs, (void*)c->stream, c->traceBlocks, {c->shadeBlocks[0], c->shadeBlocks[1], c->shadeBlocks[2]}, &c->launches};
+    return LaunchCfg{c->numSMs, (void*)c->stream, c->traceBlocks, c->shadowBlocks, {c->shadeBlocks[0], c->shadeBlocks[1], c->shadeBlocks[2]}, &c->launches};
 }
 
 // kernel attributes / occupancy of this context's device for the current stack depth (the device must be current)
 int configureDevice(PtbCtx* c)
 {
-    if (c->configuredDepth == c->S.stackDepth) return PTB_OK;
-    cudaError_t e = (cudaError_t)ptbk_configure_device(c->S, &c->traceBlocks, c->shadeBlocks);
+    if (c->configuredDepth == c->S.stackDepth && c->configuredDepthAny == c->S.stackDepthAny) return PTB_OK;
+    cudaError_t e = (cudaError_t)ptbk_configure_device(c->S, &c->traceBlocks, &c->shadowBlocks, c->shadeBlocks);
     if (e != cudaSuccess) { g_err = std::string("ptbk_configure_device: ") + cudaGetErrorString(e); return PTB_ERR_CUDA; }
-    c->configuredDepth = c->S.stackDepth;
+    c->configuredDepth = c->S.stackDepth; c->configuredDepthAny = c->S.stackDepthAny;
     return PTB_OK;
 }
 
@@ -140,12 +141,22 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
     int rc = ptbd_derive_hierarchy(c->hNodes.data(), c->numNodes, c->topLevelIndex, c->S.numIndices, c->S.numMaterials, c->hTransforms.data(),
                                    (int)(c->hTransforms.size() / 16), begin, end, dh, err);
     REQUIRE(rc == 0, rc, err);
+    // 4-wide hierarchy for the any-hit rays (rebuilt as a whole: a few ms even at 10^5 nodes); its BLAS roots travel in instTrav[k][2].w
+    PtbDerivedWide dw;
+    if (c->wideAny) ptbd_build_wide(c->hNodes.data(), c->numNodes, c->topLevelIndex, c->S.numIndices, (int)(c->hTransforms.size() / 16), dh.transOnly, dw);
+    if (dw.ok)
+    {
+        for (size_t k = 0; k < dw.instRootMeta.size(); k++) dh.instTrav[k * 4 + 2].w = u2f(dw.instRootMeta[k]);
+        CK(cudaStreamSynchronize(c->stream));       // a wave in flight may still read the old array
+        CK(c->wide.upload(dw.wide.data(), dw.wide.size(), c->stream));
+    }
     CK(c->inner.alloc((size_t)c->numNodes * 4));
     if (end > begin) CK(cudaMemcpyAsync(c->inner.p + (size_t)begin * 4, dh.inner.data(), dh.inner.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     CK(c->instTrav.upload(dh.instTrav.data(), dh.instTrav.size(), c->stream));
     CK(c->instShade.upload(dh.instShade.data(), dh.instShade.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));   // staging vectors die at scope exit
-    c->S.stackDepth = dh.stackDepth; c->S.rootMeta = dh.rootMeta;
+    c->S.stackDepth = dh.stackDepth; c->S.stackDepthAny = dw.ok ? std::max(dh.stackDepth, dw.stackDepth) : dh.stackDepth; c->S.rootMeta = dh.rootMeta;
+    c->S.wide = dw.ok ? c->wide.p : nullptr; c->S.rootMetaWide = dw.rootMeta;
     c->S.inner = c->inner.p; c->S.instTrav = c->instTrav.p; c->S.instShade = c->instShade.p;
     (void)all;
     return configureDevice(c);
@@ -463,6 +474,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     S.numTextures = d->numTextures; S.texW = d->texW; S.texH = d->texH;
     S.envW = d->envImg ? d->envW : 0; S.envH = d->envImg ? d->envH : 0; S.envTotalSum = d->envTotalSum;
 
+    if (const char* e = getenv("PTB_WIDE_ANY")) c->wideAny = atoi(e);
     int rc;
     if ((rc = buildTris(c, d)) != PTB_OK) { ptb_destroy(c); return rc; }
     if ((rc = buildLightsPre(c, d->lights, d->numLights)) != PTB_OK) { ptb_destroy(c); return rc; }
@@ -492,7 +504,7 @@ int ptb_destroy(PtbCtx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
-    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release();
+    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release(); c->wide.release();
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }

@@ -139,7 +139,7 @@ int ptbd_derive_hierarchy(const float* N, int numNodes, int topLevelIndex, int n
     out.stackDepth = std::max(4, 1 + tlasDepth + 1 + maxBlas + 1);
     DREQ(out.stackDepth <= 64, 4, "BVH deeper than the 64-entry traversal stack of the reference shader");
 
-    std::vector<char> transOnly(ni, 0);
+    std::vector<char>& transOnly = out.transOnly; transOnly.assign((size_t)ni, 0);
     for (int k = 0; k < ni; k++)
     {
         const float* D = transforms + (size_t)k * 16;
@@ -287,4 +287,110 @@ void ptbd_build_tri_shade(const int32_t* vertIndices, int numIndices, const floa
         q[2] = make_float4(n2[2], u0, n0[3], u1);
         q[3] = make_float4(n1[3], u2, n2[3], 0.f);
     }
+}
+
+namespace {
+
+struct WideBuilder
+{
+    const float* N; int numNodes, numIndices;
+    std::vector<float4>& wide;
+    const std::vector<char>& transOnly;
+    bool ok = true;
+    std::vector<int> memo;          // binary inner node -> wide index (a BLAS shared by several instances is collapsed once)
+    std::vector<int> need;          // stack entries needed below a wide node (siblings pushed while descending)
+
+    WideBuilder(const float* n, int nn, int ni, std::vector<float4>& w, const std::vector<char>& to) : N(n), numNodes(nn), numIndices(ni), wide(w), transOnly(to), memo((size_t)nn, -1) {}
+    uint32_t leafMeta(int node)
+    {
+        std::string err;
+        uint32_t m = metaOf(N, node, numIndices, err);
+        if (!err.empty()) ok = false;
+        if ((m >> 30) == PTB_K_INST)
+        {
+            const uint32_t k = m & PTB_INST_INDEX_MASK;
+            if (k >= transOnly.size()) ok = false;
+            else if (transOnly[k]) m |= PTB_INST_TRANSLATION_ONLY;
+        }
+        return m;
+    }
+
+    static float area(const float* n) { float dx = n[3] - n[0], dy = n[4] - n[1], dz = n[5] - n[2]; return dx * dy + dy * dz + dz * dx; }
+    bool inner(int i) const { return (int)N[(size_t)i * 9 + 8] == 0; }
+    bool contains(int p, int c) const
+    {
+        const float* a = N + (size_t)p * 9; const float* b = N + (size_t)c * 9;
+        return a[0] <= b[0] && a[1] <= b[1] && a[2] <= b[2] && a[3] >= b[3] && a[4] >= b[4] && a[5] >= b[5];
+    }
+
+    // collapse the binary subtree rooted at inner node r; returns the wide index
+    int build(int r, int depth)
+    {
+        if (memo[(size_t)r] >= 0) return memo[(size_t)r];
+        if (depth > 200) { ok = false; return 0; }
+        int kids[4]; int nk = 0;
+        auto addChildren = [&](int p, int at)
+        {   // replace slot `at` (or append when at == nk) by the two children of p, left first
+            int l = (int)N[(size_t)p * 9 + 6], rr = (int)N[(size_t)p * 9 + 7];
+            if (l < 0 || l >= numNodes || rr < 0 || rr >= numNodes) { ok = false; return; }
+            if (p != r && !(contains(p, l) && contains(p, rr))) ok = false;     // the dropped box must contain what replaces it
+            if (at == nk) { kids[nk++] = l; kids[nk++] = rr; }
+            else { for (int k = nk; k > at + 1; k--) kids[k] = kids[k - 1]; kids[at] = l; kids[at + 1] = rr; nk++; }
+        };
+        addChildren(r, 0);
+        while (ok && nk < 4)
+        {
+            int best = -1; float bestA = -1.f;
+            for (int k = 0; k < nk; k++) if (inner(kids[k])) { float a = area(N + (size_t)kids[k] * 9); if (a > bestA || best < 0) { bestA = a; best = k; } }
+            if (best < 0) break;
+            addChildren(kids[best], best);
+        }
+        const int w = (int)(wide.size() / 8);
+        memo[(size_t)r] = w;
+        wide.resize(wide.size() + 8, make_float4(0, 0, 0, 0));
+        need.push_back(0);
+        float box[24]; uint32_t meta[4];
+        const float qnan = std::nanf("");
+        int deepest = 0;
+        for (int k = 0; k < 4; k++)
+        {
+            if (k >= nk || !ok) { for (int j = 0; j < 6; j++) box[k * 6 + j] = qnan; meta[k] = PTB_META_NONE; continue; }
+            const float* n = N + (size_t)kids[k] * 9;
+            // every binary node's box must contain its children's boxes for the equivalence argument (checked for the nodes kept as children too)
+            if (inner(kids[k])) { int l = (int)n[6], rr = (int)n[7]; if (l < 0 || l >= numNodes || rr < 0 || rr >= numNodes || !contains(kids[k], l) || !contains(kids[k], rr)) ok = false; }
+            for (int j = 0; j < 6; j++) box[k * 6 + j] = n[j];
+            if (inner(kids[k])) { int cw = build(kids[k], depth + 1); meta[k] = (PTB_K_INNER << 30) | (uint32_t)cw; deepest = std::max(deepest, need[(size_t)cw]); }
+            else meta[k] = leafMeta(kids[k]);
+        }
+        float4* q = &wide[(size_t)w * 8];
+        for (int j = 0; j < 6; j++) q[j] = make_float4(box[j * 4 + 0], box[j * 4 + 1], box[j * 4 + 2], box[j * 4 + 3]);
+        q[6] = make_float4(u2f(meta[0]), u2f(meta[1]), u2f(meta[2]), u2f(meta[3]));
+        need[(size_t)w] = (nk - 1) + deepest;
+        return w;
+    }
+};
+
+} // namespace
+
+void ptbd_build_wide(const float* N, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, PtbDerivedWide& out)
+{
+    out = PtbDerivedWide();
+    out.instRootMeta.assign((size_t)numInstances, PTB_META_NONE);
+    WideBuilder B(N, numNodes, numIndices, out.wide, transOnly);
+    auto rootOf = [&](int node, int& needOut) -> uint32_t
+    {
+        if (node < 0 || node >= numNodes) { B.ok = false; return PTB_META_NONE; }
+        if (B.inner(node)) { int w = B.build(node, 0); needOut = std::max(needOut, B.need[(size_t)w]); return (PTB_K_INNER << 30) | (uint32_t)w; }
+        return B.leafMeta(node);
+    };
+    int needBlas = 0, needTlas = 0;
+    for (int i = topLevelIndex; i < numNodes; i++)
+    {
+        const float* n = N + (size_t)i * 9;
+        const int leaf = (int)n[8];
+        if (leaf < 0 && -leaf - 1 < numInstances) out.instRootMeta[(size_t)(-leaf - 1)] = rootOf((int)n[6], needBlas);
+    }
+    out.rootMeta = rootOf(topLevelIndex, needTlas);
+    out.stackDepth = std::max(4, 1 + needTlas + 1 + needBlas + 1);
+    out.ok = B.ok && out.stackDepth <= 96 && out.wide.size() / 8 < (1u << 30);
 }

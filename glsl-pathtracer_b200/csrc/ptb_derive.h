@@ -11,6 +11,7 @@ struct PtbDerivedHierarchy
     std::vector<float4> inner;        // rows for canonical nodes [begin, end): 4 float4 each
     std::vector<float4> instTrav;     // 4 float4 / instance
     std::vector<float4> instShade;    // 8 float4 / instance
+    std::vector<char> transOnly;      // per instance: inverse(transform) is [I | -translation] bit for bit (flag of the instance metas)
     uint32_t rootMeta = PTB_META_NONE;
     int stackDepth = 4;
 };
@@ -23,6 +24,22 @@ int ptbd_build_tris(const int32_t* vertIndices, int numIndices, const float* ver
 // per leaf-ref slot: the three vertex normals and texture coordinates the hit-attribute code interpolates (closest_hit.glsl:226-241), gathered
 // through vertIndices at upload: one 64-byte record instead of an index fetch followed by six scattered 16-byte fetches
 void ptbd_build_tri_shade(const int32_t* vertIndices, int numIndices, const float* verticesUVX, const float* normalsUVY, std::vector<float4>& out);
+// 4-wide hierarchy for the ANY-HIT traversal (anyhit.glsl:65-213).  In any-hit the distance bound never shrinks, so which leaves a ray reaches does not
+// depend on the visiting order; and because every node box of the reference's hierarchy contains its children's boxes (verified here) and the slab test
+// is monotone in the box bounds, "child box passes => parent box passes": a leaf is reached exactly when ITS OWN box passes.  Any hierarchy over the same
+// leaf boxes therefore returns the same boolean.  This one collapses the binary tree (largest-area inner child first) into nodes of up to four children
+// whose boxes are the exact boxes of the corresponding binary nodes; empty child slots carry NaN boxes (every comparison fails) and the NONE meta.
+//   wide[w*8 + 0..5] = 4 boxes x {min.xyz, max.xyz} (24 floats), wide[w*8 + 6] = 4 child metas (INNER -> wide index, LEAF / INST as in the binary layout)
+// ok = false (containment violated somewhere, or an encoding limit) disables the wide path; the binary traversal is always available.
+struct PtbDerivedWide
+{
+    std::vector<float4> wide;               // 8 float4 per wide node
+    std::vector<uint32_t> instRootMeta;     // per instance: meta of its BLAS root in the wide hierarchy
+    uint32_t rootMeta = PTB_META_NONE;      // TLAS root
+    int stackDepth = 4;                     // sentinel + TLAS siblings + marker + BLAS siblings
+    bool ok = false;
+};
+void ptbd_build_wide(const float* nodes, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, PtbDerivedWide& out);
 void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);
 // per-column / per-row pixel tables: {frame texture coordinate of the pixel centre (tile.glsl:43), bits(tile-local coordinate | tile index << 16)}
 int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err);

@@ -271,6 +271,47 @@ __device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d,
     return false;
 }
 
+// One triangle of a leaf (closest_hit.glsl:118-153 / anyhit.glsl:88-117): true when the reference's acceptance test passes for the current distance bound t;
+// ux, uy, uz = uvt.xyz are valid then.  slot = leaf-ref slot; ro / rd = ray in the space of the leaf.
+__device__ __forceinline__ bool triangleHit(const DevScene& S, uint32_t slot, float3 ro, float3 rd, float t, float& ux, float& uy, float& uz)
+{
+    const float4* tp = S.tris + (size_t)slot * 3;
+    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    const float3 v0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x);
+    // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard).  The acceptance test is
+    //   ux >= 0 && uy >= 0 && uz >= 0 && uw >= 0 && uz < t   with   u* = numerator / det,  uw = (1 - ux) - uy.
+    // Most tests are misses, and most misses can be decided from the numerators without dividing, with the SAME outcome:
+    //  * numerator and det of strictly opposite sign, |numerator| >= 1e-18 and |det| <= 1e18: the IEEE quotient is a negative number
+    //    of magnitude >= 1e-36 (it cannot round to -0, which would pass `>= 0`), or -inf for det = +-0;
+    //  * both numerators share det's sign and |a| + |b| > 1.001 |det|: ux + uy > 1.0007, so (1 - ux) - uy is below -7e-4 whatever the
+    //    rounding (or -inf when a quotient overflows).
+    // NaNs and everything near a boundary take the full path below, which is the reference's arithmetic unchanged.
+    const float3 pv = xcross(rd, e1);
+    const float det = xdot(e0, pv);
+    const float3 tv = xsub(ro, v0);
+    const float na = xdot(tv, pv);
+    const int sd = __float_as_int(det);
+    const bool detSmall = fabsf(det) <= 1e18f;
+#if PTB_TRI_EARLYOUT
+    if (((__float_as_int(na) ^ sd) < 0) && fabsf(na) >= 1e-18f && detSmall) return false;
+#endif
+    const float3 qv = xcross(tv, e0);
+    const float nb = xdot(rd, qv);
+#if PTB_TRI_EARLYOUT
+    if (((__float_as_int(nb) ^ sd) < 0) && fabsf(nb) >= 1e-18f && detSmall) return false;
+    if (((__float_as_int(na) ^ sd) >= 0) && ((__float_as_int(nb) ^ sd) >= 0) && xa(fabsf(na), fabsf(nb)) > xm(1.001f, fabsf(det))) return false;
+#endif
+    const float nc = xdot(e1, qv);
+#if PTB_TRI_EARLYOUT
+    if (((__float_as_int(nc) ^ sd) < 0) && fabsf(nc) >= 1e-18f && detSmall) return false;
+#endif
+    ux = xd(na, det);
+    uy = xd(nb, det);
+    uz = xd(nc, det);
+    const float uw = xs(xs(1.0f, ux), uy);
+    return ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < t;
+}
+
 // Stack policies: shared memory (one column per thread, conflict-free) for the wavefront trace kernels,
 // thread-local array for the rarely used inline traversal inside the shade kernel.
 struct SmemStack
@@ -403,49 +444,14 @@ struct Trav
             const uint32_t first = cur & PTB_MAX_LEAF_SLOT, cnt = (cur >> 26) & 15u;
             for (uint32_t i = 0; i < cnt; i++)
             {
-                const float4* tp = S.tris + (size_t)(first + i) * 3;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                const float3 v0 = f3(a.x, a.y, a.z), e0 = f3(a.w, b.x, b.y), e1 = f3(b.z, b.w, c.x);
-                // Moeller-Trumbore exactly as closest_hit.glsl:127-141 (three IEEE divisions by det, no det==0 guard).  The acceptance test is
-                //   ux >= 0 && uy >= 0 && uz >= 0 && uw >= 0 && uz < t   with   u* = numerator / det,  uw = (1 - ux) - uy.
-                // Most tests are misses, and most misses can be decided from the numerators without dividing, with the SAME outcome:
-                //  * numerator and det of strictly opposite sign, |numerator| >= 1e-18 and |det| <= 1e18: the IEEE quotient is a negative number
-                //    of magnitude >= 1e-36 (it cannot round to -0, which would pass `>= 0`), or -inf for det = +-0;
-                //  * both numerators share det's sign and |a| + |b| > 1.001 |det|: ux + uy > 1.0007, so (1 - ux) - uy is below -7e-4 whatever the
-                //    rounding (or -inf when a quotient overflows).
-                // NaNs and everything near a boundary take the full path below, which is the reference's arithmetic unchanged.
-                const float3 pv = xcross(rd, e1);
-                const float det = xdot(e0, pv);
-                const float3 tv = xsub(roNow(), v0);
-                const float na = xdot(tv, pv);
-                const int sd = __float_as_int(det);
-                const bool detSmall = fabsf(det) <= 1e18f;
-#if PTB_TRI_EARLYOUT
-                if (((__float_as_int(na) ^ sd) < 0) && fabsf(na) >= 1e-18f && detSmall) continue;
-#endif
-                const float3 qv = xcross(tv, e0);
-                const float nb = xdot(rd, qv);
-#if PTB_TRI_EARLYOUT
-                if (((__float_as_int(nb) ^ sd) < 0) && fabsf(nb) >= 1e-18f && detSmall) continue;
-                if (((__float_as_int(na) ^ sd) >= 0) && ((__float_as_int(nb) ^ sd) >= 0) && xa(fabsf(na), fabsf(nb)) > xm(1.001f, fabsf(det))) continue;
-#endif
-                const float nc = xdot(e1, qv);
-#if PTB_TRI_EARLYOUT
-                if (((__float_as_int(nc) ^ sd) < 0) && fabsf(nc) >= 1e-18f && detSmall) continue;
-#endif
-                const float ux = xd(na, det);
-                const float uy = xd(nb, det);
-                const float uz = xd(nc, det);
-                const float uw = xs(xs(1.0f, ux), uy);
-                if (ux >= 0.0f && uy >= 0.0f && uz >= 0.0f && uw >= 0.0f && uz < t)
+                float ux, uy, uz;
+                if (!triangleHit(S, first + i, roNow(), rd, t, ux, uy, uz)) continue;
+                if constexpr (ANY)
                 {
-                    if constexpr (ANY)
-                    {
-                        if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) { occluded = true; return true; } }
-                        else { occluded = true; return true; }
-                    }
-                    else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
+                    if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) { occluded = true; return true; } }
+                    else { occluded = true; return true; }
                 }
+                else { t = uz; h.prim = (int)(first + i); h.inst = curInst; h.bu = ux; h.bv = uy; h.light = -1; }
             }
             cur = popNext(stk);
         }
@@ -503,6 +509,98 @@ __device__ __forceinline__ bool traverse(const DevScene& S, float3 o, float3 d, 
     while (!tr.round(S, stk, alphaFn)) { }
     if (!ANY) h = tr.h;
     return tr.occluded;
+}
+
+// ------------------------------------------------------------------ 4-wide any-hit traversal ------------------------
+// AnyHit (anyhit.glsl:65-213) over the collapsed 4-wide hierarchy of ptbd_build_wide.  The result is the SAME boolean as the binary traversal's:
+// the distance bound never shrinks in any-hit, so the set of leaves reached does not depend on the visiting order, and a leaf is reached exactly when
+// its own box passes (every dropped box contains the boxes that replace it and the slab test is monotone in the bounds — for rays whose reciprocal
+// direction is finite, so that no 0 * inf NaN exists; other rays, and rays whose direction degenerates inside an instance, use the binary traversal).
+// Boxes and arithmetic are the reference's: each child box is tested with the IEEE operations of AABBIntersect (intersection.glsl:68-82).
+__device__ __forceinline__ bool wideRayOk(float3 d)
+{   // 1/d finite and d finite for all three components (false for NaN)
+    return fabsf(d.x) >= 1e-30f && fabsf(d.y) >= 1e-30f && fabsf(d.z) >= 1e-30f && fabsf(d.x) <= 1e30f && fabsf(d.y) <= 1e30f && fabsf(d.z) <= 1e30f;
+}
+
+// 0 = not occluded, 1 = occluded, 2 = undecided: trace this ray with the binary traversal
+template <bool ALPHA, bool CULL, class Stack, class AlphaFn>
+__device__ __forceinline__ int traverseWideAny(const DevScene& S, float3 o, float3 d, float tmax, Stack& stk, AlphaFn alphaFn)
+{
+    const float3 invW = f3(xd(1.0f, d.x), xd(1.0f, d.y), xd(1.0f, d.z));
+    float3 ro = o, rd = d, inv = invW;
+    const float tc = tmax * 1.00001f;
+    uint32_t cur = S.rootMetaWide;
+    int curInst = -1;
+    bool inBlas = false;
+    stk.reset();
+    stk.push(PTB_META_NONE);
+    const float4* __restrict__ wideBase = S.wide;
+    while (true)
+    {
+        while (cur < (1u << 30))
+        {
+            const float4* n = wideBase + (size_t)cur * 8;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3), q4 = __ldg(n + 4), q5 = __ldg(n + 5);
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(n + 6));
+            float e0, e1, e2, e3;
+            const float h0 = aabbHit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ro, inv, e0);
+            const float h1 = aabbHit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ro, inv, e1);
+            const float h2 = aabbHit(q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, ro, inv, e2);
+            const float h3 = aabbHit(q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, ro, inv, e3);
+            // the reference's `hit > 0` (and, in the culled variant, entry <= tmax * 1.00001); empty slots hold NaN boxes: every comparison fails
+            const bool p0 = h0 > 0.0f && !(CULL && e0 > tc), p1 = h1 > 0.0f && !(CULL && e1 > tc);
+            const bool p2 = h2 > 0.0f && !(CULL && e2 > tc), p3 = h3 > 0.0f && !(CULL && e3 > tc);
+            uint32_t c = PTB_META_NONE; bool have = false;
+            if (p3) { c = m.w; have = true; }
+            if (p2) { if (have) stk.push(c); c = m.z; have = true; }
+            if (p1) { if (have) stk.push(c); c = m.y; have = true; }
+            if (p0) { if (have) stk.push(c); c = m.x; have = true; }
+            cur = have ? c : stk.pop();
+        }
+        const uint32_t kind = cur >> 30;
+        if (kind == PTB_K_LEAF)
+        {
+            const uint32_t first = cur & PTB_MAX_LEAF_SLOT, cnt = (cur >> 26) & 15u;
+            for (uint32_t i = 0; i < cnt; i++)
+            {
+                float ux, uy, uz;
+                if (!triangleHit(S, first + i, ro, rd, tmax, ux, uy, uz)) continue;
+                if constexpr (ALPHA) { if (alphaFn((int)(first + i), curInst, ux, uy)) return 1; }
+                else return 1;
+            }
+            cur = stk.pop();
+        }
+        else if (kind == PTB_K_INST)
+        {
+            curInst = (int)(cur & PTB_INST_INDEX_MASK);
+            const float4* ip = S.instTrav + (size_t)curInst * 4;
+            const float4 r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            const bool generic = fabsf(o.x) > 0.f && fabsf(o.y) > 0.f && fabsf(o.z) > 0.f;      // (d is nonzero and finite here, o finite unless NaN/inf: then the products below are not exact shortcuts)
+            if (PTB_FAST_INST && (cur & PTB_INST_TRANSLATION_ONLY) && generic && fabsf(o.x) < CUDART_INF_F && fabsf(o.y) < CUDART_INF_F && fabsf(o.z) < CUDART_INF_F)
+                ro = f3(xa(o.x, r3.x), xa(o.y, r3.y), xa(o.z, r3.z));         // see Trav::round: exact for rays without zero components
+            else
+            {
+                const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1);
+                ro = f3(xa(xa(xa(xm(o.x, r0.x), xm(o.y, r1.x)), xm(o.z, r2.x)), xm(1.0f, r3.x)),
+                        xa(xa(xa(xm(o.x, r0.y), xm(o.y, r1.y)), xm(o.z, r2.y)), xm(1.0f, r3.y)),
+                        xa(xa(xa(xm(o.x, r0.z), xm(o.y, r1.z)), xm(o.z, r2.z)), xm(1.0f, r3.z)));
+                rd = f3(xa(xa(xa(xm(d.x, r0.x), xm(d.y, r1.x)), xm(d.z, r2.x)), xm(0.0f, r3.x)),
+                        xa(xa(xa(xm(d.x, r0.y), xm(d.y, r1.y)), xm(d.z, r2.y)), xm(0.0f, r3.y)),
+                        xa(xa(xa(xm(d.x, r0.z), xm(d.y, r1.z)), xm(d.z, r2.z)), xm(0.0f, r3.z)));
+                if (!wideRayOk(rd)) return 2;                                  // degenerate direction in object space: the equivalence argument needs finite 1/d
+                inv = f3(xd(1.0f, rd.x), xd(1.0f, rd.y), xd(1.0f, rd.z));
+            }
+            stk.push(PTB_META_NONE);                                           // marker: back to the TLAS when it is popped
+            cur = __float_as_uint(r2.w);                                       // BLAS root in the wide hierarchy
+            inBlas = true;
+        }
+        else
+        {
+            if (!inBlas) return 0;
+            inBlas = false; ro = o; rd = d; inv = invW;
+            cur = stk.pop();
+        }
+    }
 }
 
 // ------------------------------------------------------------------ camera ray --------------------------------------

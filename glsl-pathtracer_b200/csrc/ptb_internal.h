@@ -45,16 +45,19 @@ struct DevScene
     const float4* inner;        // 4 float4 / canonical node index: child boxes + child metas (valid for internal nodes)
     const float4* tris;         // 3 float4 / leaf-ref slot: v0, e0, e1, vertIndices.x
     const float4* triShade;     // 4 float4 / leaf-ref slot: n0 n1 n2 (9 floats), (u,v) x 3 (ptbd_build_tri_shade)
-    const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {0, matID, 0, rootMeta} in .w
+    const float4* instTrav;     // 4 float4 / instance: rows of inverse(transform) (xyz) + {0, matID, wide rootMeta, rootMeta} in .w
     const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
     const float4* lightsPre;    // 8 float4 / light (see buildLightsPre in ptb_api.cpp)
     const float4* lightGroups;  // 3 float4 / group of consecutive lights (shared plane + padded bounds)
+    const float4* wide;         // 8 float4 / node of the 4-wide any-hit hierarchy (ptbd_build_wide); null = not available
+    uint32_t rootMetaWide;      // TLAS root in it
     int numLightGroups;
     uint32_t rootMeta;          // meta of the TLAS root
     int numNodes, topLevelIndex, numIndices, numVertices, numMaterials, numInstances, numLights;
     int numTextures, texW, texH, envW, envH;
     float envTotalSum;
-    int stackDepth;             // traversal stack entries needed (bottom sentinel + TLAS path + marker + BLAS path)
+    int stackDepth;             // traversal stack entries needed (bottom sentinel + TLAS path + marker + BLAS path) in the binary hierarchy
+    int stackDepthAny;          // ... by the any-hit kernels: max of the binary and the 4-wide hierarchy's bound
 };
 
 struct FrameParams
@@ -137,7 +140,8 @@ struct DevStats { unsigned long long pathSegments, shadowRays; };
 struct LaunchCfg
 {
     int numSMs; void* stream;
-    int traceBlocks;            // resident k_trace / k_shadow blocks per SM on this context's device (ptbk_configure_device)
+    int traceBlocks;            // resident k_trace blocks per SM on this context's device (ptbk_configure_device)
+    int shadowBlocks;           // same for k_shadow (its stack may be deeper: 4-wide hierarchy)
     int shadeBlocks[3];         // same for the three k_shade specialisations
     unsigned long long* launches;   // per-context count of kernel launches (may be null)
 };
@@ -161,4 +165,4 @@ void ptbk_trace_closest_batch(const LaunchCfg&, const DevScene&, const FramePara
 void ptbk_trace_any_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, const float* maxDist, long long n, int* out);
 void ptbk_bsdf_batch(const LaunchCfg&, const void* queries, long long n, void* results, int sample);
 void ptbk_camera_rays(const LaunchCfg&, const FrameParams&, const WaveParams&, float* outRays);
-int  ptbk_configure_device(const DevScene&, int* traceBlocks, int shadeBlocks[3]);   // per-device attributes; returns a cudaError_t value
+int  ptbk_configure_device(const DevScene&, int* traceBlocks, int* shadowBlocks, int shadeBlocks[3]);   // per-device attributes; returns a cudaError_t value

@@ -886,8 +886,10 @@ __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams&
             bool occluded = lights && anyLights(S, o, d, maxDist);
             if (!occluded)
             {
-                HitRec h;
-                occluded = traverse<true, ALPHA, CULL>(S, o, d, maxDist, stk, h, alphaFn);
+                int r = 2;
+                if (S.wide && wideRayOk(d)) r = traverseWideAny<ALPHA, CULL>(S, o, d, maxDist, stk, alphaFn);       // same boolean, fewer and wider steps
+                if (r == 2) { HitRec h; occluded = traverse<true, ALPHA, CULL>(S, o, d, maxDist, stk, h, alphaFn); }
+                else occluded = r != 0;
             }
             if (!occluded)
             {
@@ -1035,9 +1037,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_any_batch(DevScene S, FramePa
         const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
         bool occ = OPT(F, O_LIGHTS) && anyLights(S, o, d, maxDist[i]);
         if (!occ)
-        {
-            HitRec h;
-            occ = F.cullBoxes ? traverse<true, false, true>(S, o, d, maxDist[i], stk, h, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, h, NoAlpha());
+        {   // the production any-hit path of k_shadow
+            int r = 2;
+            if (S.wide && wideRayOk(d)) r = F.cullBoxes ? traverseWideAny<false, true>(S, o, d, maxDist[i], stk, NoAlpha()) : traverseWideAny<false, false>(S, o, d, maxDist[i], stk, NoAlpha());
+            if (r == 2) { HitRec h; occ = F.cullBoxes ? traverse<true, false, true>(S, o, d, maxDist[i], stk, h, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, h, NoAlpha()); }
+            else occ = r != 0;
         }
         out[i] = occ ? 1 : 0;
     }
@@ -1080,23 +1084,27 @@ __global__ void k_camera_rays(FrameParams F, WaveParams W, float* out)
 // ------------------------------------------------------------------ launchers -----------------------------------
 static inline cudaStream_t st(const LaunchCfg& c) { return (cudaStream_t)c.stream; }
 static inline size_t stackBytes(const DevScene& S, int threads) { return (size_t)S.stackDepth * threads * sizeof(uint32_t); }
+static inline size_t stackBytesAny(const DevScene& S, int threads) { return (size_t)S.stackDepthAny * threads * sizeof(uint32_t); }
 
 // Per-device kernel attributes for the current device: dynamic shared memory of the stack-carrying kernels (the default limit is 48 KB) and the
 // resident blocks per SM the persistent grids are sized with.  Called by the host side after cudaSetDevice whenever a context is created
 // or its stack depth changes; the results live in the context, not in process-wide statics.
-int ptbk_configure_device(const DevScene& S, int* traceBlocks, int shadeBlocks[3])
+int ptbk_configure_device(const DevScene& S, int* traceBlocks, int* shadowBlocks, int shadeBlocks[3])
 {
-    const size_t smem = stackBytes(S, TRACE_THREADS);
+    const size_t smem = stackBytes(S, TRACE_THREADS), smemAny = stackBytesAny(S, TRACE_THREADS);
     cudaError_t e = cudaSuccess;
     auto upd = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     upd(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_trace_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    upd(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemAny));
     upd(cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    upd(cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upd(cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemAny));
     int nb = 0;
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace, TRACE_THREADS, smem));
     *traceBlocks = nb > 0 ? nb : 1;
+    nb = 0;
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shadow, TRACE_THREADS, smemAny));
+    *shadowBlocks = nb > 0 ? nb : 1;
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[0], k_shade<0, 4>, SHADE_THREADS, 0));
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[1], k_shade<1, 5>, SHADE_THREADS, 0));
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[2], k_shade<2, 4>, SHADE_THREADS, 0));
@@ -1155,8 +1163,8 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
 void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats)
 {
-    const int bps = c.traceBlocks;
-    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
+    const int bps = c.shadowBlocks;
+    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytesAny(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
     COUNT_LAUNCH(c, 1);
 }
 
@@ -1181,8 +1189,8 @@ void ptbk_trace_closest_batch(const LaunchCfg& c, const DevScene& S, const Frame
 }
 void ptbk_trace_any_batch(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const float* rays, const float* maxDist, long long n, int* out)
 {
-    const int bps = c.traceBlocks;
-    k_any_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, rays, maxDist, n, out);
+    const int bps = c.shadowBlocks;
+    k_any_batch<<<c.numSMs * bps, TRACE_THREADS, stackBytesAny(S, TRACE_THREADS), st(c)>>>(S, F, rays, maxDist, n, out);
     COUNT_LAUNCH(c, 1);
 }
 void ptbk_bsdf_batch(const LaunchCfg& c, const void* queries, long long n, void* results, int sample)

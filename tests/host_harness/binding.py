@@ -19,7 +19,8 @@ def lib():
         L.hh_destroy.argtypes = [vp]
         L.hh_stack_depth.argtypes = [vp]
         L.hh_trace_closest.argtypes = [vp, vp, C.c_longlong, i32, i32, vp]
-        L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, vp]
+        L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, vp]
+        L.hh_wide_nodes.argtypes = [vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
         _LIB = L
     return _LIB
@@ -52,12 +53,18 @@ class HostTrav:
         lib().hh_trace_closest(self.h, rays.ctypes.data, len(rays), int(self.lights and (not hide or depth > 0)), int(self.cull), out.ctypes.data)
         return out
 
-    def trace_any(self, rays, max_dist):
+    def trace_any(self, rays, max_dist, wide=True):
+        """wide=True: the production any-hit path (4-wide hierarchy where admissible); self.fallbacks = rays it handed back to the binary traversal"""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         md = np.ascontiguousarray(np.broadcast_to(np.asarray(max_dist, np.float32), (len(rays),)))
         out = np.zeros(len(rays), np.int32)
-        lib().hh_trace_any(self.h, rays.ctypes.data, md.ctypes.data, len(rays), int(self.lights), int(self.cull), out.ctypes.data)
+        fb = C.c_longlong(0)
+        lib().hh_trace_any(self.h, rays.ctypes.data, md.ctypes.data, len(rays), int(self.lights), int(self.cull), int(wide), out.ctypes.data, C.byref(fb))
+        self.fallbacks = fb.value
         return out
+
+    def wide_nodes(self):
+        return lib().hh_wide_nodes(self.h)
 
     def camera_rays(self, sample=1, tables=True):
         ro, cam = self.scene.renderOptions, self.scene.camera

@@ -12,8 +12,15 @@ using namespace ptb;
 struct HHScene
 {
     DevScene S{};
-    PtbDerivedHierarchy dh; PtbDerivedLights dl; std::vector<float4> tris;
+    PtbDerivedHierarchy dh; PtbDerivedLights dl; PtbDerivedWide dw; std::vector<float4> tris;
     std::vector<float> nodes, transforms; std::vector<int> vertIndices; std::vector<float4> verticesUVX;
+};
+struct BigStack      // thread-local stack sized for the wide hierarchy's bound (96)
+{
+    uint32_t a[128]; int sp = 0;
+    void reset() { sp = 0; }
+    void push(uint32_t v) { a[sp++] = v; }
+    uint32_t pop() { return a[--sp]; }
 };
 struct HHHit { float t; int kind, instance, matID, primSlot, triIDx; float bary[3]; int lightIdx; };
 
@@ -30,17 +37,22 @@ HHScene* hh_create(const float* nodes, int numNodes, int topLevelIndex, const in
     if (!rc) rc = ptbd_derive_hierarchy(nodes, numNodes, topLevelIndex, numIndices, numMaterials, transforms, numInstances, 0, numNodes, h->dh, err);
     if (rc) { if (errOut) { strncpy(errOut, err.c_str(), errCap - 1); errOut[errCap - 1] = 0; } delete h; return nullptr; }
     ptbd_build_lights(lights, numLights, h->dl);
+    ptbd_build_wide(nodes, numNodes, topLevelIndex, numIndices, numInstances, h->dh.transOnly, h->dw);
+    if (h->dw.ok) for (size_t k = 0; k < h->dw.instRootMeta.size(); k++) h->dh.instTrav[k * 4 + 2].w = __uint_as_float(h->dw.instRootMeta[k]);
     DevScene& S = h->S;
     S.nodes = h->nodes.data(); S.vertIndices = h->vertIndices.data();
     S.inner = h->dh.inner.data(); S.tris = h->tris.data(); S.instTrav = h->dh.instTrav.data(); S.instShade = h->dh.instShade.data();
     S.lightsPre = h->dl.lightsPre.data(); S.lightGroups = h->dl.lightGroups.data(); S.numLightGroups = h->dl.numGroups;
     S.rootMeta = h->dh.rootMeta; S.stackDepth = h->dh.stackDepth;
+    S.wide = h->dw.ok ? h->dw.wide.data() : nullptr; S.rootMetaWide = h->dw.rootMeta;
+    S.stackDepthAny = (h->dw.ok && h->dw.stackDepth > S.stackDepth) ? h->dw.stackDepth : S.stackDepth;
     S.numNodes = numNodes; S.topLevelIndex = topLevelIndex; S.numIndices = numIndices; S.numVertices = numVertices; S.numMaterials = numMaterials;
     S.numInstances = numInstances; S.numLights = numLights;
     return h;
 }
 void hh_destroy(HHScene* h) { delete h; }
-int hh_stack_depth(HHScene* h) { return h->S.stackDepth; }
+int hh_stack_depth(HHScene* h) { return h->S.stackDepthAny; }
+int hh_wide_nodes(HHScene* h) { return h->dw.ok ? (int)(h->dw.wide.size() / 8) : -1; }
 
 // k_trace_batch of ptb_kernels.cu, one ray after the other
 void hh_trace_closest(HHScene* h, const float* rays, long long n, int lights, int cull, HHHit* out)
@@ -70,22 +82,32 @@ void hh_trace_closest(HHScene* h, const float* rays, long long n, int lights, in
     }
 }
 
-void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long n, int lights, int cull, int* out)
+// wide: 1 = the production path of k_shadow (4-wide hierarchy where admissible, binary otherwise); 0 = binary only.  fallbacks counts the rays the wide
+// path handed back to the binary traversal
+void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long n, int lights, int cull, int wide, int* out, long long* fallbacks)
 {
     const DevScene& S = h->S;
-#pragma omp parallel for schedule(dynamic, 4096)
+    long long fb = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fb)
     for (long long i = 0; i < n; i++)
     {
-        LocalStack stk;
+        BigStack stk;
         const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
         bool occ = lights && anyLights(S, o, d, maxDist[i]);
         if (!occ)
         {
-            HitRec hr;
-            occ = cull ? traverse<true, false, true>(S, o, d, maxDist[i], stk, hr, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, hr, NoAlpha());
+            int r = 2;
+            if (wide && S.wide)
+            {
+                if (wideRayOk(d)) r = cull ? traverseWideAny<false, true>(S, o, d, maxDist[i], stk, NoAlpha()) : traverseWideAny<false, false>(S, o, d, maxDist[i], stk, NoAlpha());
+                if (r == 2) fb++;
+            }
+            if (r == 2) { HitRec hr; occ = cull ? traverse<true, false, true>(S, o, d, maxDist[i], stk, hr, NoAlpha()) : traverse<true, false, false>(S, o, d, maxDist[i], stk, hr, NoAlpha()); }
+            else occ = r != 0;
         }
         out[i] = occ ? 1 : 0;
     }
+    if (fallbacks) *fallbacks = fb;
 }
 
 // uniforms as refreshFrameParams (ptb_api.cpp) derives them from PtbOptions / PtbCamera

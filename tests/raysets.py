@@ -51,3 +51,21 @@ def assert_hits_equal(a, b):
     assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32)), "t not bit-identical"
     hit = a["kind"] == 1
     assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32)), "barycentrics not bit-identical"
+
+
+def boundary_rays(sc, n, seed=13):
+    """Adversarial rays for the slab test: origins exactly ON planes of node boxes (world space), a third of them exactly axis-parallel inside such a
+    plane (0 * inf = NaN in AABBIntersect), a third with one denormal-small direction component (1/d overflows to inf), the rest generic."""
+    rng = np.random.default_rng(seed)
+    nodes = np.ascontiguousarray(sc.nodes, np.float32).reshape(-1, 9)
+    pick = nodes[rng.integers(0, len(nodes), n)]
+    lo, hi = pick[:, 0:3], pick[:, 3:6]
+    o = (lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    ax = rng.integers(0, 3, n); side = rng.integers(0, 2, n)
+    o[np.arange(n), ax] = np.where(side == 0, lo[np.arange(n), ax], hi[np.arange(n), ax])       # exactly on a box plane
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 3
+    d[np.arange(k), ax[:k]] = np.float32(0.0) * rng.choice([-1.0, 1.0], k).astype(np.float32)   # in-plane, +-0 component
+    d[np.arange(k, 2 * k), ax[k:2 * k]] = (np.float32(1e-41) * rng.choice([-1.0, 1.0], k)).astype(np.float32)   # denormal component
+    return np.concatenate([o, d.astype(np.float32)], axis=1)

@@ -6,7 +6,7 @@ changes where no GPU exists.  The G1 gate proper (tests/test_gpu_trace.py) runs 
 import numpy as np
 import pytest
 from conftest import scene_at
-from raysets import random_rays, bounce_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
+from raysets import random_rays, bounce_rays, boundary_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
 from host_harness.binding import HostTrav
 
 SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
@@ -33,13 +33,21 @@ def test_host_compiled_traversal_equals_oracle(name, oracle_mod):
     b = bounce_rays(rays, faithful)
     ht.set_cull(False); assert_hits_equal(ht.trace_closest(b, 1), orc.trace_closest(b, 1))
     ht.set_cull(True); assert_hits_equal(ht.trace_closest(b, 1), orc_c.trace_closest(b, 1))
-    # any-hit: occlusion is the same boolean in both variants
-    ar = np.concatenate([random_rays(sc, 30_000, 5), b[:20_000]])
+    # closest hit on adversarial rays (origins exactly on node-box planes, in-plane axis-parallel and denormal directions)
+    adv = boundary_rays(sc, 30_000)
+    ht.set_cull(False); assert_hits_equal(ht.trace_closest(adv, 1), orc.trace_closest(adv, 1))
+    ht.set_cull(True); assert_hits_equal(ht.trace_closest(adv, 1), orc_c.trace_closest(adv, 1))
+    # any-hit: occlusion is the same boolean in both traversal variants AND over the 4-wide hierarchy (the production path of k_shadow)
+    ar = np.concatenate([random_rays(sc, 30_000, 5), b[:20_000], adv])
     md = any_hit_distances(sc, len(ar))
     want = orc.trace_any(ar, md)
+    assert ht.wide_nodes() > 0 or len(sc.nodes) < 4, "the wide hierarchy must be available for every fixture scene"
     for cull in (False, True):
         ht.set_cull(cull)
-        got = ht.trace_any(ar, md)
-        assert np.array_equal(got, want), f"cull={cull}: {np.count_nonzero(got != want)} occlusion mismatches"
-    assert ht.stack_depth() <= 64
+        for wide in (False, True):
+            got = ht.trace_any(ar, md, wide=wide)
+            assert np.array_equal(got, want), f"cull={cull} wide={wide}: {np.count_nonzero(got != want)} occlusion mismatches"
+            if wide:
+                assert ht.fallbacks < 0.6 * len(ar)      # the generic rays really went through the wide hierarchy
+    assert ht.stack_depth() <= 96
     ht.close(); orc.close(); orc_c.close()
