@@ -156,6 +156,7 @@ int deriveHierarchy(PtbCtx* c, int begin, int end, bool all)
     CK(c->instShade.upload(dh.instShade.data(), dh.instShade.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));   // staging vectors die at scope exit
     c->S.stackDepth = dh.stackDepth; c->S.stackDepthAny = dw.ok ? std::max(dh.stackDepth, dw.stackDepth) : dh.stackDepth; c->S.rootMeta = dh.rootMeta;
+    if (const char* e = getenv("PTB_ANY_STACK_MIN")) c->S.stackDepthAny = std::max(c->S.stackDepthAny, atoi(e));      // measurement aid: shared-memory footprint of k_shadow
     c->S.wide = dw.ok ? c->wide.p : nullptr; c->S.rootMetaWide = dw.rootMeta;
     c->S.inner = c->inner.p; c->S.instTrav = c->instTrav.p; c->S.instShade = c->instShade.p;
     (void)all;
@@ -342,13 +343,14 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
             ptbk_sort_tile_local(L, nullptr, c->slotKeys.p, ci + CTR_NPATHS, 8, c->slotSorted.p, 7, W.nSlots);
             traceQueue = c->slotSorted.p;
         }
+        uint32_t* globalHist = (c->sortMode == 3 && numKeys <= 4096) ? nullptr : c->sortHist.p;     // key histogram over the whole queue: global sorter only
         mark(c, KIND_TRACE);
         if (it == 0 && fusedCamera)
-            ptbk_trace_primary(L, c->S, F, W, P, ctr, lightsFromDepth, c->dstats.p, sortThis ? c->sortKeys.p : nullptr, c->sortHist.p,
+            ptbk_trace_primary(L, c->S, F, W, P, ctr, lightsFromDepth, c->dstats.p, sortThis ? c->sortKeys.p : nullptr, globalHist,
                                (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys);
         else
             ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
-                       sortThis ? c->sortKeys.p : nullptr, c->sortHist.p, nOv, (uint32_t)numKeys);
+                       sortThis ? c->sortKeys.p : nullptr, globalHist, nOv, (uint32_t)numKeys);
         const uint32_t* shadeQueue = traceQueue;
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)

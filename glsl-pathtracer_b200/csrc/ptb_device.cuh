@@ -33,6 +33,9 @@
 #ifndef PTB_FAST_INST
 #define PTB_FAST_INST 1         // short instance entry for translation-only transforms
 #endif
+#ifndef PTB_CHEAP_MATH
+#define PTB_CHEAP_MATH 1        // shading math (never hit-deciding): bare MUFU reciprocal / rsqrt / sqrt without the range fix-ups of div.approx & co
+#endif
 
 namespace ptb {
 
@@ -45,7 +48,19 @@ __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x 
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 // Shading-math division: div.approx (MUFU.RCP + FMUL, 2 ulp) instead of the ~8-instruction full-range sequence; operands here are
 // BSDF terms far from the 2^126 range limit.  Hit-deciding code never uses these (it uses the x* exact intrinsics below).
+#if PTB_CHEAP_MATH && !defined(PTB_HOST_HARNESS)
+// One MUFU each (max error 1 ulp, denormals flushed): the operands here are BSDF / pdf terms far from the ends of the exponent range, so the scaling
+// and special-case code div.approx.f32, rsqrtf() and sqrtf() carry around the same MUFU instruction (4-5 extra instructions each, ~100 divisions in
+// DisneyEval/Sample) buys nothing.  G2 (1e-4 relative) is unaffected: measured in tests/test_gpu_render.py::test_bsdf_eval_matches_oracle.
+__device__ __forceinline__ float rcpApprox(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float rsqrtApprox(float b) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float sqrtApprox(float b) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * rcpApprox(b); }
+#else
+__device__ __forceinline__ float rsqrtApprox(float b) { return rsqrtf(b); }
+__device__ __forceinline__ float sqrtApprox(float b) { return sqrtf(b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+#endif
 __device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(fdiv(a.x, b.x), fdiv(a.y, b.y), fdiv(a.z, b.z)); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
@@ -58,8 +73,8 @@ __device__ __forceinline__ float3& operator*=(float3& a, float s) { a = a * s; r
 __device__ __forceinline__ float3& operator/=(float3& a, float s) { a = a / s; return a; }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ float3 normalize(float3 a) { const float r = rsqrtf(dot(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
+__device__ __forceinline__ float length(float3 a) { return sqrtApprox(dot(a, a)); }
+__device__ __forceinline__ float3 normalize(float3 a) { const float r = rsqrtApprox(dot(a, a)); return f3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float3 mix(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -71,7 +86,7 @@ __device__ __forceinline__ float3 refract(float3 I, float3 N, float eta)
     float d = dot(N, I);
     float k = 1.0f - eta * eta * (1.0f - d * d);
     if (k < 0.0f) return f3(0.0f);
-    return I * eta - N * (eta * d + sqrtf(k));
+    return I * eta - N * (eta * d + sqrtApprox(k));
 }
 __device__ __forceinline__ float Luminance(float3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; }   // globals.glsl:173
 
@@ -708,8 +723,8 @@ __device__ __forceinline__ float3 SampleGTR1(float rgh, float r1, float r2)   //
     float a = fmaxf(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * PTB_TWO_PI;
-    float cosTheta = sqrtf(fdiv(1.0f - powf(a2, 1.0f - r2), 1.0f - a2));
-    float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    float cosTheta = sqrtApprox(fdiv(1.0f - powf(a2, 1.0f - r2), 1.0f - a2));
+    float sinTheta = clampf(sqrtApprox(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
     return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
@@ -717,16 +732,16 @@ __device__ __forceinline__ float3 SampleGGXVNDF(float3 V, float ax, float ay, fl
 {
     float3 Vh = normalize(f3(ax * V.x, ay * V.y, V.z));
     float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
-    float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * rsqrtf(lensq) : f3(1, 0, 0);
+    float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * rsqrtApprox(lensq) : f3(1, 0, 0);
     float3 T2 = cross(Vh, T1);
-    float r = sqrtf(r1);
+    float r = sqrtApprox(r1);
     float phi = 2.0f * PTB_PI * r2;
     float sp, cp; sincosf(phi, &sp, &cp);
     float t1 = r * cp;
     float t2 = r * sp;
     float s = 0.5f * (1.0f + Vh.z);
-    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
-    float3 Nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+    t2 = (1.0f - s) * sqrtApprox(1.0f - t1 * t1) + s * t2;
+    float3 Nh = t1 * T1 + t2 * T2 + sqrtApprox(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
     return normalize(f3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
 }
 __device__ __forceinline__ float GTR2Aniso(float NDotH, float HDotX, float HDotY, float ax, float ay)   // :90-96
@@ -740,14 +755,14 @@ __device__ __forceinline__ float SmithG(float NDotV, float alphaG)   // :109-114
 {
     float a = alphaG * alphaG;
     float b = NDotV * NDotV;
-    return fdiv(2.0f * NDotV, NDotV + sqrtf(a + b - a * b));
+    return fdiv(2.0f * NDotV, NDotV + sqrtApprox(a + b - a * b));
 }
 __device__ __forceinline__ float SmithGAniso(float NDotV, float VDotX, float VDotY, float ax, float ay)   // :116-122
 {
     float a = VDotX * ax;
     float b = VDotY * ay;
     float c = NDotV;
-    return fdiv(2.0f * NDotV, NDotV + sqrtf(a * a + b * b + c * c));
+    return fdiv(2.0f * NDotV, NDotV + sqrtApprox(a * a + b * b + c * c));
 }
 __device__ __forceinline__ float SchlickWeight(float u)   // :124-129
 {
@@ -759,7 +774,7 @@ __device__ __forceinline__ float DielectricFresnel(float cosThetaI, float eta)  
 {
     float sinThetaTSq = eta * eta * (1.0f - cosThetaI * cosThetaI);
     if (sinThetaTSq > 1.0f) return 1.0f;
-    float cosThetaT = sqrtf(fmaxf(1.0f - sinThetaTSq, 0.0f));
+    float cosThetaT = sqrtApprox(fmaxf(1.0f - sinThetaTSq, 0.0f));
     float rs = fdiv(eta * cosThetaT - cosThetaI, eta * cosThetaT + cosThetaI);
     float rp = fdiv(eta * cosThetaI - cosThetaT, eta * cosThetaI + cosThetaT);
     return 0.5f * (rs * rs + rp * rp);
@@ -767,17 +782,17 @@ __device__ __forceinline__ float DielectricFresnel(float cosThetaI, float eta)  
 __device__ __forceinline__ float3 CosineSampleHemisphere(float r1, float r2)   // :147-156
 {
     float3 dir;
-    float r = sqrtf(r1);
+    float r = sqrtApprox(r1);
     float phi = PTB_TWO_PI * r2;
     float sp, cp; sincosf(phi, &sp, &cp);
     dir.x = r * cp;
     dir.y = r * sp;
-    dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+    dir.z = sqrtApprox(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
     return dir;
 }
 __device__ __forceinline__ float3 UniformSampleHemisphere(float r1, float r2)   // :158-163
 {
-    float r = sqrtf(fmaxf(0.0f, 1.0f - r1 * r1));
+    float r = sqrtApprox(fmaxf(0.0f, 1.0f - r1 * r1));
     float phi = PTB_TWO_PI * r2;
     float sp, cp; sincosf(phi, &sp, &cp);
     return f3(r * cp, r * sp, r1);
@@ -803,7 +818,7 @@ __device__ __forceinline__ float3 SampleHG(float3 V, float g, float r1, float r2
         cosTheta = -(1 + g * g - sqrTerm * sqrTerm) / (2 * g);
     }
     float phi = r1 * PTB_TWO_PI;
-    float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    float sinTheta = clampf(sqrtApprox(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
     float3 v1, v2;
     Onb(V, v1, v2);
@@ -812,7 +827,7 @@ __device__ __forceinline__ float3 SampleHG(float3 V, float g, float r1, float r2
 __device__ __forceinline__ float PhaseHG(float cosTheta, float g)   // :272-276
 {
     float denom = 1 + g * g + 2 * g * cosTheta;
-    return PTB_INV_4_PI * (1 - g * g) / (denom * sqrtf(denom));
+    return PTB_INV_4_PI * (1 - g * g) / (denom * sqrtApprox(denom));
 }
 
 // ------------------------------------------------------------------ material / surface state --------------------
@@ -999,7 +1014,8 @@ __device__ __forceinline__ float3 DisneyEvalLocal(const Material& mat, float eta
                 float eta2 = eta * eta;
                 float jacobian = fdiv(fabsf(LDotH), denom);
                 tmpPdf = fdiv(G1 * fmaxf(0.0f, VDotH2) * D * jacobian, V.z);
-                fr = vpow(mat.baseColor, 0.5f) * (f3(1.0f) - f3(F)) * fdiv(D * G2 * fabsf(VDotH2) * jacobian * eta2, fabsf(L.z * V.z));
+                // pow(mat.baseColor, vec3(0.5)) of disney.glsl:122 as a square root
+                fr = f3(sqrtApprox(mat.baseColor.x), sqrtApprox(mat.baseColor.y), sqrtApprox(mat.baseColor.z)) * (f3(1.0f) - f3(F)) * fdiv(D * G2 * fabsf(VDotH2) * jacobian * eta2, fabsf(L.z * V.z));
             }
             f += fr * p.glassWt;
             pdf += tmpPdf * p.glassPr * (1.0f - F);
@@ -1121,7 +1137,7 @@ __device__ __forceinline__ void materialFromRow(const float4* P, Material& mat, 
 }
 __device__ __forceinline__ void materialFinish(Material& mat)
 {
-    float aspect = sqrtf(1.0f - mat.anisotropic * 0.9f);
+    float aspect = sqrtApprox(1.0f - mat.anisotropic * 0.9f);
     mat.ax = fmaxf(0.001f, fdiv(mat.roughness, aspect));
     mat.ay = fmaxf(0.001f, mat.roughness * aspect);
 }

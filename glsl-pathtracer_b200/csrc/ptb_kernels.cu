@@ -28,6 +28,9 @@ enum {
 constexpr int TRACE_THREADS = 256;
 constexpr int TRACE_MIN_BLOCKS = 5;     // 48 registers: measured 772 spp/s vs 720 (3 blocks, 72 regs), 767 (4), 753 (6)
 constexpr int SHADE_THREADS = 128;
+#ifndef PTB_SHADE_LATER_BLOCKS
+#define PTB_SHADE_LATER_BLOCKS 4      // resident k_shade<0> blocks per SM for the bounces after the first (latency-bound: scattered, material-sorted state)
+#endif
 
 // ------------------------------------------------------------------ slot <-> pixel mapping ----------------------
 // Path slots of one sample pass are ordered in 8x4 pixel blocks so that a warp's primary rays are spatially coherent.
@@ -164,8 +167,11 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             {   // histogram of shading keys, one atomic per distinct key per (converged part of the) warp
                 const uint32_t key = shadeKey(S, hi);
                 keys[i] = key;
-                const unsigned peers = __match_any_sync(__activemask(), key);
-                if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+                if (hist)
+                {   // global counting sort only (PTB_SORT=1/2); the tile-local sorter builds its own histograms
+                    const unsigned peers = __match_any_sync(__activemask(), key);
+                    if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+                }
             }
         }
     }
@@ -1156,6 +1162,8 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
     const int* bps = c.shadeBlocks;
     if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
+    else if (PTB_SHADE_LATER_BLOCKS != 4 && !firstIter)
+        k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
     COUNT_LAUNCH(c, 1);
 }
