@@ -78,6 +78,7 @@ struct PtbCtx
     DevBuf<float> nodes, lights, envImg, envCdf;
     DevBuf<int> vertIndices;
     DevBuf<float4> triShade, wide;
+    DevBuf<uint32_t> lightGrid;
     int wideAny = 1;           // 1: shadow rays use the 4-wide any-hit hierarchy where it is provably equivalent (PTB_WIDE_ANY)
     DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
@@ -225,8 +226,9 @@ int buildLightsPre(PtbCtx* c, const float* lights, int n)
     ptbd_build_lights(lights, n, dl);
     CK(c->lightsPre.upload(dl.lightsPre.data(), dl.lightsPre.size(), c->stream));
     CK(c->lightGroups.upload(dl.lightGroups.data(), dl.lightGroups.size(), c->stream));
+    CK(c->lightGrid.upload(dl.lightGrid.data(), dl.lightGrid.size(), c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->S.lightsPre = c->lightsPre.p; c->S.lightGroups = c->lightGroups.p; c->S.numLightGroups = dl.numGroups;
+    c->S.lightsPre = c->lightsPre.p; c->S.lightGroups = c->lightGroups.p; c->S.lightGrid = c->lightGrid.p; c->S.numLightGroups = dl.numGroups;
     return PTB_OK;
 }
 
@@ -507,7 +509,7 @@ int ptb_destroy(PtbCtx* c)
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release(); c->wide.release();
-    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
+    c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->lightGrid.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
     c->sortKeys.release(); c->sortedQueue.release(); c->sortHist.release(); c->slotKeys.release(); c->slotSorted.release();

@@ -220,7 +220,7 @@ void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out)
         lp[i * 8 + 7] = make_float4(0, 0, 0, 0);
     }
     // groups of consecutive quads on one plane (+ singleton groups for everything else), with padded bounds of the member quads
-    std::vector<float4>& groups = out.lightGroups; groups.clear();
+    std::vector<float4>& groups = out.lightGroups; groups.clear(); out.lightGrid.clear();
     for (int i = 0; i < n;)
     {
         int j = i + 1;
@@ -238,11 +238,42 @@ void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out)
         }
         double ext = quad ? std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]}) : 0.0;
         double pad = 1e-4 * (1.0 + mag + ext);
-        groups.push_back(make_float4(u2f((uint32_t)i), u2f((uint32_t)(j - i)), u2f(quad ? 0u : 1u), 0.f));
+        // Cell grid over the group's padded box in the plane's two widest axes (groups of 4..32 quads): cell -> bit mask of the quads whose own padded box
+        // touches the cell (+-1 cell for the rounding of the device's cell index).  A plane hit inside a cell can only pass the inside test of those
+        // quads (same argument as for the group box), so the others are skipped without changing the result; bit order = index order.
+        uint32_t kindWord = quad ? 0u : 1u; float gridOff = 0.f, invA = 0.f, invB = 0.f;
+        const int cnt = j - i;
+        if (quad && cnt >= 4 && cnt <= 32)
+        {
+            const float bmin[3] = {(float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad)}, bmax[3] = {(float)(hi[0] + pad), (float)(hi[1] + pad), (float)(hi[2] + pad)};
+            int ax[3] = {0, 1, 2};
+            std::sort(ax, ax + 3, [&](int a, int b) { return (hi[a] - lo[a]) > (hi[b] - lo[b]); });
+            const int A = ax[0], B = ax[1];
+            const float ia = (float)PTB_LIGHT_GRID / (bmax[A] - bmin[A]), ib = (float)PTB_LIGHT_GRID / (bmax[B] - bmin[B]);
+            if (std::isfinite(ia) && std::isfinite(ib) && ia > 0.f && ib > 0.f)
+            {
+                const size_t off = out.lightGrid.size();
+                out.lightGrid.resize(off + PTB_LIGHT_GRID * PTB_LIGHT_GRID, 0u);
+                for (int k = i; k < j; k++)
+                {
+                    const float* p = lights + (size_t)k * 15;
+                    double l2[3] = {1e300, 1e300, 1e300}, h2[3] = {-1e300, -1e300, -1e300};
+                    for (int cu = 0; cu < 2; cu++) for (int cv = 0; cv < 2; cv++) for (int a = 0; a < 3; a++)
+                    { double v = (double)p[a] + cu * (double)p[6 + a] + cv * (double)p[9 + a]; l2[a] = std::min(l2[a], v); h2[a] = std::max(h2[a], v); }
+                    auto cell = [&](double v, int axis, float inv) { return (int)std::floor((v - (double)bmin[axis]) * (double)inv); };
+                    const int a0 = std::max(0, cell(l2[A] - pad, A, ia) - 1), a1 = std::min(PTB_LIGHT_GRID - 1, cell(h2[A] + pad, A, ia) + 1);
+                    const int b0 = std::max(0, cell(l2[B] - pad, B, ib) - 1), b1 = std::min(PTB_LIGHT_GRID - 1, cell(h2[B] + pad, B, ib) + 1);
+                    for (int cb = b0; cb <= b1; cb++) for (int ca = a0; ca <= a1; ca++) out.lightGrid[off + (size_t)cb * PTB_LIGHT_GRID + ca] |= 1u << (k - i);
+                }
+                kindWord = 2u | ((uint32_t)A << 4) | ((uint32_t)B << 8);
+                gridOff = u2f((uint32_t)off); invA = ia; invB = ib;
+            }
+        }
+        groups.push_back(make_float4(u2f((uint32_t)i), u2f((uint32_t)cnt), u2f(kindWord), gridOff));
         if (quad)
         {
-            groups.push_back(make_float4((float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad), 0.f));
-            groups.push_back(make_float4((float)(hi[0] + pad), (float)(hi[1] + pad), (float)(hi[2] + pad), 0.f));
+            groups.push_back(make_float4((float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad), invA));
+            groups.push_back(make_float4((float)(hi[0] + pad), (float)(hi[1] + pad), (float)(hi[2] + pad), invB));
         }
         else { groups.push_back(make_float4(0, 0, 0, 0)); groups.push_back(make_float4(0, 0, 0, 0)); }
         i = j;

@@ -15,7 +15,7 @@ struct PtbDerivedHierarchy
     uint32_t rootMeta = PTB_META_NONE;
     int stackDepth = 4;
 };
-struct PtbDerivedLights { std::vector<float4> lightsPre, lightGroups; int numGroups = 0; };
+struct PtbDerivedLights { std::vector<float4> lightsPre, lightGroups; std::vector<uint32_t> lightGrid; int numGroups = 0; };
 
 // status codes: 0 ok, 1 invalid argument, 4 unsupported (same values as PtbStatus)
 int ptbd_derive_hierarchy(const float* nodes, int numNodes, int topLevelIndex, int numIndices, int numMaterials, const float* transforms, int numInstances,

@@ -217,6 +217,18 @@ __device__ __forceinline__ bool outsideBox(float3 p, float4 bmin, float4 bmax)
 {
     return !(p.x >= bmin.x && p.x <= bmax.x && p.y >= bmin.y && p.y <= bmax.y && p.z >= bmin.z && p.z <= bmax.z);
 }
+// Member mask of the grid cell that holds plane hit p (p lies inside the group's padded box [bmin, bmax]); gk = group word (bit 1 gridded, bits 4-5 / 8-9 the two
+// grid axes), gridOff = bits(offset into S.lightGrid), bmin.w / bmax.w = cells per unit length along the two axes.
+__device__ __forceinline__ uint32_t lightGridMask(const DevScene& S, uint32_t gk, float gridOff, float4 bmin, float4 bmax, float3 p)
+{
+    const int A = (int)((gk >> 4) & 3u), B = (int)((gk >> 8) & 3u);
+    const float pa = A == 0 ? p.x : (A == 1 ? p.y : p.z), pb = B == 0 ? p.x : (B == 1 ? p.y : p.z);
+    const float la = A == 0 ? bmin.x : (A == 1 ? bmin.y : bmin.z), lb = B == 0 ? bmin.x : (B == 1 ? bmin.y : bmin.z);
+    int ia = (int)((pa - la) * bmin.w), ib = (int)((pb - lb) * bmax.w);
+    ia = ia < 0 ? 0 : (ia > PTB_LIGHT_GRID - 1 ? PTB_LIGHT_GRID - 1 : ia);
+    ib = ib < 0 ? 0 : (ib > PTB_LIGHT_GRID - 1 ? PTB_LIGHT_GRID - 1 : ib);
+    return __ldg(S.lightGrid + __float_as_uint(gridOff) + (uint32_t)(ib * PTB_LIGHT_GRID + ia));
+}
 // Light loop of ClosestHit (closest_hit.glsl:28-86): nearest light, first index wins ties (strict <).
 __device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float3 d, float& t, int& light)
 {
@@ -226,14 +238,28 @@ __device__ __forceinline__ void closestLights(const DevScene& S, float3 o, float
         const float4 g0 = __ldg(gp);
         const int first = __float_as_int(g0.x), count = __float_as_int(g0.y);
         const float4* p = S.lightsPre + (size_t)first * 8;
-        if (__float_as_int(g0.z) == 0)
+        const uint32_t gk = __float_as_uint(g0.z);
+        if ((gk & 1u) == 0u)
         {
             const float4 e = __ldg(p + 4);
             PlaneHit ph;
             planeEval(f3(e), e.w, o, d, ph);
             if (ph.dt > 0.f) continue;                       // hide backfacing quad light (closest_hit.glsl:50)
             if (!ph.valid) continue;                         // RectIntersect returns INF for every member
-            if (count > 1 && outsideBox(ph.p, __ldg(gp + 1), __ldg(gp + 2))) continue;
+            const float4 bmin = __ldg(gp + 1), bmax = __ldg(gp + 2);
+            if (count > 1 && outsideBox(ph.p, bmin, bmax)) continue;
+            if (gk & 2u)
+            {   // gridded group: only the quads whose padded box touches the cell of the plane hit, in index order
+                uint32_t mask = lightGridMask(S, gk, g0.w, bmin, bmax, ph.p);
+                while (mask)
+                {
+                    const int i = __ffs((int)mask) - 1; mask &= mask - 1u;
+                    const float4* q = p + (size_t)i * 8;
+                    float dist = rectInside(ph, f3(__ldg(q)), f3(__ldg(q + 5)), f3(__ldg(q + 6)));
+                    if (dist < t) { t = dist; light = first + i; }
+                }
+                continue;
+            }
             for (int i = 0; i < count; i++, p += 8)
             {
                 float dist = rectInside(ph, f3(__ldg(p)), f3(__ldg(p + 5)), f3(__ldg(p + 6)));
@@ -265,13 +291,26 @@ __device__ __forceinline__ bool anyLights(const DevScene& S, float3 o, float3 d,
         const float4 g0 = __ldg(gp);
         const int first = __float_as_int(g0.x), count = __float_as_int(g0.y);
         const float4* p = S.lightsPre + (size_t)first * 8;
-        if (__float_as_int(g0.z) == 0)
+        const uint32_t gk = __float_as_uint(g0.z);
+        if ((gk & 1u) == 0u)
         {
             const float4 e = __ldg(p + 4);
             PlaneHit ph;
             planeEval(f3(e), e.w, o, d, ph);
             if (!(ph.valid && ph.t < maxDist)) continue;     // d > 0 && d < maxDist can only hold for d == t
-            if (count > 1 && outsideBox(ph.p, __ldg(gp + 1), __ldg(gp + 2))) continue;
+            const float4 bmin = __ldg(gp + 1), bmax = __ldg(gp + 2);
+            if (count > 1 && outsideBox(ph.p, bmin, bmax)) continue;
+            if (gk & 2u)
+            {
+                uint32_t mask = lightGridMask(S, gk, g0.w, bmin, bmax, ph.p);
+                while (mask)
+                {
+                    const int i = __ffs((int)mask) - 1; mask &= mask - 1u;
+                    const float4* q = p + (size_t)i * 8;
+                    if (rectInside(ph, f3(__ldg(q)), f3(__ldg(q + 5)), f3(__ldg(q + 6))) < maxDist) return true;
+                }
+                continue;
+            }
             for (int i = 0; i < count; i++, p += 8)
                 if (rectInside(ph, f3(__ldg(p)), f3(__ldg(p + 5)), f3(__ldg(p + 6))) < maxDist) return true;
         }

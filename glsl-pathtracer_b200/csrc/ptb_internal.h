@@ -21,6 +21,7 @@
 // closest_hit.glsl:91,166).
 enum : uint32_t { PTB_K_INNER = 0u, PTB_K_LEAF = 1u, PTB_K_INST = 2u, PTB_K_NONE = 3u };
 #define PTB_META_NONE 0xFFFFFFFFu
+#define PTB_LIGHT_GRID 16
 #define PTB_INST_TRANSLATION_ONLY (1u << 29)
 #define PTB_INST_INDEX_MASK ((1u << 29) - 1)
 #define PTB_MAX_LEAF_TRIS 15
@@ -49,6 +50,7 @@ struct DevScene
     const float4* instShade;    // 8 float4 / instance: transform rows (4) + inverse(mat3) rows (3) + pad
     const float4* lightsPre;    // 8 float4 / light (see buildLightsPre in ptb_api.cpp)
     const float4* lightGroups;  // 3 float4 / group of consecutive lights (shared plane + padded bounds)
+    const uint32_t* lightGrid;  // PTB_LIGHT_GRID^2 member masks per gridded group (ptbd_build_lights)
     const float4* wide;         // 8 float4 / node of the 4-wide any-hit hierarchy (ptbd_build_wide); null = not available
     uint32_t rootMetaWide;      // TLAS root in it
     int numLightGroups;

@@ -36,3 +36,4 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 using std::min; using std::max;
 // sincosf: glibc's (declared by <cmath> with _GNU_SOURCE, which g++ defines)
 #define CUDART_INF_F (__builtin_inff())
+static inline int __ffs(int x) { return __builtin_ffs(x); }

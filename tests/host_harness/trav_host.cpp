@@ -42,7 +42,7 @@ HHScene* hh_create(const float* nodes, int numNodes, int topLevelIndex, const in
     DevScene& S = h->S;
     S.nodes = h->nodes.data(); S.vertIndices = h->vertIndices.data();
     S.inner = h->dh.inner.data(); S.tris = h->tris.data(); S.instTrav = h->dh.instTrav.data(); S.instShade = h->dh.instShade.data();
-    S.lightsPre = h->dl.lightsPre.data(); S.lightGroups = h->dl.lightGroups.data(); S.numLightGroups = h->dl.numGroups;
+    S.lightsPre = h->dl.lightsPre.data(); S.lightGroups = h->dl.lightGroups.data(); S.lightGrid = h->dl.lightGrid.data(); S.numLightGroups = h->dl.numGroups;
     S.rootMeta = h->dh.rootMeta; S.stackDepth = h->dh.stackDepth;
     S.wide = h->dw.ok ? h->dw.wide.data() : nullptr; S.rootMetaWide = h->dw.rootMeta;
     S.stackDepthAny = (h->dw.ok && h->dw.stackDepth > S.stackDepth) ? h->dw.stackDepth : S.stackDepth;

@@ -69,3 +69,25 @@ def boundary_rays(sc, n, seed=13):
     d[np.arange(k), ax[:k]] = np.float32(0.0) * rng.choice([-1.0, 1.0], k).astype(np.float32)   # in-plane, +-0 component
     d[np.arange(k, 2 * k), ax[k:2 * k]] = (np.float32(1e-41) * rng.choice([-1.0, 1.0], k)).astype(np.float32)   # denormal component
     return np.concatenate([o, d.astype(np.float32)], axis=1)
+
+
+def light_rays(sc, n, seed=17):
+    """Rays aimed at the analytic lights: targets spread over (and a little beyond) the lights' bounds, and targets exactly on quad corners and edges
+    (a1 / a2 of RectIntersect at 0 or 1), from origins inside the scene bounds.  Exercises the light loops incl. the shared-plane groups and their cell grid."""
+    L = np.ascontiguousarray(sc.lights, np.float32).reshape(-1, 15)
+    if len(L) == 0:
+        return np.zeros((0, 6), np.float32)
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array(sc.sceneBounds[0], np.float32), np.array(sc.sceneBounds[1], np.float32)
+    o = (lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    k = rng.integers(0, len(L), n)
+    pos, u, v = L[k, 0:3], L[k, 6:9], L[k, 9:12]
+    a = rng.random((n, 2), dtype=np.float32) * np.float32(1.6) - np.float32(0.3)          # inside and just outside the quad
+    third = n // 3
+    a[:third] = rng.choice(np.array([0.0, 0.5, 1.0], np.float32), (third, 2))            # corners, edge midpoints, centre
+    tgt = pos + u * a[:, :1] + v * a[:, 1:]
+    sph = L[k, 14] == 1
+    tgt[sph] = pos[sph] + rng.normal(size=(int(sph.sum()), 3)).astype(np.float32) * L[k[sph], 12:13]
+    d = (tgt - o).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    return np.concatenate([o, d.astype(np.float32)], axis=1)

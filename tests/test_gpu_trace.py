@@ -4,7 +4,7 @@ reference-faithful host traversal of the same flattened BVH, on primary, random 
 import numpy as np
 import pytest
 from conftest import scene_at
-from raysets import random_rays, assert_hits_equal, assert_hits_nearly_equal
+from raysets import random_rays, boundary_rays, light_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
 
 pytestmark = pytest.mark.gpu
 SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
@@ -101,6 +101,26 @@ def test_any_hit_matches_oracle(name, oracle_mod):
     ctx.set_cull(True)
     assert np.array_equal(ctx.trace_any(rays, md), b)
     ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_adversarial_and_light_rays_match_oracle(name, oracle_mod):
+    """Origins exactly on node-box planes (in-plane axis-parallel and denormal directions: 0 * inf NaNs, 1/d = inf) and rays aimed at quad-light corners / edges
+    (shared-plane light groups and their cell grid): closest hit bit-identical in both variants; any-hit — over the 4-wide hierarchy where it is admissible —
+    the same boolean as the oracle's reference-order traversal."""
+    sc = scene_at(name, 64, 64, 32, 32)
+    ctx = _ctx(sc); orc = oracle_mod.Oracle(sc); orc_c = oracle_mod.Oracle(sc, cull=True)
+    rays = np.concatenate([boundary_rays(sc, 100_000), light_rays(sc, 100_000)])
+    for depth in (0, 1):
+        ctx.set_cull(False); assert_hits_equal(ctx.trace_closest(rays, depth), orc.trace_closest(rays, depth))
+        ctx.set_cull(True); assert_hits_equal(ctx.trace_closest(rays, depth), orc_c.trace_closest(rays, depth))
+    md = any_hit_distances(sc, len(rays))
+    want = orc.trace_any(rays, md)
+    for cull in (False, True):
+        ctx.set_cull(cull)
+        got = ctx.trace_any(rays, md)
+        assert np.array_equal(got, want), f"cull={cull}: {np.count_nonzero(got != want)} occlusion mismatches"
+    ctx.close(); orc.close(); orc_c.close()
 
 
 def test_empty_and_invalid_inputs():

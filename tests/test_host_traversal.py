@@ -6,7 +6,7 @@ changes where no GPU exists.  The G1 gate proper (tests/test_gpu_trace.py) runs 
 import numpy as np
 import pytest
 from conftest import scene_at
-from raysets import random_rays, bounce_rays, boundary_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
+from raysets import random_rays, bounce_rays, boundary_rays, light_rays, any_hit_distances, assert_hits_equal, assert_hits_nearly_equal
 from host_harness.binding import HostTrav
 
 SCENES = ["cornell_box_orig", "cornell_box_sphere", "hyperion_rect_lights", "hyperion_sphere_light", "volume_cube", "teapot", "ibl_spheres", "instancing", "gltf_mix"]
@@ -34,7 +34,7 @@ def test_host_compiled_traversal_equals_oracle(name, oracle_mod):
     ht.set_cull(False); assert_hits_equal(ht.trace_closest(b, 1), orc.trace_closest(b, 1))
     ht.set_cull(True); assert_hits_equal(ht.trace_closest(b, 1), orc_c.trace_closest(b, 1))
     # closest hit on adversarial rays (origins exactly on node-box planes, in-plane axis-parallel and denormal directions)
-    adv = boundary_rays(sc, 30_000)
+    adv = np.concatenate([boundary_rays(sc, 30_000), light_rays(sc, 30_000)])
     ht.set_cull(False); assert_hits_equal(ht.trace_closest(adv, 1), orc.trace_closest(adv, 1))
     ht.set_cull(True); assert_hits_equal(ht.trace_closest(adv, 1), orc_c.trace_closest(adv, 1))
     # any-hit: occlusion is the same boolean in both traversal variants AND over the 4-wide hierarchy (the production path of k_shadow)
