@@ -97,6 +97,7 @@ struct PtbCtx
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
+    int streamShade = 5;       // SHADE_* flags allowed for the first shade pass (PTB_STREAM_SHADE): 1 identity queue, 2 static chunks, 4 count-only
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
                                //    tiles of 2048 slots, instead of over the compacted arrival-order queue (PTB_SLOT_ORDER)
@@ -363,7 +364,11 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
             shadeQueue = c->sortedQueue.p;
         }
         mark(c, KIND_SHADE);
-        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0, (useSlotOrder && it == 0) ? c->slotKeys.p : nullptr, nOv);
+        // first shade pass after a fused camera/trace launch: identity queue -> streaming mode (no queue read, no fetch atomic; with the slot-ordered
+        // bounce 1 the continuing paths are only counted)
+        uint32_t shadeFlags = 0;
+        if (it == 0 && fusedCamera && !sortThis) shadeFlags = (uint32_t)c->streamShade & (1u | 2u | (useSlotOrder ? 4u : 0u));
+        ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0, (useSlotOrder && it == 0) ? c->slotKeys.p : nullptr, nOv, shadeFlags);
         if (!F.inlineShadow)
         {
             mark(c, KIND_SHADOW);
@@ -498,6 +503,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
     if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
     if (const char* e = getenv("PTB_FUSE_CAMERA")) c->fuseCamera = atoi(e);
+    if (const char* e = getenv("PTB_STREAM_SHADE")) c->streamShade = atoi(e);
     *out = c;
     return PTB_OK;
 }

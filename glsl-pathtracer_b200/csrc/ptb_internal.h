@@ -128,6 +128,7 @@ struct PathState
     uint32_t* queue[2];
 };
 
+#define PTB_HIT_DEAD ((int)0x80000000)      // hitInst of a path slot that holds no path (off-image pixel of a padded 8x4 block)
 #define PTB_FLAG_INMEDIUM   (1u << 16)
 #define PTB_FLAG_SURFSCAT   (1u << 17)
 
@@ -157,7 +158,8 @@ void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, co
                uint32_t* sorted);
 void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey = -1, uint32_t nOverride = 0);
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys = nullptr, uint32_t nOverride = 0);
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys = nullptr, uint32_t nOverride = 0,
+                uint32_t flags = 0);     // flags: SHADE_* of ptb_kernels.cu (1 identity queue, 2 static chunks, 4 count the continuing paths only)
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);

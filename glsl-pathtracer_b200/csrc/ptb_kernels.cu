@@ -127,6 +127,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             const bool live = px < W.rw && py < W.rh;
             pq = live ? i : 0xffffffffu;
             P.queue[0][i] = pq;
+            if (!live) P.hitInst[i] = PTB_HIT_DEAD;        // off-image pixel of a padded block: the streaming first shade pass skips it without reading the queue
             if (live)
             {
                 Rng rng;
@@ -799,27 +800,38 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
     }
 }
 
+// flags: first shade pass of a wave whose camera rays were generated by k_trace_primary — the queue is the identity over the path slots, so it streams:
+//   SHADE_IDENTITY   entry i is path slot i (no queue read in front of the state loads; off-image slots of padded pixel blocks carry PTB_HIT_DEAD)
+//   SHADE_STATIC     chunks are dealt to the warps round-robin (uniform work per chunk: no fetch atomic to wait for)
+//   SHADE_COUNT_ONLY the continuing paths are counted, not queued (the next trace runs over the slots in screen order: slot-ordered bounce 1)
+enum { SHADE_IDENTITY = 1, SHADE_STATIC = 2, SHADE_COUNT_ONLY = 4 };
+
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
-                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* __restrict__ slotKeys, uint32_t nOverride)
+                                                          uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* __restrict__ slotKeys, uint32_t nOverride,
+                                                          uint32_t flags)
 {
     const uint32_t n = nOverride ? nOverride : ctrThis[CTR_NPATHS];
     const uint32_t lane = threadIdx.x & 31u;
     InlineCounters ic{0u, 0u};
-    uint32_t nextBase = 0;
-    if (lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);
+    const bool staticChunks = (flags & SHADE_STATIC) != 0u;
+    const uint32_t chunkStride = gridDim.x * (SHADE_THREADS / 32) * 32u;
+    uint32_t nextBase = (blockIdx.x * (SHADE_THREADS / 32) + (threadIdx.x >> 5)) * 32u;
+    if (!staticChunks && lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);
+    uint32_t continued = 0;
     while (true)
     {
-        const uint32_t base = __shfl_sync(0xffffffffu, nextBase, 0);
+        const uint32_t base = staticChunks ? nextBase : __shfl_sync(0xffffffffu, nextBase, 0);
         if (base >= n) break;
-        if (lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);      // prefetch the next chunk index
+        if (staticChunks) nextBase += chunkStride;
+        else if (lane == 0) nextBase = atomicAdd(&ctrThis[CTR_FETCH_SHADE], 32u);      // prefetch the next chunk index
         const uint32_t i = base + lane;
         bool cont = false;
         ShadowOut sa, sb; sa.valid = false; sb.valid = false;
         uint32_t p = 0;
         if (i < n)
         {
-            p = queue[i];
+            p = (flags & SHADE_IDENTITY) ? (P.hitInst[i] == PTB_HIT_DEAD ? 0xffffffffu : i) : queue[i];
             if (p != 0xffffffffu)                     // (hole of a slot-ordered queue)
             {
                 shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis);
@@ -838,7 +850,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             }
         }
         unsigned m = __ballot_sync(0xffffffffu, cont);
-        if (m)
+        if (flags & SHADE_COUNT_ONLY) continued += (uint32_t)__popc(m);
+        else if (m)
         {
             uint32_t b = 0;
             if (lane == 0) b = atomicAdd(&ctrNext[CTR_NPATHS], (uint32_t)__popc(m));
@@ -851,6 +864,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
         }
     }
+    if ((flags & SHADE_COUNT_ONLY) && lane == 0 && continued) atomicAdd(&ctrNext[CTR_NPATHS], continued);       // one reduction per warp, nothing waits for it
     if (MODE == 2 && (ic.segs | ic.shadows))
     {
         atomicAdd(&stats->pathSegments, (unsigned long long)ic.segs);
@@ -1157,14 +1171,14 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride)
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride, uint32_t flags)
 {
     const int* bps = c.shadeBlocks;
-    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
-    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
+    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
     else if (PTB_SHADE_LATER_BLOCKS != 4 && !firstIter)
-        k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
-    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride);
+        k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
     COUNT_LAUNCH(c, 1);
 }
 
