@@ -390,7 +390,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rig = Rig(args.workload, local, rank, world, args.samples_per_wave, args.cull)
+    rig = Rig(args.workload, local, rank, world, args.samples_per_wave, args.cull, *(args.res or (None, None)))
     sc, ctx = rig.sc, rig.ctx
     warm = max(args.warmup, 3)
 
@@ -474,7 +474,10 @@ def run_ours(args):
             # the kernels on this workload (deterministic paths), taken from the capture; the time is THIS run's k_trace time
             sms, clk_hz = 148, (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1965.0) * 1e6
             ti = cap.get("k_trace_thread_inst_per_step")
+            l2p = os.path.join(ROOT, "profiles", "r02_l2_peak.json")
+            l2_peak = json.load(open(l2p))["l2_copy_gbs"] if os.path.exists(l2p) else None
             roof["lane_issue"] = {"k_trace_thread_inst_per_step": ti, "k_trace_warp_inst_per_step": cap.get("k_trace_warp_inst_per_step"),
+                                  "l2_peak_gbs": l2_peak, "l2_peak_source": "profiles/r02_l2_peak.json (scripts/measure_l2_peak.py: L2-resident copy, read+write)",
                                   "frac": (ti / (sms * 4 * 32 * clk_hz * trace_ms_last * 1e-3) if ti and trace_ms_last > 0 else None),
                                   "k_shadow_frac_in_capture": cap.get("k_shadow_lane_issue_frac"), "k_trace_frac_in_capture": cap.get("k_trace_lane_issue_frac"),
                                   "l2_gbs_in_capture": cap.get("k_trace_l2_gbs"), "capture_commit": cap.get("commit"), "capture_file": "profiles/r02_capture.json",
@@ -526,6 +529,7 @@ def main():
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the other BASELINE configs (other_workloads key)")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (profiling runs): no image check, cull0, strong, other workloads, drop-in, CPU baseline")
     ap.add_argument("--workload", default=SCENE, choices=sorted(WORKLOADS))
+    ap.add_argument("--res", type=int, nargs=2, default=None, metavar=("W", "H"), help="override the workload's resolution (experiments only: not the BASELINE config)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -75,13 +75,15 @@ int main(int argc, char** argv)
         bool clockStarted = warmup == 0;
         while (renderer->GetSampleCount() < renderOptions.maxSpp)
         {
+            renderer->Update(0.016f);
             if (!clockStarted && renderer->GetSampleCount() >= warmup + 1)
-            {
-                renderer->GetOutputBuffer(&data, ow, oh); delete[] data;      // drains the GPU: the timed region starts idle
+            {   // pass `warmup` has just completed and nothing of the next pass has been traced yet (its wave starts in the Render() below):
+                // drain the GPU and start the clock here, so that every pass counted is traced inside the timed region
+                renderer->GetOutputBuffer(&data, ow, oh); delete[] data;
                 ptb_mgpu_get_stats(MgpuOfB200(*renderer), &st0);
                 t0 = std::chrono::steady_clock::now(); clockStarted = true;
             }
-            renderer->Update(0.016f); renderer->Render(); renderer->Present(); updates++;
+            renderer->Render(); renderer->Present(); updates++;
         }
     }
     renderer->GetOutputBuffer(&data, ow, oh);            // SaveFrame, Main.cpp:164-173: the one device->host copy (inside the timed region)

@@ -19,7 +19,11 @@ for name, sc in cases:
     ctx.read_output(0.5)
     ctx.update_instances(sc.transforms, sc.materials, sc.nodes[sc.topLevelIndex:])
     ctx.render_samples(3, 1)
+    for s in (4, 5, 6):                       # coalesced-pass path: look-ahead wave + per-pass accumulate, frozen output
+        ctx.render_pass(s, 3)
+    ctx.snapshot_output(1.0 / 6); ctx.read_snapshot()
     rays = np.concatenate([np.tile(sc.camera.position, (256, 1)), np.random.default_rng(1).normal(size=(256, 3))], axis=1).astype(np.float32)
+    rays[:16, 3:] = np.eye(3, dtype=np.float32)[np.arange(16) % 3]        # axis-parallel: the binary any-hit path next to the 4-wide one
     ctx.trace_closest(rays); ctx.trace_any(rays, 1e6)
     print(name, "ok", float(np.nan_to_num(a[..., :3]).mean()), ctx.stats()["kernelLaunches"], "launches")
     ctx.close()
