@@ -67,7 +67,7 @@ SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_derive_features",
            "ptb_mgpu_create", "ptb_mgpu_destroy", "ptb_mgpu_num_devices", "ptb_mgpu_context", "ptb_mgpu_set_options", "ptb_mgpu_set_camera", "ptb_mgpu_set_cull",
            "ptb_mgpu_update_instances", "ptb_mgpu_update_envmap", "ptb_mgpu_reset_accum", "ptb_mgpu_render_samples", "ptb_mgpu_read_output_rgba8",
            "ptb_mgpu_read_accum_f32", "ptb_mgpu_get_stats", "ptb_mgpu_synchronize", "ptb_mgpu_render_pass", "ptb_mgpu_snapshot_output", "ptb_mgpu_read_snapshot_rgba8",
-           "ptb_snapshot_output_from", "ptb_set_snapshot_float", "ptb_read_snapshot_rgb32f"]
+           "ptb_snapshot_output_from", "ptb_set_snapshot_float", "ptb_read_snapshot_rgb32f", "ptb_mgpu_read_snapshot_rgb32f"]
 
 _lib = None
 
@@ -97,7 +97,7 @@ def load():
         "ptb_bsdf_eval": [vp, vp, i64, vp], "ptb_bsdf_sample": [vp, vp, i64, vp], "ptb_lambert_eval": [vp, vp, i64, vp], "ptb_lambert_sample": [vp, vp, i64, vp], "ptb_camera_rays": [vp, i32, vp],
         "ptb_trace_closest_device": [vp, vp, i64, i32, vp], "ptb_read_nodes": [vp, vp, i32], "ptb_stack_depth": [vp, C.POINTER(i32)],
         "ptb_render_pass": [vp, i32, i32, i32], "ptb_snapshot_output_from": [vp, vp, f32], "ptb_set_snapshot_float": [vp, i32], "ptb_read_snapshot_rgb32f": [vp, vp], "ptb_mgpu_render_pass": [vp, i32, i32],
-        "ptb_mgpu_snapshot_output": [vp, f32], "ptb_mgpu_read_snapshot_rgba8": [vp, vp], "ptb_read_output_rgba8_from": [vp, vp, f32, vp], "ptb_snapshot_output": [vp, f32], "ptb_read_snapshot_rgba8": [vp, vp],
+        "ptb_mgpu_snapshot_output": [vp, f32], "ptb_mgpu_read_snapshot_rgba8": [vp, vp], "ptb_mgpu_read_snapshot_rgb32f": [vp, vp], "ptb_read_output_rgba8_from": [vp, vp, f32, vp], "ptb_snapshot_output": [vp, f32], "ptb_read_snapshot_rgba8": [vp, vp],
         "ptb_host_alloc": [C.c_uint64, C.POINTER(vp)], "ptb_host_free": [vp],
         "ptb_mgpu_create": [C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions), C.POINTER(i32), i32, C.POINTER(vp)], "ptb_mgpu_destroy": [vp],
         "ptb_mgpu_num_devices": [vp], "ptb_mgpu_set_options": [vp, C.POINTER(PtbOptions)], "ptb_mgpu_set_camera": [vp, C.POINTER(PtbCamera)],

@@ -63,6 +63,9 @@ struct PtbMgpu
     std::vector<cudaStream_t> streams;      // per-device stream the contexts run on (NCCL is enqueued on the same streams)
     void* scratch = nullptr;                // float4[w*h] on devices[0]: reduced sum
     size_t scratchBytes = 0;
+    // ptb_mgpu_snapshot_output with several GPUs: every GPU freezes ITS running sum with an asynchronous device-to-device copy (no cross-GPU
+    // synchronisation while rendering goes on); the reduce + tonemap happen when the frozen image is asked for
+    std::vector<void*> frozen; size_t frozenBytes = 0; float frozenInv = 1.f; bool frozenPending = false;
     int w = 0, h = 0;
     int nextPass = 1;
 };
@@ -75,6 +78,7 @@ int ptb_mgpu_destroy(PtbMgpu* m)
     for (size_t i = 0; i < m->comms.size(); i++) if (m->comms[i]) g_nccl.CommDestroy(m->comms[i]);
     for (size_t i = 0; i < m->ctx.size(); i++) if (m->ctx[i]) ptb_destroy(m->ctx[i]);
     if (m->scratch) { cudaSetDevice(m->devices[0]); cudaFree(m->scratch); }
+    for (size_t i = 0; i < m->frozen.size(); i++) if (m->frozen[i]) { cudaSetDevice(m->devices[i]); cudaFree(m->frozen[i]); }
     for (size_t i = 0; i < m->streams.size(); i++) if (m->streams[i]) { cudaSetDevice(m->devices[i]); cudaStreamDestroy(m->streams[i]); }
     delete m;
     return PTB_OK;
@@ -166,8 +170,8 @@ int ptb_mgpu_render_pass(PtbMgpu* m, int32_t sample, int32_t maxLookahead)
     return ptb_render_pass(m->ctx[(sample - 1) % N], sample, N, maxLookahead);
 }
 
-// sum of the per-GPU running sums -> scratch on devices[0] (the running sums are left untouched)
-static int reduceToScratch(PtbMgpu* m, const void** devSum)
+// sum of the per-GPU running sums (or, fromFrozen, of their frozen copies) -> scratch on devices[0]; the sources are left untouched
+static int reduceToScratch(PtbMgpu* m, const void** devSum, bool fromFrozen = false)
 {
     const int N = (int)m->ctx.size();
     void* p0 = nullptr; uint64_t nbytes = 0;
@@ -186,7 +190,7 @@ static int reduceToScratch(PtbMgpu* m, const void** devSum)
     for (int i = 0; i < N && r == NCCL_SUCCESS; i++)
     {
         void* pi = nullptr;
-        ptb_accum_device_ptr(m->ctx[i], &pi, nullptr);
+        if (fromFrozen) pi = m->frozen[i]; else ptb_accum_device_ptr(m->ctx[i], &pi, nullptr);
         cudaSetDevice(m->devices[i]);
         r = g_nccl.Reduce(pi, i == 0 ? m->scratch : nullptr, (size_t)(nbytes / 4), NCCL_FLOAT, NCCL_SUM, 0, m->comms[i], m->streams[i]);
     }
@@ -212,16 +216,68 @@ int ptb_mgpu_read_output_rgba8(PtbMgpu* m, float invSampleCounter, uint8_t* out)
 int ptb_mgpu_snapshot_output(PtbMgpu* m, float invSampleCounter)
 {
     if (!m) return fail(PTB_ERR_INVALID_ARGUMENT, "null argument");
-    const void* sum = nullptr;
-    int rc = reduceToScratch(m, &sum);
+    const int N = (int)m->ctx.size();
+    if (N == 1) return ptb_snapshot_output(m->ctx[0], invSampleCounter);
+    // Several GPUs: a reduce here would make every GPU wait for every other one once per pass (the drop-in calls this at each pass end while the
+    // GPUs trace waves of their own passes).  Freeze each running sum locally instead; resolveFrozen() combines them when the image is read.
+    void* p0 = nullptr; uint64_t nbytes = 0;
+    int rc = ptb_accum_device_ptr(m->ctx[0], &p0, &nbytes);
     if (rc) return rc;
-    return ptb_snapshot_output_from(m->ctx[0], sum, invSampleCounter);      // stream-ordered after the reduce; nothing waits on the host
+    if (m->frozen.size() != (size_t)N || m->frozenBytes < nbytes)
+    {
+        for (size_t i = 0; i < m->frozen.size(); i++) if (m->frozen[i]) { cudaSetDevice(m->devices[i]); cudaFree(m->frozen[i]); }
+        m->frozen.assign(N, nullptr); m->frozenBytes = 0;
+        for (int i = 0; i < N; i++)
+        {
+            cudaSetDevice(m->devices[i]);
+            if (cudaMalloc(&m->frozen[i], nbytes) != cudaSuccess) return fail(PTB_ERR_OUT_OF_MEMORY, "frozen-sum allocation failed");
+        }
+        m->frozenBytes = nbytes;
+    }
+    for (int i = 0; i < N; i++)
+    {
+        void* pi = nullptr;
+        ptb_accum_device_ptr(m->ctx[i], &pi, nullptr);
+        cudaSetDevice(m->devices[i]);
+        if (cudaMemcpyAsync(m->frozen[i], pi, nbytes, cudaMemcpyDeviceToDevice, m->streams[i]) != cudaSuccess) return fail(PTB_ERR_CUDA, "freezing a running sum failed");
+    }
+    m->frozenInv = invSampleCounter; m->frozenPending = true;
+    return PTB_OK;
+}
+
+// combine the frozen sums into the tonemapped snapshot on devices[0] (one ncclReduce), if a newer freeze is pending
+static int resolveFrozen(PtbMgpu* m)
+{
+    if (m->ctx.size() == 1 || !m->frozenPending) return PTB_OK;
+    const void* sum = nullptr;
+    int rc = reduceToScratch(m, &sum, true);
+    if (rc) return rc;
+    rc = ptb_snapshot_output_from(m->ctx[0], sum, m->frozenInv);
+    if (rc) return rc;
+    m->frozenPending = false;
+    return PTB_OK;
 }
 
 int ptb_mgpu_read_snapshot_rgba8(PtbMgpu* m, uint8_t* out)
 {
     if (!m || !out) return fail(PTB_ERR_INVALID_ARGUMENT, "null argument");
-    return ptb_read_snapshot_rgba8(m->ctx[0], out);
+    int rc = resolveFrozen(m);
+    if (rc) return rc;
+    rc = ptb_read_snapshot_rgba8(m->ctx[0], out);
+    if (rc) return rc;
+    for (size_t i = 1; i < m->ctx.size(); i++) { rc = ptb_synchronize(m->ctx[i]); if (rc) return rc; }     // the other GPUs' send side has completed
+    return PTB_OK;
+}
+
+int ptb_mgpu_read_snapshot_rgb32f(PtbMgpu* m, float* outRgb)
+{
+    if (!m || !outRgb) return fail(PTB_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = resolveFrozen(m);
+    if (rc) return rc;
+    rc = ptb_read_snapshot_rgb32f(m->ctx[0], outRgb);
+    if (rc) return rc;
+    for (size_t i = 1; i < m->ctx.size(); i++) { rc = ptb_synchronize(m->ctx[i]); if (rc) return rc; }
+    return PTB_OK;
 }
 
 int ptb_mgpu_read_accum_f32(PtbMgpu* m, float* out)

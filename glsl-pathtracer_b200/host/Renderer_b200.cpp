@@ -37,6 +37,7 @@ namespace GLSLPT
             bool coalesce = true;                          // a whole sample pass per first-tile Render() (PTB_COALESCE=0: one wave per tile)
             bool passCoalesced = false;                    // the pass being walked was rendered at its first tile
             std::vector<float> denoiseIn, denoiseOut;      // denoiserInputFramePtr / frameOutputPtr (Renderer.cpp:347-348)
+            PtbCamera sentCam; PtbOptions sentOpts; bool sentValid = false;     // uniforms last pushed to the contexts: Update() runs once per TILE, most calls change nothing
         };
         std::map<const Renderer*, Side>& table() { static std::map<const Renderer*, Side> t; return t; }
 
@@ -180,6 +181,7 @@ namespace GLSLPT
         Side& sd = table()[this];
         PtbOptions o = options(scene, sd.samplesPerWave, sd.features);
         check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");     // new size: buffers reallocated, frozen image dropped
+        sd.sentValid = false;
         check(ptb_mgpu_reset_accum(sd.m), "ptb_reset_accum");         // the reference re-creates (clears) every FBO texture
         InitFBOs();
     }
@@ -190,6 +192,7 @@ namespace GLSLPT
         sd.features = deriveFeatures(scene);
         PtbOptions o = options(scene, sd.samplesPerWave, sd.features);
         check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");
+        sd.sentValid = false;
     }
 
     void Renderer::Render()
@@ -264,13 +267,14 @@ namespace GLSLPT
                   "ptb_update_envmap");
         // Denoiser hook (Renderer.cpp:695-730): same trigger and cadence as the reference; the filter itself (OIDN there) is whatever
         // the host registered with SetDenoiserB200 — without one the branch leaves `denoised` false, as a build without OIDN would.
+        check(ptb_set_snapshot_float(sd.ctx0, (scene->renderOptions.enableDenoiser && denoiser()) ? 1 : 0), "ptb_set_snapshot_float");   // keep the RGBA32F form of frozen images for the hook
         if (scene->renderOptions.enableDenoiser && sampleCounter > 1 && denoiser())
         {
             if (!denoised || (frameCounter % (scene->renderOptions.denoiserFrameCnt * (numTiles.x * numTiles.y)) == 0))
             {
                 const size_t n = (size_t)renderSize.x * renderSize.y * 3;
                 sd.denoiseIn.resize(n); sd.denoiseOut.resize(n);
-                check(ptb_read_snapshot_rgb32f(sd.ctx0, sd.denoiseIn.data()), "ptb_read_snapshot_rgb32f");    // glGetTexImage(GL_RGB, GL_FLOAT)
+                check(ptb_mgpu_read_snapshot_rgb32f(sd.m, sd.denoiseIn.data()), "ptb_read_snapshot_rgb32f");    // glGetTexImage(GL_RGB, GL_FLOAT)
                 denoiser()(sd.denoiseIn.data(), sd.denoiseOut.data(), renderSize.x, renderSize.y, denoiserUser());
                 denoised = true;
             }
@@ -305,9 +309,13 @@ namespace GLSLPT
             }
         }
         PtbCamera cam = camera(scene);
-        check(ptb_mgpu_set_camera(sd.m, &cam), "ptb_set_camera");
         PtbOptions o = options(scene, sd.samplesPerWave, sd.features);      // uniforms only: the OPT_* set changes in ReloadShaders, as in the reference
-        check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");
+        if (!sd.sentValid || memcmp(&cam, &sd.sentCam, sizeof(cam)) != 0 || memcmp(&o, &sd.sentOpts, sizeof(o)) != 0)
+        {   // the reference sets its uniforms on every Update (Renderer.cpp:766-811); here they are pushed to the N contexts when they changed
+            check(ptb_mgpu_set_camera(sd.m, &cam), "ptb_set_camera");
+            check(ptb_mgpu_set_options(sd.m, &o), "ptb_set_options");
+            sd.sentCam = cam; sd.sentOpts = o; sd.sentValid = true;
+        }
         sd.invSampleCounter = 1.0f / (sampleCounter);
     }
 
@@ -317,6 +325,7 @@ namespace GLSLPT
         Side& sd = table()[&r];
         PtbCamera cam = camera(scene);
         check(ptb_mgpu_set_camera(sd.m, &cam), "ptb_set_camera");
+        sd.sentValid = false;
         int first = r.GetSampleCount();
         check(ptb_mgpu_render_samples(sd.m, first, n), "ptb_render_samples");
         RendererB200Access::advance(r, n);

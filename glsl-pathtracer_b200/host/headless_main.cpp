@@ -20,7 +20,7 @@ int main(int argc, char** argv)
 {
     std::string sceneFile, out = "out.png", accumOut;
     int spp = 16, w = 0, h = 0, depth = -1, warmup = 0, denoiseEvery = 0; bool whole = false;
-    static int denoiseCalls = 0;
+    static int denoiseCalls = 0; static double denoiseInSum = 0.0;
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i];
@@ -58,7 +58,7 @@ int main(int argc, char** argv)
     if (denoiseEvery > 0) { renderOptions.enableDenoiser = true; renderOptions.denoiserFrameCnt = denoiseEvery; }
     scene->renderOptions = renderOptions;                // Main.cpp:154
     if (denoiseEvery > 0)      // stand-in for OIDN: the hook, its trigger and its cadence are the deliverable, not the filter
-        SetDenoiserB200([](const float* in, float* out, int w_, int h_, void*) { denoiseCalls++; memcpy(out, in, (size_t)w_ * h_ * 12); }, nullptr);
+        SetDenoiserB200([](const float* in, float* out, int w_, int h_, void*) { denoiseCalls++; denoiseInSum = 0.0; for (size_t i = 0; i < (size_t)w_ * h_ * 3; i++) denoiseInSum += in[i]; memcpy(out, in, (size_t)w_ * h_ * 12); }, nullptr);
 
     Renderer* renderer = new Renderer(scene, "shaders/");
     auto t0 = std::chrono::steady_clock::now();
@@ -92,9 +92,9 @@ int main(int argc, char** argv)
     printf("rendered %d spp in %.3f s (%.1f spp/s), %llu path segments, %llu shadow rays, %llu kernel launches\n", spp, sec, spp / sec,
            (unsigned long long)(st.pathSegments - st0.pathSegments), (unsigned long long)(st.shadowRays - st0.shadowRays), (unsigned long long)(st.kernelLaunches - st0.kernelLaunches));
     printf("BENCH {\"spp\": %d, \"seconds\": %.6f, \"path_segments\": %llu, \"shadow_rays\": %llu, \"kernel_launches\": %llu, \"updates\": %lld, \"gpus\": %d, "
-           "\"coalesced\": %s, \"whole_frame\": %s, \"denoiser_calls\": %d}\n", spp, sec, (unsigned long long)(st.pathSegments - st0.pathSegments),
+           "\"coalesced\": %s, \"whole_frame\": %s, \"denoiser_calls\": %d, \"denoiser_input_sum\": %.3f}\n", spp, sec, (unsigned long long)(st.pathSegments - st0.pathSegments),
            (unsigned long long)(st.shadowRays - st0.shadowRays), (unsigned long long)(st.kernelLaunches - st0.kernelLaunches), updates, ptb_mgpu_num_devices(MgpuOfB200(*renderer)),
-           (getenv("PTB_COALESCE") && atoi(getenv("PTB_COALESCE")) == 0) ? "false" : "true", whole ? "true" : "false", denoiseCalls);
+           (getenv("PTB_COALESCE") && atoi(getenv("PTB_COALESCE")) == 0) ? "false" : "true", whole ? "true" : "false", denoiseCalls, denoiseInSum);
 
     stbi_flip_vertically_on_write(true);
     stbi_write_png(out.c_str(), ow, oh, 4, data, ow * 4);

@@ -236,8 +236,11 @@ int  ptb_mgpu_reset_accum(PtbMgpu* m);
 int  ptb_mgpu_render_samples(PtbMgpu* m, int32_t firstSample, int32_t nSamples);    /* passes [first, first+n) over all GPUs, asynchronous */
 int  ptb_mgpu_render_pass(PtbMgpu* m, int32_t sample, int32_t maxLookahead);         /* ptb_render_pass on GPU (sample-1) mod N, stride N */
 int  ptb_mgpu_read_output_rgba8(PtbMgpu* m, float invSampleCounter, uint8_t* outRgba8);   /* reduce -> tonemap -> host (GetOutputBuffer) */
-int  ptb_mgpu_snapshot_output(PtbMgpu* m, float invSampleCounter);                  /* reduce -> tonemap, kept on devices[0] (asynchronous) */
+/* ptb_snapshot_output for N GPUs: every GPU freezes its own running sum (asynchronous device copy, no cross-GPU synchronisation while the GPUs
+ * render their waves); the ONE ncclReduce + tonemap of the frozen sums happens when the image is read. */
+int  ptb_mgpu_snapshot_output(PtbMgpu* m, float invSampleCounter);
 int  ptb_mgpu_read_snapshot_rgba8(PtbMgpu* m, uint8_t* outRgba8);
+int  ptb_mgpu_read_snapshot_rgb32f(PtbMgpu* m, float* outRgb);                      /* for the denoiser hook (ptb_set_snapshot_float on context 0) */
 int  ptb_mgpu_read_accum_f32(PtbMgpu* m, float* outRgba);                           /* reduced linear sum (parity) */
 int  ptb_mgpu_get_stats(PtbMgpu* m, PtbStats* out);                                 /* counters summed, lastRenderMs = max over GPUs */
 int  ptb_mgpu_synchronize(PtbMgpu* m);

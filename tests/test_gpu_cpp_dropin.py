@@ -68,6 +68,7 @@ def test_denoiser_hook_runs_at_the_reference_cadence(tmp_path):
     # the file's 200x200 tiles -> 1 tile per pass; Update() tests the trigger before it advances the counters: first run in the Update that
     # sees sampleCounter 2 (frameCounter 3 -> 4), then in the Updates that see frameCounter 6 and 9; the loop ends at sampleCounter 10
     assert b["denoiser_calls"] == 3, b
+    assert b["denoiser_input_sum"] > 100.0          # the hook received the tonemapped float image of a completed pass, not an empty buffer
     b = _run(["-s", scene, "-o", str(tmp_path / "o.png"), "--spp", "9", "--res", "100", "72"])
     assert b["denoiser_calls"] == 0
 
