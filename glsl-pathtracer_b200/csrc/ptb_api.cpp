@@ -79,6 +79,9 @@ struct PtbCtx
     DevBuf<int> vertIndices;
     DevBuf<float4> triShade, wide;
     DevBuf<uint32_t> lightGrid;
+    // device-side TLAS rebuild (ptb_rebuild_instances): per-instance BLAS root / material id, scratch of the builder
+    DevBuf<int> tlasBlasRoot, tlasMatID, tlasNodeOf, tlasRemap, tlasResult; DevBuf<float> tlasBounds, tlasCent; DevBuf<char> tlasRec[3];
+    int lastRebuildWhere = -1;   // 0 device, 1 host (asked for), 2 host (fallback of the device builder)
     int wideAny = 1;           // 1: shadow rays use the 4-wide any-hit hierarchy where it is provably equivalent (PTB_WIDE_ANY)
     DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
@@ -514,7 +517,7 @@ int ptb_destroy(PtbCtx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
-    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release(); c->wide.release();
+    c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release(); c->wide.release(); c->tlasBlasRoot.release(); c->tlasMatID.release(); c->tlasNodeOf.release(); c->tlasRemap.release(); c->tlasResult.release(); c->tlasBounds.release(); c->tlasCent.release(); for (int k = 0; k < 3; k++) c->tlasRec[k].release();
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->lightGrid.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
     for (int k = 0; k < 2; k++) { c->shO[k].release(); c->shD[k].release(); c->shC[k].release(); c->queue[k].release(); }
@@ -591,6 +594,63 @@ int ptb_update_instances(PtbCtx* c, const float* transforms, int32_t numInstance
     refreshDerivedFlags(c);
     return PTB_OK;
 }
+
+int ptb_rebuild_instances(PtbCtx* c, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials, const int32_t* instanceMaterialIDs, int32_t onHost)
+{
+    REQUIRE(c && transforms && materials, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    REQUIRE(numInstances == c->S.numInstances && numMaterials > 0, PTB_ERR_INVALID_ARGUMENT, "instance count changed (the reference keeps it across RebuildInstances)");
+    REQUIRE(c->numNodes - c->topLevelIndex >= 2 * numInstances, PTB_ERR_INVALID_ARGUMENT, "TLAS slice smaller than 2 * numInstances slots");
+    CK(cudaSetDevice(c->device));
+    const int n = numInstances, top = c->topLevelIndex;
+    // per instance: BLAS root and material id, as the current TLAS leaves carry them (bvh_translator.cpp:70-78)
+    std::vector<int> root((size_t)n, -1), mat((size_t)n, 0);
+    for (int i = top; i < c->numNodes; i++)
+    {
+        const float* nd = &c->hNodes[(size_t)i * 9];
+        const int leaf = (int)nd[8];
+        if (leaf < 0 && -leaf - 1 < n) { root[(size_t)(-leaf - 1)] = (int)nd[6]; mat[(size_t)(-leaf - 1)] = (int)nd[7]; }
+    }
+    for (int i = 0; i < n; i++)
+    {
+        if (instanceMaterialIDs) mat[(size_t)i] = instanceMaterialIDs[i];
+        REQUIRE(root[(size_t)i] >= 0 && root[(size_t)i] < top, PTB_ERR_INVALID_ARGUMENT, "instance without a TLAS leaf");
+        REQUIRE(mat[(size_t)i] >= 0 && mat[(size_t)i] < numMaterials, PTB_ERR_INVALID_ARGUMENT, "instance material id out of range");
+    }
+    std::vector<float> slice;
+    bool built = false;
+    if (!onHost)
+    {   // k_tlas_build writes the slice straight into the canonical device node array; it is read back for the host-side derivation of the packed layouts
+        const size_t recBytes = (size_t)ptbk_tlas_rec_size() * ((size_t)n + 2);
+        CK(c->tlasBlasRoot.upload(root.data(), (size_t)n, c->stream)); CK(c->tlasMatID.upload(mat.data(), (size_t)n, c->stream));
+        CK(c->transforms.upload((const float4*)transforms, (size_t)n * 4, c->stream));
+        CK(c->tlasNodeOf.alloc((size_t)n)); CK(c->tlasRemap.alloc((size_t)n + 2)); CK(c->tlasResult.alloc(2));
+        CK(c->tlasBounds.alloc((size_t)n * 6)); CK(c->tlasCent.alloc((size_t)n * 3));
+        for (int k = 0; k < 3; k++) CK(c->tlasRec[k].alloc(recBytes));
+        ptbk_tlas_build(cfg(c), c->nodes.p, top, c->transforms.p, n, c->tlasBlasRoot.p, c->tlasMatID.p, c->tlasBounds.p, c->tlasCent.p, c->tlasNodeOf.p,
+                        c->tlasRec[0].p, c->tlasRec[1].p, c->tlasRec[2].p, c->tlasRemap.p, c->tlasResult.p);
+        CK(cudaGetLastError());
+        int res[2] = {1, 0};
+        slice.resize((size_t)2 * n * 9);
+        CK(cudaMemcpyAsync(res, c->tlasResult.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(slice.data(), c->nodes.p + (size_t)top * 9, slice.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        built = res[0] == 0;            // flag: an input where the reference's element order matters (or -0.0 / non-finite boxes) -> exact sequential build below
+        c->lastRebuildWhere = built ? 0 : 2;
+    }
+    if (!built)
+    {
+        std::string err;
+        int rc = ptbd_build_tlas_host(c->hNodes.data(), top, transforms, n, root.data(), mat.data(), slice, nullptr, err);
+        REQUIRE(rc == 0, rc, err);
+        if (onHost) c->lastRebuildWhere = 1;
+    }
+    // slots beyond the 2n the translator reserves do not exist in reference-made arrays; keep whatever a caller-provided array held there
+    std::vector<float> full(c->hNodes.begin() + (size_t)top * 9, c->hNodes.end());
+    memcpy(full.data(), slice.data(), slice.size() * sizeof(float));
+    return ptb_update_instances(c, transforms, numInstances, materials, numMaterials, full.data(), c->numNodes - top);
+}
+
+int ptb_last_rebuild_where(PtbCtx* c, int32_t* out) { REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument"); *out = c->lastRebuildWhere; return PTB_OK; }
 
 int ptb_update_envmap(PtbCtx* c, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum)
 {

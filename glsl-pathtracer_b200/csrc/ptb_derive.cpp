@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 namespace {
 
@@ -424,4 +425,128 @@ void ptbd_build_wide(const float* N, int numNodes, int topLevelIndex, int numInd
     out.rootMeta = rootOf(topLevelIndex, needTlas);
     out.stackDepth = std::max(4, 1 + needTlas + 1 + needBlas + 1);
     out.ok = B.ok && out.stackDepth <= 96 && out.wide.size() / 8 < (1u << 30);
+}
+
+// ------------------------------------------------------------------ TLAS rebuild (host, exact) ------------------------------------------------------------------
+void ptbd_instance_bounds(const float* N, const float* transforms, int numInstances, const int32_t* blasRoot, std::vector<float>& out)
+{
+    out.resize((size_t)numInstances * 6);
+    for (int i = 0; i < numInstances; i++)
+    {   // Scene.cpp:154-184: rows of the transform scaled by the box corners, component-wise min / max, sums left to right, then the translation
+        const float* b = N + (size_t)blasRoot[i] * 9;          // meshes[meshID]->bvh->Bounds() is the BLAS root's box
+        const float* M = transforms + (size_t)i * 16;
+        float lo[3], hi[3];
+        for (int c = 0; c < 3; c++)
+        {
+            const float xa = M[0 + c] * b[0], xb = M[0 + c] * b[3];
+            const float ya = M[4 + c] * b[1], yb = M[4 + c] * b[4];
+            const float za = M[8 + c] * b[2], zb = M[8 + c] * b[5];
+            lo[c] = ((std::min(xa, xb) + std::min(ya, yb)) + std::min(za, zb)) + M[12 + c];
+            hi[c] = ((std::max(xa, xb) + std::max(ya, yb)) + std::max(za, zb)) + M[12 + c];
+        }
+        float* o = &out[(size_t)i * 6];
+        o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+    }
+}
+
+namespace {
+
+struct Box3
+{
+    float lo[3], hi[3];
+    Box3() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<float>::max(); hi[a] = -std::numeric_limits<float>::max(); } }     // bbox() of bbox.h
+    void grow(const float* p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void growBox(const float* b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[3 + a]); } }
+    int maxdim() const
+    {   // bbox::maxdim (bbox.h)
+        const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        if (ex >= ey && ex >= ez) return 0;
+        if (ey >= ex && ey >= ez) return 1;
+        if (ez >= ex && ez >= ey) return 2;
+        return 0;
+    }
+};
+
+struct TlasBuilder
+{
+    const float* bounds; const float* cent; int* prim; float* out; int top; const int32_t* blasRoot; const int32_t* materialID;
+    int cur = 0, height = 0;
+
+    // Bvh::BuildNode (bvh.cpp:68-243, m_usesah == false) fused with ProcessTLASNodes (bvh_translator.cpp:58-86): both visit the nodes in the same pre-order
+    int build(int startidx, int numprims, const Box3& nb, const Box3& cb, int level)
+    {
+        height = std::max(height, level);
+        const int index = cur;
+        float* n = out + (size_t)index * 9;
+        n[0] = nb.lo[0]; n[1] = nb.lo[1]; n[2] = nb.lo[2]; n[3] = nb.hi[0]; n[4] = nb.hi[1]; n[5] = nb.hi[2];
+        if (numprims < 2)
+        {
+            const int inst = prim[startidx];
+            n[6] = (float)blasRoot[inst]; n[7] = (float)materialID[inst]; n[8] = (float)(-inst - 1);
+            return index;
+        }
+        const int axis = cb.maxdim();
+        const float border = (cb.hi[axis] + cb.lo[axis]) * 0.5f;                  // centroid_bounds.center()[axis]
+        Box3 lb, rb, lcb, rcb;
+        int splitidx = startidx;
+        const bool near2far = ((numprims + startidx) & 1) != 0;
+        if (cb.hi[axis] - cb.lo[axis] > 0.f)
+        {
+            int first = startidx, last = startidx + numprims;
+            auto C = [&](int i) { return cent[(size_t)prim[i] * 3 + axis]; };
+            auto growL = [&](int i) { lb.growBox(bounds + (size_t)prim[i] * 6); lcb.grow(cent + (size_t)prim[i] * 3); };
+            auto growR = [&](int i) { rb.growBox(bounds + (size_t)prim[i] * 6); rcb.grow(cent + (size_t)prim[i] * 3); };
+            while (true)
+            {   // the reference's in-place partition, both orientations (`near2far` puts the smaller centroids left)
+                while (first != last && (near2far ? C(first) < border : C(first) >= border)) { growL(first); ++first; }
+                if (first == last--) break;
+                growR(first);
+                while (first != last && (near2far ? C(last) >= border : C(last) < border)) { growR(last); --last; }
+                if (first == last) break;
+                growL(last);
+                std::swap(prim[first++], prim[last]);
+            }
+            splitidx = first;
+        }
+        if (splitidx == startidx || splitidx == startidx + numprims)
+        {
+            splitidx = startidx + (numprims >> 1);
+            // (the reference grows the boxes accumulated above further here, without resetting them)
+            for (int i = startidx; i < splitidx; ++i) { lb.growBox(bounds + (size_t)prim[i] * 6); lcb.grow(cent + (size_t)prim[i] * 3); }
+            for (int i = splitidx; i < startidx + numprims; ++i) { rb.growBox(bounds + (size_t)prim[i] * 6); rcb.grow(cent + (size_t)prim[i] * 3); }
+        }
+        n[8] = 0.f;
+        cur++;
+        const int l = build(startidx, splitidx - startidx, lb, lcb, level + 1);
+        cur++;
+        const int r = build(splitidx, numprims - (splitidx - startidx), rb, rcb, level + 1);
+        n = out + (size_t)index * 9;
+        n[6] = (float)(top + l); n[7] = (float)(top + r);
+        return index;
+    }
+};
+
+} // namespace
+
+int ptbd_build_tlas_host(const float* N, int topLevelIndex, const float* transforms, int numInstances, const int32_t* blasRoot, const int32_t* materialID,
+                         std::vector<float>& tlasOut, int* heightOut, std::string& err)
+{
+    DREQ(numInstances > 0, 1, "no instances");
+    std::vector<float> bounds; ptbd_instance_bounds(N, transforms, numInstances, blasRoot, bounds);
+    std::vector<float> cent((size_t)numInstances * 3);
+    std::vector<int> prim((size_t)numInstances);
+    Box3 all, call;
+    for (int i = 0; i < numInstances; i++)
+    {
+        const float* b = &bounds[(size_t)i * 6];
+        all.growBox(b);                                                             // Bvh::Build: m_bounds
+        for (int a = 0; a < 3; a++) cent[(size_t)i * 3 + a] = (b[3 + a] + b[a]) * 0.5f;       // bbox::center
+        call.grow(&cent[(size_t)i * 3]);
+        prim[(size_t)i] = i;
+    }
+    tlasOut.assign((size_t)numInstances * 2 * 9, 0.f);                              // BvhTranslator reserves 2 * numInstances slots (bvh_translator.cpp:97), 2n - 1 used
+    TlasBuilder B{bounds.data(), cent.data(), prim.data(), tlasOut.data(), topLevelIndex, blasRoot, materialID};
+    B.build(0, numInstances, all, call, 0);
+    if (heightOut) *heightOut = B.height;
+    return 0;
 }

@@ -40,6 +40,16 @@ struct PtbDerivedWide
     bool ok = false;
 };
 void ptbd_build_wide(const float* nodes, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, PtbDerivedWide& out);
+// TLAS rebuild after an instance edit — what Scene::RebuildInstances (Scene.cpp:200-214) does on the reference's host: instance world boxes from the BLAS
+// root boxes and the transforms (Scene::createTLAS, Scene.cpp:148-187), Bvh(10, 64, usesah = false)::Build (bvh.cpp:68-243: split at the centre of the
+// centroid bounds along their widest axis, one instance per leaf, children in DFS pre-order) and BvhTranslator::ProcessTLASNodes (bvh_translator.cpp:58-86).
+// Output: the canonical TLAS slice nodes[topLevelIndex ..] (9 floats per node, 2 * numInstances slots of which 2n-1 are used), byte-identical to the reference's.
+// blasRoot / materialID: per instance, the LRLeaf.x / LRLeaf.y its TLAS leaf carries.  This host version is the exact sequential algorithm (it is also the
+// fallback of the device builder for degenerate inputs, where the reference's in-place partition order matters).
+int ptbd_build_tlas_host(const float* nodes, int topLevelIndex, const float* transforms, int numInstances, const int32_t* blasRoot, const int32_t* materialID,
+                         std::vector<float>& tlasOut, int* heightOut, std::string& err);
+// the per-instance world boxes alone (6 floats each: min, max), the arithmetic of Scene.cpp:154-184
+void ptbd_instance_bounds(const float* nodes, const float* transforms, int numInstances, const int32_t* blasRoot, std::vector<float>& boundsOut);
 void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);
 // per-column / per-row pixel tables: {frame texture coordinate of the pixel centre (tile.glsl:43), bits(tile-local coordinate | tile index << 16)}
 int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err);

@@ -169,4 +169,7 @@ void ptbk_trace_closest_batch(const LaunchCfg&, const DevScene&, const FramePara
 void ptbk_trace_any_batch(const LaunchCfg&, const DevScene&, const FrameParams&, const float* rays, const float* maxDist, long long n, int* out);
 void ptbk_bsdf_batch(const LaunchCfg&, const void* queries, long long n, void* results, int sample);
 void ptbk_camera_rays(const LaunchCfg&, const FrameParams&, const WaveParams&, float* outRays);
+int  ptbk_tlas_build(const LaunchCfg&, float* nodes, int top, const float4* transforms, int n, const int* blasRoot, const int* materialID, float* instBounds, float* cent,
+                     int* nodeOf, void* recA, void* recB, void* recC, int* remap, int* result);     // rec buffers: (n + 2) records of ptbk_tlas_rec_size() bytes; remap: n + 2 ints
+int  ptbk_tlas_rec_size();
 int  ptbk_configure_device(const DevScene&, int* traceBlocks, int* shadowBlocks, int shadeBlocks[3]);   // per-device attributes; returns a cudaError_t value

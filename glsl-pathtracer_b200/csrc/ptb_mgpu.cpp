@@ -141,6 +141,12 @@ int ptb_mgpu_update_instances(PtbMgpu* m, const float* transforms, int32_t numIn
     EACH(ptb_update_instances(c, transforms, numInstances, materials, numMaterials, tlasNodes, numTlasNodes));
     return PTB_OK;
 }
+int ptb_mgpu_rebuild_instances(PtbMgpu* m, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials, const int32_t* instanceMaterialIDs, int32_t onHost)
+{
+    if (!m) return fail(PTB_ERR_INVALID_ARGUMENT, "null argument");
+    EACH(ptb_rebuild_instances(c, transforms, numInstances, materials, numMaterials, instanceMaterialIDs, onHost));
+    return PTB_OK;
+}
 int ptb_mgpu_update_envmap(PtbMgpu* m, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum)
 {
     if (!m) return fail(PTB_ERR_INVALID_ARGUMENT, "null argument");

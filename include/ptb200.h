@@ -127,6 +127,15 @@ int  ptb_set_camera(PtbCtx* ctx, const PtbCamera* cam);
  * nodes[topLevelIndex..numNodes) (9 floats each, numTlasNodes = numNodes - topLevelIndex). */
 int  ptb_update_instances(PtbCtx* ctx, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
                           const float* tlasNodes, int32_t numTlasNodes);
+/* Scene::RebuildInstances (Scene.cpp:200-214) + the upload above, from the TRANSFORMS alone: the TLAS is rebuilt by the library — on the device
+ * (k_tlas_build: instance world boxes of Scene::createTLAS, Scene.cpp:148-187; Bvh(10, 64, false)::Build, RadeonRays/bvh.cpp:68-243;
+ * BvhTranslator::ProcessTLASNodes, bvh_translator.cpp:58-86) — into the canonical node array, byte-identical to what the reference's host code builds
+ * (ptb_read_nodes shows it).  instanceMaterialIDs: per-instance material id (MeshInstance::materialID), NULL = unchanged.  onHost != 0, and inputs where the
+ * reference's in-place partition order matters (coincident centroids, -0.0 / non-finite boxes), use the exact sequential builder on the host instead;
+ * ptb_last_rebuild_where: 0 device, 1 host as asked, 2 host as fallback. */
+int  ptb_rebuild_instances(PtbCtx* ctx, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
+                           const int32_t* instanceMaterialIDs, int32_t onHost);
+int  ptb_last_rebuild_where(PtbCtx* ctx, int32_t* out);
 /* Renderer::Update envMapModified branch (Renderer.cpp:668-692). */
 int  ptb_update_envmap(PtbCtx* ctx, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum);
 
@@ -231,6 +240,8 @@ int  ptb_mgpu_set_camera(PtbMgpu* m, const PtbCamera* cam);
 int  ptb_mgpu_set_cull(PtbMgpu* m, int32_t enable);
 int  ptb_mgpu_update_instances(PtbMgpu* m, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
                                const float* tlasNodes, int32_t numTlasNodes);
+int  ptb_mgpu_rebuild_instances(PtbMgpu* m, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
+                                const int32_t* instanceMaterialIDs, int32_t onHost);                /* ptb_rebuild_instances on every GPU */
 int  ptb_mgpu_update_envmap(PtbMgpu* m, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum);
 int  ptb_mgpu_reset_accum(PtbMgpu* m);
 int  ptb_mgpu_render_samples(PtbMgpu* m, int32_t firstSample, int32_t nSamples);    /* passes [first, first+n) over all GPUs, asynchronous */

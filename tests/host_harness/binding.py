@@ -21,6 +21,7 @@ def lib():
         L.hh_trace_closest.argtypes = [vp, vp, C.c_longlong, i32, i32, vp]
         L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, vp]
         L.hh_wide_nodes.argtypes = [vp]
+        L.hh_build_tlas.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
         _LIB = L
     return _LIB
@@ -81,3 +82,15 @@ class HostTrav:
     def close(self):
         if self.h:
             lib().hh_destroy(self.h); self.h = None
+
+
+def build_tlas(nodes, top, transforms, material_ids=None):
+    """ptbd_build_tlas_host on a scene's arrays: returns (TLAS slice [2 * numInstances, 9] float32, height).  material_ids: per-instance material ids
+    (default: those of the current TLAS leaves)."""
+    nodes = np.ascontiguousarray(nodes, np.float32).reshape(-1, 9); tr = np.ascontiguousarray(transforms, np.float32).reshape(-1, 16)
+    out = np.zeros((2 * len(tr), 9), np.float32); h = C.c_int(0)
+    mid = None if material_ids is None else np.ascontiguousarray(material_ids, np.int32)
+    rc = lib().hh_build_tlas(nodes.ctypes.data, len(nodes), top, tr.ctypes.data, len(tr), None if mid is None else mid.ctypes.data, out.ctypes.data, C.byref(h))
+    if rc:
+        raise RuntimeError(f"ptbd_build_tlas_host failed: {rc}")
+    return out, h.value

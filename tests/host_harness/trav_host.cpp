@@ -133,4 +133,21 @@ void hh_camera_rays(int renderW, int renderH, int tileW, int tileH, const float*
     }
 }
 
+// TLAS rebuild (ptbd_build_tlas_host) from the scene's own arrays: blasRoot / materialID per instance are read from the current TLAS leaves
+int hh_build_tlas(const float* nodes, int numNodes, int topLevelIndex, const float* transforms, int numInstances, const int32_t* materialIDs, float* tlasOut, int* heightOut)
+{
+    std::vector<int32_t> root(numInstances, -1), mat(numInstances, 0);
+    for (int i = topLevelIndex; i < numNodes; i++)
+    {
+        const float* n = nodes + (size_t)i * 9;
+        if ((int)n[8] < 0 && -(int)n[8] - 1 < numInstances) { root[-(int)n[8] - 1] = (int)n[6]; mat[-(int)n[8] - 1] = (int)n[7]; }
+    }
+    if (materialIDs) mat.assign(materialIDs, materialIDs + numInstances);         // meshInstances[i].materialID as the application edited it
+    std::vector<float> out; std::string err;
+    int rc = ptbd_build_tlas_host(nodes, topLevelIndex, transforms, numInstances, root.data(), mat.data(), out, heightOut, err);
+    if (rc) return rc;
+    memcpy(tlasOut, out.data(), out.size() * sizeof(float));
+    return 0;
+}
+
 } // extern "C"

@@ -91,3 +91,32 @@ def test_render_options_update_without_recreate(oracle_mod):
     orc = oracle_mod.Oracle(sc2)
     assert rel_mse(orc.render(1, 2), b) <= 1e-3 and not np.allclose(a, b)
     ctx.close(); orc.close()
+
+
+def test_malformed_scenes_are_rejected_not_dereferenced():
+    """Scene validation at the boundary: a BLAS leaf that references triangles past the end of vertIndices, a TLAS leaf whose material id is out
+    of range, and a delta upload that shrinks the material table below an instance's id all return PTB_ERR_INVALID_ARGUMENT instead of reading out of bounds."""
+    from glsl_pathtracer_b200 import capi
+    sc = scene_at("cornell_box_orig", 32, 32, 16, 16)
+    nodes = np.ascontiguousarray(sc.nodes, np.float32).reshape(-1, 9)
+    bad = copy.deepcopy(sc); bad.nodes = nodes.copy()
+    leaf = np.nonzero(bad.nodes[:, 8] > 0)[0][0]
+    bad.nodes[leaf, 6] = len(sc.vertIndices) - 1; bad.nodes[leaf, 7] = 3           # first + count runs past the end
+    with pytest.raises(capi.PtbError) as e:
+        capi.Context(bad)
+    assert e.value.code == capi.PTB_ERR_INVALID_ARGUMENT
+    bad = copy.deepcopy(sc); bad.nodes = nodes.copy()
+    tl = np.nonzero(bad.nodes[:, 8] < 0)[0][0]
+    bad.nodes[tl, 7] = len(sc.materials) + 5                                         # TLAS leaf material id out of range
+    with pytest.raises(capi.PtbError) as e:
+        capi.Context(bad)
+    assert e.value.code == capi.PTB_ERR_INVALID_ARGUMENT
+    ctx = capi.Context(sc)
+    ctx.render_samples(1, 1)
+    before = ctx.read_accum()
+    with pytest.raises(capi.PtbError) as e:                                          # fewer materials than the instances reference
+        ctx.update_instances(sc.transforms, np.ascontiguousarray(sc.materials, np.float32)[:1], nodes[sc.topLevelIndex:])
+    assert e.value.code == capi.PTB_ERR_INVALID_ARGUMENT
+    ctx.reset_accum(); ctx.render_samples(1, 1)                                      # the context was left untouched by the rejected update
+    assert ctx.read_accum().tobytes() == before.tobytes()
+    ctx.close()

@@ -51,3 +51,29 @@ def test_host_compiled_traversal_equals_oracle(name, oracle_mod):
                 assert ht.fallbacks < 0.6 * len(ar)      # the generic rays really went through the wide hierarchy
     assert ht.stack_depth() <= 96
     ht.close(); orc.close(); orc_c.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_tlas_rebuild_is_byte_identical_to_the_reference(name):
+    """N3: the library's TLAS builder (instance world boxes, centre split, pre-order layout) applied to a scene's transforms reproduces the TLAS slice the
+    reference's own Scene::createTLAS + Bvh::Build + BvhTranslator::ProcessTLAS put into the fixture, byte for byte (10 001 instances in `instancing`)."""
+    from host_harness.binding import build_tlas
+    sc = scene_at(name, 64, 64)
+    nodes = np.ascontiguousarray(sc.nodes, np.float32).reshape(-1, 9)
+    tlas, height = build_tlas(nodes, sc.topLevelIndex, sc.transforms)
+    assert tlas.tobytes() == nodes[sc.topLevelIndex:].tobytes()
+    assert height + 1 == sc.tlasHeight          # the fixture counts levels, Bvh::m_height counts edges
+
+
+@pytest.mark.parametrize("name", ["cornell_box_orig", "hyperion_rect_lights"])
+def test_tlas_rebuild_after_an_instance_edit_matches_the_reference(name):
+    """... and for the instance edit the reference made itself (Scene::RebuildInstances on a moved + scaled instance, tests/golden/instance_edit.npz)."""
+    from conftest import edited_scene
+    from host_harness.binding import build_tlas
+    sc, sc2 = edited_scene(name, 64, 64)
+    nodes = np.ascontiguousarray(sc.nodes, np.float32).reshape(-1, 9)
+    want = np.ascontiguousarray(sc2.nodes, np.float32).reshape(-1, 9)[sc.topLevelIndex:]
+    leaves = want[want[:, 8] < 0]
+    mats = np.zeros(len(leaves), np.int32); mats[(-leaves[:, 8] - 1).astype(int)] = leaves[:, 7].astype(np.int32)     # meshInstances[i].materialID after the edit
+    tlas, _ = build_tlas(nodes, sc.topLevelIndex, sc2.transforms, mats)     # old node array (BLAS boxes, BLAS roots) + NEW transforms and material ids
+    assert tlas.tobytes() == want.tobytes()
