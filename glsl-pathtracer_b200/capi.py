@@ -67,7 +67,7 @@ SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_derive_features",
            "ptb_mgpu_create", "ptb_mgpu_destroy", "ptb_mgpu_num_devices", "ptb_mgpu_context", "ptb_mgpu_set_options", "ptb_mgpu_set_camera", "ptb_mgpu_set_cull",
            "ptb_mgpu_update_instances", "ptb_mgpu_update_envmap", "ptb_mgpu_reset_accum", "ptb_mgpu_render_samples", "ptb_mgpu_read_output_rgba8",
            "ptb_mgpu_read_accum_f32", "ptb_mgpu_get_stats", "ptb_mgpu_synchronize", "ptb_mgpu_render_pass", "ptb_mgpu_snapshot_output", "ptb_mgpu_read_snapshot_rgba8",
-           "ptb_snapshot_output_from", "ptb_set_snapshot_float", "ptb_read_snapshot_rgb32f", "ptb_mgpu_read_snapshot_rgb32f", "ptb_rebuild_instances", "ptb_last_rebuild_where", "ptb_mgpu_rebuild_instances"]
+           "ptb_snapshot_output_from", "ptb_set_snapshot_float", "ptb_read_snapshot_rgb32f", "ptb_mgpu_read_snapshot_rgb32f", "ptb_rebuild_instances", "ptb_last_rebuild_info", "ptb_mgpu_rebuild_instances"]
 
 _lib = None
 
@@ -97,7 +97,7 @@ def load():
         "ptb_bsdf_eval": [vp, vp, i64, vp], "ptb_bsdf_sample": [vp, vp, i64, vp], "ptb_lambert_eval": [vp, vp, i64, vp], "ptb_lambert_sample": [vp, vp, i64, vp], "ptb_camera_rays": [vp, i32, vp],
         "ptb_trace_closest_device": [vp, vp, i64, i32, vp], "ptb_read_nodes": [vp, vp, i32], "ptb_stack_depth": [vp, C.POINTER(i32)],
         "ptb_render_pass": [vp, i32, i32, i32], "ptb_snapshot_output_from": [vp, vp, f32], "ptb_set_snapshot_float": [vp, i32], "ptb_read_snapshot_rgb32f": [vp, vp], "ptb_mgpu_render_pass": [vp, i32, i32],
-        "ptb_mgpu_snapshot_output": [vp, f32], "ptb_mgpu_read_snapshot_rgba8": [vp, vp], "ptb_mgpu_read_snapshot_rgb32f": [vp, vp], "ptb_rebuild_instances": [vp, vp, i32, vp, i32, vp, i32], "ptb_last_rebuild_where": [vp, C.POINTER(i32)],
+        "ptb_mgpu_snapshot_output": [vp, f32], "ptb_mgpu_read_snapshot_rgba8": [vp, vp], "ptb_mgpu_read_snapshot_rgb32f": [vp, vp], "ptb_rebuild_instances": [vp, vp, i32, vp, i32, vp, i32], "ptb_last_rebuild_info": [vp, C.POINTER(i32)],
         "ptb_mgpu_rebuild_instances": [vp, vp, i32, vp, i32, vp, i32], "ptb_read_output_rgba8_from": [vp, vp, f32, vp], "ptb_snapshot_output": [vp, f32], "ptb_read_snapshot_rgba8": [vp, vp],
         "ptb_host_alloc": [C.c_uint64, C.POINTER(vp)], "ptb_host_free": [vp],
         "ptb_mgpu_create": [C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions), C.POINTER(i32), i32, C.POINTER(vp)], "ptb_mgpu_destroy": [vp],
@@ -257,8 +257,9 @@ class Context:
         t = np.ascontiguousarray(transforms, np.float32); m = np.ascontiguousarray(materials, np.float32)
         ids = None if material_ids is None else np.ascontiguousarray(material_ids, np.int32)
         check(load().ptb_rebuild_instances(self.h, _ptr(t), len(t.reshape(-1, 16)), _ptr(m), len(m.reshape(-1, 32)), None if ids is None else ids.ctypes.data, int(on_host)))
-        w = C.c_int32()
-        check(load().ptb_last_rebuild_where(self.h, C.byref(w)))
+        w, b, t = C.c_int32(), C.c_float(), C.c_float()
+        check(load().ptb_last_rebuild_info(self.h, C.byref(w), C.byref(b), C.byref(t)))
+        self.last_rebuild = {"where": w.value, "build_ms": b.value, "total_ms": t.value}
         return w.value
 
     def update_envmap(self, img, cdf, total):

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 static thread_local std::string g_err;
 extern "C" const char* ptb_last_error(void) { return g_err.c_str(); }
@@ -82,6 +83,7 @@ struct PtbCtx
     // device-side TLAS rebuild (ptb_rebuild_instances): per-instance BLAS root / material id, scratch of the builder
     DevBuf<int> tlasBlasRoot, tlasMatID, tlasNodeOf, tlasRemap, tlasResult; DevBuf<float> tlasBounds, tlasCent; DevBuf<char> tlasRec[3];
     int lastRebuildWhere = -1;   // 0 device, 1 host (asked for), 2 host (fallback of the device builder)
+    float lastRebuildBuildMs = 0.f, lastRebuildTotalMs = 0.f;    // TLAS build alone (kernel: CUDA events; host builder: wall clock) / the whole call
     int wideAny = 1;           // 1: shadow rays use the 4-wide any-hit hierarchy where it is provably equivalent (PTB_WIDE_ANY)
     DevBuf<float4> verticesUVX, normalsUVY, materials, transforms, inner, tris, instTrav, instShade, lightsPre, lightGroups;
     DevBuf<uchar4> textures;
@@ -618,39 +620,56 @@ int ptb_rebuild_instances(PtbCtx* c, const float* transforms, int32_t numInstanc
     }
     std::vector<float> slice;
     bool built = false;
+    const auto tAll = std::chrono::steady_clock::now();
     if (!onHost)
     {   // k_tlas_build writes the slice straight into the canonical device node array; it is read back for the host-side derivation of the packed layouts
         const size_t recBytes = (size_t)ptbk_tlas_rec_size() * ((size_t)n + 2);
         CK(c->tlasBlasRoot.upload(root.data(), (size_t)n, c->stream)); CK(c->tlasMatID.upload(mat.data(), (size_t)n, c->stream));
         CK(c->transforms.upload((const float4*)transforms, (size_t)n * 4, c->stream));
-        CK(c->tlasNodeOf.alloc((size_t)n)); CK(c->tlasRemap.alloc((size_t)n + 2)); CK(c->tlasResult.alloc(2));
+        CK(c->tlasNodeOf.alloc((size_t)n)); CK(c->tlasRemap.alloc((size_t)n + 2)); CK(c->tlasResult.alloc(4));
+        CK(cudaMemsetAsync(c->tlasResult.p, 0, 4 * sizeof(int), c->stream));
         CK(c->tlasBounds.alloc((size_t)n * 6)); CK(c->tlasCent.alloc((size_t)n * 3));
         for (int k = 0; k < 3; k++) CK(c->tlasRec[k].alloc(recBytes));
-        ptbk_tlas_build(cfg(c), c->nodes.p, top, c->transforms.p, n, c->tlasBlasRoot.p, c->tlasMatID.p, c->tlasBounds.p, c->tlasCent.p, c->tlasNodeOf.p,
-                        c->tlasRec[0].p, c->tlasRec[1].p, c->tlasRec[2].p, c->tlasRemap.p, c->tlasResult.p);
+        cudaEventRecord(c->evStart, c->stream);
+        CK((cudaError_t)ptbk_tlas_build(cfg(c), c->nodes.p, top, c->transforms.p, n, c->tlasBlasRoot.p, c->tlasMatID.p, c->tlasBounds.p, c->tlasCent.p, c->tlasNodeOf.p,
+                                        c->tlasRec[0].p, c->tlasRec[1].p, c->tlasRec[2].p, c->tlasRemap.p, c->tlasResult.p));
+        cudaEventRecord(c->evStop, c->stream);
+        c->timingValid = false;
         CK(cudaGetLastError());
         int res[2] = {1, 0};
         slice.resize((size_t)2 * n * 9);
         CK(cudaMemcpyAsync(res, c->tlasResult.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(slice.data(), c->nodes.p + (size_t)top * 9, slice.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        cudaEventElapsedTime(&c->lastRebuildBuildMs, c->evStart, c->evStop);
         built = res[0] == 0;            // flag: an input where the reference's element order matters (or -0.0 / non-finite boxes) -> exact sequential build below
         c->lastRebuildWhere = built ? 0 : 2;
     }
     if (!built)
     {
         std::string err;
+        const auto t0 = std::chrono::steady_clock::now();
         int rc = ptbd_build_tlas_host(c->hNodes.data(), top, transforms, n, root.data(), mat.data(), slice, nullptr, err);
         REQUIRE(rc == 0, rc, err);
+        c->lastRebuildBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (onHost) c->lastRebuildWhere = 1;
     }
     // slots beyond the 2n the translator reserves do not exist in reference-made arrays; keep whatever a caller-provided array held there
     std::vector<float> full(c->hNodes.begin() + (size_t)top * 9, c->hNodes.end());
     memcpy(full.data(), slice.data(), slice.size() * sizeof(float));
-    return ptb_update_instances(c, transforms, numInstances, materials, numMaterials, full.data(), c->numNodes - top);
+    int rc = ptb_update_instances(c, transforms, numInstances, materials, numMaterials, full.data(), c->numNodes - top);
+    c->lastRebuildTotalMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tAll).count();
+    return rc;
 }
 
-int ptb_last_rebuild_where(PtbCtx* c, int32_t* out) { REQUIRE(c && out, PTB_ERR_INVALID_ARGUMENT, "null argument"); *out = c->lastRebuildWhere; return PTB_OK; }
+int ptb_last_rebuild_info(PtbCtx* c, int32_t* where, float* buildMs, float* totalMs)
+{
+    REQUIRE(c, PTB_ERR_INVALID_ARGUMENT, "null argument");
+    if (where) *where = c->lastRebuildWhere;
+    if (buildMs) *buildMs = c->lastRebuildBuildMs;
+    if (totalMs) *totalMs = c->lastRebuildTotalMs;
+    return PTB_OK;
+}
 
 int ptb_update_envmap(PtbCtx* c, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum)
 {

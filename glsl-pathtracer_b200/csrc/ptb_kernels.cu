@@ -10,6 +10,7 @@
 //   k_accumulate  tile.glsl:70-74      sum of the wave's samples into the running-sum buffer
 //   k_tonemap     tonemap.glsl         on readback
 #include "ptb_device.cuh"
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1239,12 +1240,38 @@ void ptbk_camera_rays(const LaunchCfg& c, const FrameParams& F, const WaveParams
 // every instance carries the record id of the node it currently sits in, and one level is  classify -> count + grow the child records with atomics -> emit nodes.
 // The cases where the reference's element ORDER matters (a side stays empty: coincident centroids or a centre that rounds onto an end; -0.0 / non-finite
 // coordinates) raise a flag and the host rebuilds with the sequential algorithm.
+constexpr int TLAS_THREADS = 512;
 struct TlasRec { int start, count, dfs, lastPrim; unsigned key[12]; };      // key: bounds min.xyz, max.xyz, centroid min.xyz, max.xyz as order-preserving uints
 
 __device__ __forceinline__ unsigned fkey(float f) { unsigned b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
 __device__ __forceinline__ float keyf(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
 __device__ __forceinline__ float stdmin(float a, float b) { return b < a ? b : a; }       // std::min / std::max as Vec3::Min / Max use them
 __device__ __forceinline__ float stdmax(float a, float b) { return a < b ? b : a; }
+
+// grow record q by one instance's box / centroid keys.  `peers` = lanes of this warp that grow the SAME record (at the top levels whole warps do): they are
+// reduced with redux.sync first, one lane issues the 12 atomics — without this the first levels serialise 14 atomics per instance on two records.
+__device__ __forceinline__ void tlasGrow(TlasRec& q, unsigned peers, int i, const unsigned (&k)[12])
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const bool leader = lane == (unsigned)(__ffs((int)peers) - 1);
+    if (__popc(peers) == 1)
+    {
+        atomicAdd(&q.count, 1); q.lastPrim = i;
+        for (int a = 0; a < 3; a++) { atomicMin(&q.key[a], k[a]); atomicMax(&q.key[3 + a], k[3 + a]); atomicMin(&q.key[6 + a], k[6 + a]); atomicMax(&q.key[9 + a], k[9 + a]); }
+        return;
+    }
+    unsigned r[12];
+    for (int a = 0; a < 3; a++)
+    {
+        r[a] = __reduce_min_sync(peers, k[a]); r[3 + a] = __reduce_max_sync(peers, k[3 + a]);
+        r[6 + a] = __reduce_min_sync(peers, k[6 + a]); r[9 + a] = __reduce_max_sync(peers, k[9 + a]);
+    }
+    if (leader)
+    {
+        atomicAdd(&q.count, __popc(peers)); q.lastPrim = i;
+        for (int a = 0; a < 3; a++) { atomicMin(&q.key[a], r[a]); atomicMax(&q.key[3 + a], r[3 + a]); atomicMin(&q.key[6 + a], r[6 + a]); atomicMax(&q.key[9 + a], r[9 + a]); }
+    }
+}
 
 __device__ __forceinline__ void tlasEmitLeaf(float* out, int top, const TlasRec& r, const float* __restrict__ instBounds, const int* __restrict__ blasRoot, const int* __restrict__ materialID)
 {
@@ -1255,25 +1282,31 @@ __device__ __forceinline__ void tlasEmitLeaf(float* out, int top, const TlasRec&
     n[6] = (float)blasRoot[inst]; n[7] = (float)materialID[inst]; n[8] = (float)(-inst - 1);
 }
 
-// one CTA builds the whole TLAS (levels are separated by block barriers; 10^4 instances: ~0.2 ms, 10^5: ~2 ms)
-__global__ void __launch_bounds__(1024) k_tlas_build(float* __restrict__ nodes, int top, const float4* __restrict__ transforms, int n, const int* __restrict__ blasRoot,
+// Cooperative launch, one CTA per SM: the levels (and the phases inside a level) are separated by grid-wide barriers.
+__global__ void __launch_bounds__(TLAS_THREADS) k_tlas_build(float* __restrict__ nodes, int top, const float4* __restrict__ transforms, int n, const int* __restrict__ blasRoot,
                                                       const int* __restrict__ materialID, float* __restrict__ instBounds, float* __restrict__ cent, int* __restrict__ nodeOf,
-                                                      TlasRec* recA, TlasRec* recB, TlasRec* recC, int* __restrict__ remap, int* __restrict__ result /* [0] fallback flag, [1] height */)
+                                                      TlasRec* recA, TlasRec* recB, TlasRec* recC, int* __restrict__ remap, int* result /* [0] fallback flag, [1] height, [2] nodes of the next level; zeroed by the host */)
 {
-    __shared__ int sFlag, sActive, sHeight;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { sFlag = 0; sHeight = 0; }
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    volatile int* vres = result;
+#define sFlag (vres[0])
+#define sActive (result[2])
     const unsigned EMPTY_LO = fkey(3.402823466e+38f), EMPTY_HI = fkey(-3.402823466e+38f);
     TlasRec* cur = recA; TlasRec* nxt = recB; TlasRec* cmp = recC;      // this level's internal nodes (compact) / their children (2 per node) / next level (compact)
-    if (tid == 0) { TlasRec r; r.start = 0; r.count = n; r.dfs = 0; r.lastPrim = 0; for (int a = 0; a < 3; a++) { r.key[a] = EMPTY_LO; r.key[3 + a] = EMPTY_HI; r.key[6 + a] = EMPTY_LO; r.key[9 + a] = EMPTY_HI; } cur[0] = r; }
-    __syncthreads();
+    if (tid == 0) { TlasRec r; r.start = 0; r.count = 0 /* counted by tlasGrow */; r.dfs = 0; r.lastPrim = 0; for (int a = 0; a < 3; a++) { r.key[a] = EMPTY_LO; r.key[3 + a] = EMPTY_HI; r.key[6 + a] = EMPTY_LO; r.key[9 + a] = EMPTY_HI; } cur[0] = r; }
+    grid.sync();
     // instance world boxes and centroids (Scene.cpp:154-184, bbox::center), root bounds (Bvh::Build / BuildImpl)
-    for (int i = tid; i < n; i += nt)
-    {
+    for (int base = tid & ~31; base < n; base += nt)
+    {   // (warp-uniform trip count: the aggregation in tlasGrow uses warp collectives)
+        const int i = base + (tid & 31);
+        const unsigned live = __ballot_sync(0xffffffffu, i < n);
+        if (i >= n) continue;
         const float* b = nodes + (size_t)blasRoot[i] * 9;
         const float4 r0 = transforms[(size_t)i * 4], r1 = transforms[(size_t)i * 4 + 1], r2 = transforms[(size_t)i * 4 + 2], r3 = transforms[(size_t)i * 4 + 3];
         const float R[3] = {r0.x, r0.y, r0.z}, U[3] = {r1.x, r1.y, r1.z}, Fw[3] = {r2.x, r2.y, r2.z}, T[3] = {r3.x, r3.y, r3.z};
         bool bad = false;
+        unsigned rk[12];
         for (int c = 0; c < 3; c++)
         {
             const float xa = __fmul_rn(R[c], b[0]), xb = __fmul_rn(R[c], b[3]), ya = __fmul_rn(U[c], b[1]), yb = __fmul_rn(U[c], b[4]), za = __fmul_rn(Fw[c], b[2]), zb = __fmul_rn(Fw[c], b[5]);
@@ -1283,13 +1316,13 @@ __global__ void __launch_bounds__(1024) k_tlas_build(float* __restrict__ nodes, 
             instBounds[(size_t)i * 6 + c] = lo; instBounds[(size_t)i * 6 + 3 + c] = hi; cent[(size_t)i * 3 + c] = ce;
             // order-free unions need: finite values and no negative zero (std::min keeps the FIRST of +0 / -0 it meets)
             bad |= !(fabsf(lo) <= 3.0e38f) || !(fabsf(hi) <= 3.0e38f) || __float_as_uint(lo) == 0x80000000u || __float_as_uint(hi) == 0x80000000u || __float_as_uint(ce) == 0x80000000u;
-            atomicMin(&cur[0].key[c], fkey(lo)); atomicMax(&cur[0].key[3 + c], fkey(hi)); atomicMin(&cur[0].key[6 + c], fkey(ce)); atomicMax(&cur[0].key[9 + c], fkey(ce));
+            rk[c] = fkey(lo); rk[3 + c] = fkey(hi); rk[6 + c] = fkey(ce); rk[9 + c] = fkey(ce);
         }
-        if (bad) sFlag = 1;
+        if (bad) vres[0] = 1;
         nodeOf[i] = 0;
-        cur[0].lastPrim = i;        // (n == 1: the root is a leaf holding this instance)
+        tlasGrow(cur[0], live, i, rk);        // root bounds (n == 1: the root is a leaf holding this instance: lastPrim)
     }
-    __syncthreads();
+    grid.sync();
     int numCur = 1, level = 0;
     if (n == 1) { if (tid == 0) tlasEmitLeaf(nodes, top, cur[0], instBounds, blasRoot, materialID); numCur = 0; }
     while (numCur > 0 && !sFlag)
@@ -1302,37 +1335,46 @@ __global__ void __launch_bounds__(1024) k_tlas_build(float* __restrict__ nodes, 
             for (int a = 0; a < 3; a++) { l.key[a] = EMPTY_LO; l.key[3 + a] = EMPTY_HI; l.key[6 + a] = EMPTY_LO; l.key[9 + a] = EMPTY_HI; }
             nxt[j] = l;
         }
-        if (tid == 0) sActive = 0;
-        __syncthreads();
+        if (tid == 0) vres[2] = 0;
+        grid.sync();
         // phase 2: classify every instance that sits in an internal node (bvh.cpp:97-98, 150-206) and grow its child's record
-        for (int i = tid; i < n; i += nt)
+        for (int base = tid & ~31; base < n; base += nt)
         {
-            const int j = nodeOf[i];
-            if (j < 0) continue;                                             // already in a leaf
-            const TlasRec& p = cur[j];
-            float clo[3], chi[3];
-            for (int a = 0; a < 3; a++) { clo[a] = keyf(p.key[6 + a]); chi[a] = keyf(p.key[9 + a]); }
-            const float ex = __fsub_rn(chi[0], clo[0]), ey = __fsub_rn(chi[1], clo[1]), ez = __fsub_rn(chi[2], clo[2]);
-            const int axis = (ex >= ey && ex >= ez) ? 0 : ((ey >= ex && ey >= ez) ? 1 : ((ez >= ex && ez >= ey) ? 2 : 0));      // bbox::maxdim
-            const float border = __fmul_rn(__fadd_rn(chi[axis], clo[axis]), 0.5f);                                          // centroid_bounds.center()[axis]
-            const float ext = axis == 0 ? ex : (axis == 1 ? ey : ez);
-            if (!(ext > 0.f)) { sFlag = 1; continue; }                        // the reference splits by position then: order matters
-            const bool near2far = ((p.count + p.start) & 1) != 0;
-            const float c = cent[(size_t)i * 3 + axis];
-            const bool left = near2far ? (c < border) : (c >= border);
-            const int child = 2 * j + (left ? 0 : 1);
-            TlasRec& q = nxt[child];
-            atomicAdd(&q.count, 1);
-            q.lastPrim = i;
-            for (int a = 0; a < 3; a++)
+            const int i = base + (tid & 31);
+            const int j = i < n ? nodeOf[i] : -1;                            // -1: already in a leaf
+            int child = -1;
+            if (j >= 0)
             {
-                atomicMin(&q.key[a], fkey(instBounds[(size_t)i * 6 + a])); atomicMax(&q.key[3 + a], fkey(instBounds[(size_t)i * 6 + 3 + a]));
-                const unsigned ck = fkey(cent[(size_t)i * 3 + a]);
-                atomicMin(&q.key[6 + a], ck); atomicMax(&q.key[9 + a], ck);
+                const TlasRec& p = cur[j];
+                float clo[3], chi[3];
+                for (int a = 0; a < 3; a++) { clo[a] = keyf(p.key[6 + a]); chi[a] = keyf(p.key[9 + a]); }
+                const float ex = __fsub_rn(chi[0], clo[0]), ey = __fsub_rn(chi[1], clo[1]), ez = __fsub_rn(chi[2], clo[2]);
+                const int axis = (ex >= ey && ex >= ez) ? 0 : ((ey >= ex && ey >= ez) ? 1 : ((ez >= ex && ez >= ey) ? 2 : 0));      // bbox::maxdim
+                const float border = __fmul_rn(__fadd_rn(chi[axis], clo[axis]), 0.5f);                                          // centroid_bounds.center()[axis]
+                const float ext = axis == 0 ? ex : (axis == 1 ? ey : ez);
+                if (!(ext > 0.f)) vres[0] = 1;                                  // the reference splits by position then: order matters
+                else
+                {
+                    const bool near2far = ((p.count + p.start) & 1) != 0;
+                    const float c = cent[(size_t)i * 3 + axis];
+                    const bool left = near2far ? (c < border) : (c >= border);
+                    child = 2 * j + (left ? 0 : 1);
+                }
             }
-            nodeOf[i] = child;
+            const unsigned growing = __ballot_sync(0xffffffffu, child >= 0);
+            if (child >= 0)
+            {
+                unsigned k[12];
+                for (int a = 0; a < 3; a++)
+                {
+                    k[a] = fkey(instBounds[(size_t)i * 6 + a]); k[3 + a] = fkey(instBounds[(size_t)i * 6 + 3 + a]);
+                    k[6 + a] = k[9 + a] = fkey(cent[(size_t)i * 3 + a]);
+                }
+                tlasGrow(nxt[child], __match_any_sync(growing, child), i, k);
+                nodeOf[i] = child;
+            }
         }
-        __syncthreads();
+        grid.sync();
         // phase 3: emit the internal nodes of this level and the leaves among their children; number the children in pre-order; the children that are
         // internal nodes themselves form the next level (compacted into cmp, remap = child record -> index there, -1 for leaves)
         for (int j = tid; j < numCur; j += nt)
@@ -1340,7 +1382,7 @@ __global__ void __launch_bounds__(1024) k_tlas_build(float* __restrict__ nodes, 
             const TlasRec p = cur[j];
             TlasRec& l = nxt[2 * j]; TlasRec& r = nxt[2 * j + 1];
             remap[2 * j] = -1; remap[2 * j + 1] = -1;
-            if (l.count == 0 || r.count == 0) { sFlag = 1; continue; }       // a side stayed empty: the reference falls back to a split by position
+            if (l.count == 0 || r.count == 0) { vres[0] = 1; continue; }       // a side stayed empty: the reference falls back to a split by position
             l.start = p.start; r.start = p.start + l.count;
             l.dfs = p.dfs + 1; r.dfs = p.dfs + 2 * l.count;                   // a subtree with k single-instance leaves has 2k - 1 nodes
             float* o = nodes + (size_t)(top + p.dfs) * 9;
@@ -1350,25 +1392,29 @@ __global__ void __launch_bounds__(1024) k_tlas_build(float* __restrict__ nodes, 
             else { const int k = atomicAdd(&sActive, 1); cmp[k] = l; remap[2 * j] = k; }
             if (r.count == 1) tlasEmitLeaf(nodes, top, r, instBounds, blasRoot, materialID);
             else { const int k = atomicAdd(&sActive, 1); cmp[k] = r; remap[2 * j + 1] = k; }
-            atomicMax(&sHeight, level + 1);
+            atomicMax(&result[1], level + 1);
         }
-        __syncthreads();
+        grid.sync();
         for (int i = tid; i < n; i += nt) { const int j = nodeOf[i]; if (j >= 0) nodeOf[i] = remap[j]; }
-        numCur = sActive;
+        numCur = vres[2];
         TlasRec* t = cur; cur = cmp; cmp = t;
         level++;
-        __syncthreads();
+        grid.sync();
     }
     // the slot BvhTranslator reserves but never uses (2n slots, 2n - 1 nodes) stays zero, as nodes.resize() leaves it
     if (tid < 9) nodes[(size_t)(top + 2 * n - 1) * 9 + tid] = 0.f;
-    if (tid == 0) { result[0] = sFlag; result[1] = sHeight; }
+#undef sFlag
+#undef sActive
 }
 
 int ptbk_tlas_build(const LaunchCfg& c, float* nodes, int top, const float4* transforms, int n, const int* blasRoot, const int* materialID, float* instBounds, float* cent,
                     int* nodeOf, void* recA, void* recB, void* recC, int* remap, int* result)
 {
-    k_tlas_build<<<1, 1024, 0, st(c)>>>(nodes, top, transforms, n, blasRoot, materialID, instBounds, cent, nodeOf, (TlasRec*)recA, (TlasRec*)recB, (TlasRec*)recC, remap, result);
+    TlasRec* a = (TlasRec*)recA; TlasRec* b = (TlasRec*)recB; TlasRec* cc = (TlasRec*)recC;
+    void* args[] = {&nodes, &top, &transforms, &n, &blasRoot, &materialID, &instBounds, &cent, &nodeOf, &a, &b, &cc, &remap, &result};
+    // one CTA per SM is always co-resident (32 registers, no shared memory): the grid barrier cannot deadlock
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tlas_build, dim3(c.numSMs), dim3(TLAS_THREADS), args, 0, st(c));
     COUNT_LAUNCH(c, 1);
-    return (int)sizeof(TlasRec);
+    return (int)e;
 }
 int ptbk_tlas_rec_size() { return (int)sizeof(TlasRec); }

@@ -15,6 +15,11 @@ namespace GLSLPT
     void SetDenoiserB200(DenoiseFnB200 fn, void* user);
     const float* DenoisedImageB200(Renderer& r);          // what the reference uploads to denoisedTexture (nullptr before the first run)
     PtbMgpu* MgpuOfB200(Renderer& r);
+    // Scene::RebuildInstances (Scene.cpp:200-214) without the host BVH build: copies meshInstances[i].transform into scene->transforms, lets the library rebuild the
+    // TLAS ON THE DEVICE(S) from the transforms and material ids (ptb_mgpu_rebuild_instances: byte-identical to what sceneBvh->Build + bvhTranslator.UpdateTLAS produce),
+    // reads the slice back into scene->bvhTranslator.nodes so that the Scene stays consistent, and marks the scene dirty.  Call it where the application calls
+    // scene->RebuildInstances() (Main.cpp:505); instancesModified stays false — the contexts are already up to date.
+    void RebuildInstancesB200(Renderer& r, Scene* scene);
 
     // Equivalent to n * numTiles.x * numTiles.y Update()+Render() pairs on a non-dirty scene, as ONE wavefront per batch of passes.
     void RenderSamplesB200(Renderer& r, Scene* scene, int n);

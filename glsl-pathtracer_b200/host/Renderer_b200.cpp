@@ -331,6 +331,22 @@ namespace GLSLPT
         RendererB200Access::advance(r, n);
         check(ptb_mgpu_snapshot_output(sd.m, 1.0f / (float)(first + n - 1)), "ptb_snapshot_output");
     }
+    void RebuildInstancesB200(Renderer& r, Scene* scene)
+    {
+        Side& sd = table()[&r];
+        const int n = (int)scene->meshInstances.size();
+        std::vector<int32_t> mats((size_t)n);
+        for (int i = 0; i < n; i++) { scene->transforms[i] = scene->meshInstances[i].transform; mats[(size_t)i] = scene->meshInstances[i].materialID; }     // Scene.cpp:208-210
+        check(ptb_mgpu_rebuild_instances(sd.m, (const float*)scene->transforms.data(), n, (const float*)scene->materials.data(), (int)scene->materials.size(), mats.data(), 0),
+              "ptb_rebuild_instances");
+        // keep the Scene's copy of the node array in step with the devices' (what bvhTranslator.UpdateTLAS would have written)
+        std::vector<float> nodes(scene->bvhTranslator.nodes.size() * 9);
+        check(ptb_read_nodes(sd.ctx0, nodes.data(), (int)scene->bvhTranslator.nodes.size()), "ptb_read_nodes");
+        const int top = scene->bvhTranslator.topLevelIndex;
+        memcpy(&scene->bvhTranslator.nodes[top], &nodes[(size_t)top * 9], (scene->bvhTranslator.nodes.size() - (size_t)top) * 9 * sizeof(float));
+        scene->instancesModified = false;
+        scene->dirty = true;
+    }
     PtbCtx* ContextOfB200(Renderer& r) { return table()[&r].ctx0; }
     PtbMgpu* MgpuOfB200(Renderer& r) { return table()[&r].m; }
     void SetDevicesB200(const int* devices, int n) { configuredDevices().assign(devices, devices + (n > 0 ? n : 0)); }

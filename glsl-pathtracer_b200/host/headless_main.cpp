@@ -21,6 +21,7 @@ int main(int argc, char** argv)
     std::string sceneFile, out = "out.png", accumOut;
     int spp = 16, w = 0, h = 0, depth = -1, warmup = 0, denoiseEvery = 0; bool whole = false;
     static int denoiseCalls = 0; static double denoiseInSum = 0.0;
+    int editInst = -1; float editD[3] = {0, 0, 0}; bool editOnDevice = false;
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i];
@@ -34,6 +35,8 @@ int main(int argc, char** argv)
         else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);          // passes rendered before the clock starts (same loop)
         else if (a == "--no-coalesce") setenv("PTB_COALESCE", "0", 1);               // one wavefront per Render() tile, as the reference draws
         else if (a == "--devices" && i + 1 < argc) setenv("PTB_DEVICES", argv[++i], 1);   // "0,1,2,3"
+        else if (a == "--edit-instance" && i + 5 < argc)      // K DX DY DZ device|host: move instance K before rendering, TLAS rebuilt by the library on the GPU or by the reference on the host
+        { editInst = atoi(argv[++i]); for (int k = 0; k < 3; k++) editD[k] = (float)atof(argv[++i]); editOnDevice = std::string(argv[++i]) == "device"; }
         else if (a == "--denoise-every" && i + 1 < argc) denoiseEvery = atoi(argv[++i]);  // exercise the denoiser hook with a stand-in filter
         else { printf("usage: ptb_headless -s file.scene [-o out.png] [--spp N] [--warmup N] [--res W H] [--depth D] [--whole-frame] [--no-coalesce] "
                       "[--devices 0,1,..] [--denoise-every N] [--accum file.f32]\n"); return 2; }
@@ -61,6 +64,13 @@ int main(int argc, char** argv)
         SetDenoiserB200([](const float* in, float* out, int w_, int h_, void*) { denoiseCalls++; denoiseInSum = 0.0; for (size_t i = 0; i < (size_t)w_ * h_ * 3; i++) denoiseInSum += in[i]; memcpy(out, in, (size_t)w_ * h_ * 12); }, nullptr);
 
     Renderer* renderer = new Renderer(scene, "shaders/");
+    if (editInst >= 0 && editInst < (int)scene->meshInstances.size())
+    {   // what the application does when an instance is dragged (Main.cpp:495-510): edit the transform, then rebuild the instances
+        Mat4& m = scene->meshInstances[editInst].transform;
+        m[3][0] += editD[0]; m[3][1] += editD[1]; m[3][2] += editD[2];
+        if (editOnDevice) RebuildInstancesB200(*renderer, scene);       // TLAS rebuilt on the device from the transforms
+        else scene->RebuildInstances();                                  // the reference's host rebuild; Update() uploads its slice (instancesModified)
+    }
     auto t0 = std::chrono::steady_clock::now();
     unsigned char* data = nullptr; int ow, oh;
     PtbStats st0{}; long long updates = 0;

@@ -132,10 +132,11 @@ int  ptb_update_instances(PtbCtx* ctx, const float* transforms, int32_t numInsta
  * BvhTranslator::ProcessTLASNodes, bvh_translator.cpp:58-86) — into the canonical node array, byte-identical to what the reference's host code builds
  * (ptb_read_nodes shows it).  instanceMaterialIDs: per-instance material id (MeshInstance::materialID), NULL = unchanged.  onHost != 0, and inputs where the
  * reference's in-place partition order matters (coincident centroids, -0.0 / non-finite boxes), use the exact sequential builder on the host instead;
- * ptb_last_rebuild_where: 0 device, 1 host as asked, 2 host as fallback. */
+ * ptb_last_rebuild_info: where = 0 device, 1 host as asked, 2 host as fallback; buildMs = the TLAS build alone (kernel time / host builder time),
+ * totalMs = the whole call incl. the derivation and upload of the packed layouts. */
 int  ptb_rebuild_instances(PtbCtx* ctx, const float* transforms, int32_t numInstances, const float* materials, int32_t numMaterials,
                            const int32_t* instanceMaterialIDs, int32_t onHost);
-int  ptb_last_rebuild_where(PtbCtx* ctx, int32_t* out);
+int  ptb_last_rebuild_info(PtbCtx* ctx, int32_t* where, float* buildMs, float* totalMs);
 /* Renderer::Update envMapModified branch (Renderer.cpp:668-692). */
 int  ptb_update_envmap(PtbCtx* ctx, const float* img, const float* cdf, int32_t w, int32_t h, float totalSum);
 

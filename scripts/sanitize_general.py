@@ -27,3 +27,12 @@ for name, sc in cases:
     ctx.trace_closest(rays); ctx.trace_any(rays, 1e6)
     print(name, "ok", float(np.nan_to_num(a[..., :3]).mean()), ctx.stats()["kernelLaunches"], "launches")
     ctx.close()
+# device-side TLAS rebuild (cooperative launch) on a scene with many instances and on a small one, then render
+for name in ("instancing", "cornell_box_orig"):
+    sc = scene_at(name, 48, 27, 24, 14)
+    ctx = capi.Context(sc)
+    T = np.ascontiguousarray(sc.transforms, np.float32).reshape(-1, 16).copy(); T[:, 12] += 0.25
+    where = ctx.rebuild_instances(T, sc.materials)
+    ctx.render_samples(1, 1)
+    print("rebuild", name, "built at", where, float(np.nan_to_num(ctx.read_accum()[..., :3]).mean()))
+    ctx.close()

@@ -86,3 +86,20 @@ def test_cpp_dropin_on_two_gpus(tmp_path):
         assert b["gpus"] == k + 1
         accs.append(np.fromfile(acc, np.float32))
     np.testing.assert_allclose(accs[0], accs[1], rtol=2e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not (os.path.exists(BIN) and os.path.isdir(ASSETS)), reason="host/build/ptb_headless or assets not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("scene,inst", [("hyperion_rect_lights", 3), ("cornell_box_orig", 6)])
+def test_device_rebuild_equals_the_references_host_rebuild_in_the_cpp_dropin(scene, inst, tmp_path):
+    """An instance is moved as the application moves it; the TLAS is rebuilt once by the reference's own Scene::RebuildInstances (host BVH build, slice uploaded by
+    Update()) and once by RebuildInstancesB200 (device build from the transforms): the renders are bitwise equal."""
+    accs = []
+    for mode in ("host", "device"):
+        acc = str(tmp_path / f"{mode}.f32")
+        _run(["-s", os.path.join(ASSETS, scene + ".scene"), "-o", str(tmp_path / f"{mode}.png"), "--spp", "3", "--res", "320", "180", "--accum", acc,
+              "--edit-instance", str(inst), "0.3", "0.1", "-0.2", mode])
+        accs.append(np.fromfile(acc, np.float32))
+    assert accs[0].tobytes() == accs[1].tobytes() and np.isfinite(accs[0]).all() and accs[0].max() > 0
+    base = str(tmp_path / "base.f32")
+    _run(["-s", os.path.join(ASSETS, scene + ".scene"), "-o", str(tmp_path / "base.png"), "--spp", "3", "--res", "320", "180", "--accum", base])
+    assert np.fromfile(base, np.float32).tobytes() != accs[0].tobytes()          # the edit is visible
