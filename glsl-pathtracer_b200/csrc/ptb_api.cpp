@@ -102,6 +102,7 @@ struct PtbCtx
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
+    int traceFinish = 1;       // misses / light hits of the lights-only specialisation are finished inside the trace kernel (PTB_TRACE_FINISH)
     int streamShade = 5;       // SHADE_* flags allowed for the first shade pass (PTB_STREAM_SHADE): 1 identity queue, 2 static chunks, 4 count-only
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
@@ -335,6 +336,8 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     // slot-ordered bounce 1 needs the tile-local material sorter (it drops the holes for k_shade) and is kept to scenes without alpha re-traces
     const bool useSlotOrder = c->slotOrder && c->sortMode == 3 && numKeys + 1 <= 4096 && !alphaScene && F.maxDepth >= 1 && !W.previewMode;
     if (useSlotOrder) CK(cudaMemsetAsync(c->slotKeys.p, 0x07, (size_t)W.nSlots * sizeof(uint32_t), c->stream));   // 0x07070707 clamps to 7 = ended / never live
+    // lights-only scenes: paths ending in a miss or on a light are finished by the trace kernel and leave the queues as holes (needs the tile-local sorter)
+    const bool finishInTrace = c->traceFinish && F.general == 0 && c->sortMode == 3 && numKeys + 1 <= 4096;
     int it = 0;
     while (true)
     {
@@ -355,15 +358,16 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
         mark(c, KIND_TRACE);
         if (it == 0 && fusedCamera)
             ptbk_trace_primary(L, c->S, F, W, P, ctr, lightsFromDepth, c->dstats.p, sortThis ? c->sortKeys.p : nullptr, globalHist,
-                               (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys);
+                               (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys, finishInTrace ? 1u : 0u);
         else
             ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
-                       sortThis ? c->sortKeys.p : nullptr, globalHist, nOv, (uint32_t)numKeys);
+                       sortThis ? c->sortKeys.p : nullptr, globalHist, nOv, (uint32_t)numKeys, finishInTrace ? (1u | (it == 0 ? 2u : 0u)) : 0u);
         const uint32_t* shadeQueue = traceQueue;
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)
             mark(c, KIND_SORT);
             if (nOv) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys + 1, c->sortedQueue.p, numKeys, W.nSlots);     // queue with holes
+            else if (finishInTrace) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys + 1, c->sortedQueue.p, numKeys, 0);   // finished paths = holes
             else if (c->sortMode == 3 && numKeys <= 4096) ptbk_sort_tile_local(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, numKeys, c->sortedQueue.p);
             else ptbk_sort(L, traceQueue, c->sortKeys.p, ci + CTR_NPATHS, c->sortHist.p, c->sortHist.p + numKeys, numKeys, c->sortedQueue.p);
             shadeQueue = c->sortedQueue.p;
@@ -509,6 +513,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
     if (const char* e = getenv("PTB_FUSE_CAMERA")) c->fuseCamera = atoi(e);
     if (const char* e = getenv("PTB_STREAM_SHADE")) c->streamShade = atoi(e);
+    if (const char* e = getenv("PTB_TRACE_FINISH")) c->traceFinish = atoi(e);
     *out = c;
     return PTB_OK;
 }

@@ -151,9 +151,9 @@ struct LaunchCfg
 
 void ptbk_camera(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0);
 void ptbk_trace(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride = 0, uint32_t holeKey = 0);
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride = 0, uint32_t holeKey = 0, uint32_t tflags = 0);
 void ptbk_trace_primary(const LaunchCfg&, const DevScene&, const FrameParams&, const WaveParams&, const PathState&, uint32_t* ctr0, int depthForLights, DevStats* stats,
-                        uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey);
+                        uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey, uint32_t tflags = 0);
 void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, uint32_t* hist, uint32_t* cursor, int numKeys,
                uint32_t* sorted);
 void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey = -1, uint32_t nOverride = 0);

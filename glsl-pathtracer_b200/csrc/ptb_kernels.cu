@@ -95,6 +95,56 @@ __device__ __forceinline__ uint32_t shadeKey(const DevScene& S, int hitInst)
     return 2u + (uint32_t)__float_as_int(__ldg(S.instTrav + (size_t)hitInst * 4 + 1).w);
 }
 
+// lightSample.pdf / emission of a light hit (closest_hit.glsl:56-62, 72-83)
+__device__ __forceinline__ void lightHitInfo(const DevScene& S, int idx, float3 ro, float3 rd, float t, float& pdf, float3& emission)
+{
+    const float4* p = S.lightsPre + (size_t)idx * 8;
+    float4 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 4);
+    emission = f3(b);
+    float area = b.w;
+    if (a.w == 0.0f)
+    {
+        float cosTheta = dot(-rd, f3(e));
+        pdf = (t * t) / (area * cosTheta);
+    }
+    else
+    {
+        float3 hitPt = ro + t * rd;
+        float cosTheta = dot(-rd, normalize(hitPt - f3(a)));
+        pdf = (t * t) / (area * cosTheta * 0.5f);
+    }
+}
+
+// Paths that end at this closest hit without shading work — a miss (pathtrace.glsl:305-339) or an analytic-light hit (:341-364) in the lights-only
+// specialisation (F.general == 0: no env map, no emission textures, no media) — are finished by the trace kernel itself: radiance += MIS weight x emission x
+// throughput, same expressions as shadePath<0>.  On hyperion 43 % of the closest-hit rays end this way; they never enter a shade queue (key = hole).
+enum { TRACE_FINISH = 1, TRACE_FIRST_ITER = 2 };
+__device__ __forceinline__ void finishInTrace(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, int hi, float3 ro, float3 rd, float t, int depth,
+                                              float prevPdf, bool firstIter)
+{
+    if (hi == -1 && !firstIter && !OPT(F, O_UNIFORM)) return;              // a later-bounce miss adds nothing: the radiance sum is already in place
+    const float4 thr4 = firstIter ? make_float4(1.f, 1.f, 1.f, 0.f) : P.thr[p], rad4 = firstIter ? make_float4(0.f, 0.f, 0.f, 1.f) : P.rad[p];
+    float3 thr = f3(thr4), rad = f3(rad4);
+    float alpha = rad4.w;
+    if (hi == -1)
+    {
+        if (OPT(F, O_BG) || OPT(F, O_TRANSPBG)) { if (depth == 0) alpha = 0.0f; }
+        if (!OPT(F, O_HIDE) || depth > 0)
+        {
+            if (OPT(F, O_UNIFORM)) rad += f3(F.uniformLightCol[0], F.uniformLightCol[1], F.uniformLightCol[2]) * thr;
+        }
+    }
+    else
+    {
+        float lpdf; float3 lem;
+        lightHitInfo(S, -(hi + 2), ro, rd, t, lpdf, lem);
+        float misWeight = 1.0f;
+        if (depth > 0) misWeight = PowerHeuristic(prevPdf, lpdf);
+        rad += misWeight * lem * thr;
+    }
+    P.rad[p] = make_float4(rad.x, rad.y, rad.z, alpha);
+}
+
 // Persistent warps fetch 32 consecutive queue entries at a time (one atomic per fetch).  A lane-granular refill of finished
 // lanes was measured and rejected: it breaks the screen-space coherence of the warp (primary rays 0.68 -> 1.17 ms per 8.3 M rays)
 // and did not help the incoherent bounces (1.33 -> 1.35 ms), see DESIGN.md.
@@ -103,7 +153,7 @@ __device__ __forceinline__ uint32_t shadeKey(const DevScene& S, int hitInst)
 // for the off-image pixels of a padded block) are written once from here, for the first shade pass.
 template <bool CULL, bool CAM>
 __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, const uint32_t* __restrict__ queue, uint32_t n,
-                                          uint32_t* fetchCtr, int lightsFromDepth, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t holeKey)
+                                          uint32_t* fetchCtr, int lightsFromDepth, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t holeKey, uint32_t tflags)
 {
     const uint32_t lane = threadIdx.x & 31u;
     SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
@@ -118,7 +168,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
         if (base >= n) break;
         const uint32_t i = base + lane;
         uint32_t pq;
-        float3 o, d; int depth = 0;
+        float3 o, d; int depth = 0; float prevPdf = 0.0f;
         if (CAM)
         {   // slot -> (sample, 8x4 block, pixel): the divisions are per fetch, not per pixel (n is a multiple of 32)
             const uint32_t b = base >> 5;
@@ -150,7 +200,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             if (pq != 0xffffffffu)
             {
                 const float4 o4 = P.rayO[pq], d4 = P.rayD[pq];
-                o = f3(o4); d = f3(d4);
+                o = f3(o4); d = f3(d4); prevPdf = o4.w;
                 depth = (int)(short)(__float_as_uint(d4.w) & 0xffffu);
             }
         }
@@ -162,12 +212,22 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             float t = PTB_INF;
             if (lights && depth >= lightsFromDepth) closestLights(S, o, d, t, h.light);         // OPT_HIDE_EMITTERS: lights only at depth > 0
             traverse<false, false, CULL>(S, o, d, t, stk, h, NoAlpha());
-            P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
             const int hi = (h.inst >= 0) ? h.inst : (h.light >= 0 && h.t < PTB_INF ? -(h.light + 2) : -1);
-            P.hitInst[p] = hi;
+            const bool finished = (tflags & TRACE_FINISH) && hi < 0;
+            if (finished)
+            {
+                const bool firstIter = CAM || (tflags & TRACE_FIRST_ITER);
+                finishInTrace(S, F, P, p, hi, o, d, h.t, depth, prevPdf, firstIter);
+                if (firstIter) P.hitInst[p] = PTB_HIT_DEAD;       // the first shade pass may run over the identity queue: it skips the slot on this mark
+            }
+            else
+            {
+                P.hit[p] = make_float4(h.t, h.bu, h.bv, __int_as_float(h.prim));
+                P.hitInst[p] = hi;
+            }
             if (keys)
             {   // histogram of shading keys, one atomic per distinct key per (converged part of the) warp
-                const uint32_t key = shadeKey(S, hi);
+                const uint32_t key = finished ? holeKey : shadeKey(S, hi);
                 keys[i] = key;
                 if (hist)
                 {   // global counting sort only (PTB_SORT=1/2); the tile-local sorter builds its own histograms
@@ -181,23 +241,23 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
 
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue,
                                                           const uint32_t* __restrict__ countPtr, uint32_t* fetchCtr, int lightsFromDepth, DevStats* stats,
-                                                          uint32_t* __restrict__ keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey)
+                                                          uint32_t* __restrict__ keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey, uint32_t tflags)
 {
     const uint32_t live = *countPtr;                     // rays actually traced (statistics)
     const uint32_t n = nOverride ? nOverride : live;     // queue length: the slot count when the queue is slot-ordered with holes
     if (blockIdx.x == 0 && threadIdx.x == 0 && live) atomicAdd(&stats->pathSegments, (unsigned long long)live);
     const WaveParams W{};
-    if (F.cullBoxes) traceLoop<true, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
-    else traceLoop<false, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey);
+    if (F.cullBoxes) traceLoop<true, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey, tflags);
+    else traceLoop<false, false>(S, F, W, P, queue, n, fetchCtr, lightsFromDepth, keys, hist, holeKey, tflags);
 }
 
 // First bounce: camera-ray generation fused into the closest-hit trace (see traceLoop<., true>).  liveCount = rays generated (host-known).
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_primary(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0, int lightsFromDepth,
-                                                                  DevStats* stats, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey)
+                                                                  DevStats* stats, uint32_t* __restrict__ keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey, uint32_t tflags)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&stats->pathSegments, (unsigned long long)liveCount); ctr0[CTR_NPATHS] = liveCount; }
-    if (F.cullBoxes) traceLoop<true, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey);
-    else traceLoop<false, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey);
+    if (F.cullBoxes) traceLoop<true, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey, tflags);
+    else traceLoop<false, true>(S, F, W, P, nullptr, W.nSlots, &ctr0[CTR_FETCH_TRACE], lightsFromDepth, keys, hist, holeKey, tflags);
 }
 
 // Exclusive scan of the key histogram into bucket cursors (one warp); clears the histogram for the next bounce.
@@ -411,26 +471,6 @@ __device__ __forceinline__ void getMaterial(const DevScene& S, const FrameParams
 
 __device__ __forceinline__ bool materialNeedsTangents(const DevScene& S, int matID) { return __ldg(S.materials + (size_t)matID * 8 + 6).z >= 0.f; }
 
-// lightSample.pdf / emission of a light hit (closest_hit.glsl:56-62, 72-83)
-__device__ __forceinline__ void lightHitInfo(const DevScene& S, int idx, float3 ro, float3 rd, float t, float& pdf, float3& emission)
-{
-    const float4* p = S.lightsPre + (size_t)idx * 8;
-    float4 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 4);
-    emission = f3(b);
-    float area = b.w;
-    if (a.w == 0.0f)
-    {
-        float cosTheta = dot(-rd, f3(e));
-        pdf = (t * t) / (area * cosTheta);
-    }
-    else
-    {
-        float3 hitPt = ro + t * rd;
-        float cosTheta = dot(-rd, normalize(hitPt - f3(a)));
-        pdf = (t * t) / (area * cosTheta * 0.5f);
-    }
-}
-
 // ------------------------------------------------------------------ inline traversal (RNG-consuming shadow rays) -
 struct InlineCounters { unsigned segs, shadows; };
 
@@ -624,6 +664,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
     float alpha = rad4.w, prevPdf = ro4.w, prevRough = thr4.w;
     constexpr bool GEN = MODE >= 1, FULL = MODE == 2;
     cont = false;
+    if (hitInst == PTB_HIT_DEAD) return;          // finished by the trace kernel (finishInTrace)
 
     if (hitInst == -1)      // miss: pathtrace.glsl:305-339
     {
@@ -1141,18 +1182,18 @@ void ptbk_camera(const LaunchCfg& c, const DevScene& S, const FrameParams& F, co
 }
 
 void ptbk_trace(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey)
+                const uint32_t* countPtr, uint32_t* fetchCtr, int depthForLights, DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t nOverride, uint32_t holeKey, uint32_t tflags)
 {
     const int bps = c.traceBlocks;
-    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist, nOverride, holeKey);
+    k_trace<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, queue, countPtr, fetchCtr, depthForLights, stats, keys, hist, nOverride, holeKey, tflags);
     COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_trace_primary(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const WaveParams& W, const PathState& P, uint32_t* ctr0, int depthForLights,
-                        DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey)
+                        DevStats* stats, uint32_t* keys, uint32_t* hist, uint32_t liveCount, uint32_t holeKey, uint32_t tflags)
 {
     const int bps = c.traceBlocks;
-    k_trace_primary<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, W, P, ctr0, depthForLights, stats, keys, hist, liveCount, holeKey);
+    k_trace_primary<<<c.numSMs * bps, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, W, P, ctr0, depthForLights, stats, keys, hist, liveCount, holeKey, tflags);
     COUNT_LAUNCH(c, 1);
 }
 
