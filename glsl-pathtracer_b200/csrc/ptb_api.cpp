@@ -102,7 +102,7 @@ struct PtbCtx
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
     int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
-    int traceFinish = 1;       // misses / light hits of the lights-only specialisation are finished inside the trace kernel (PTB_TRACE_FINISH)
+    int traceFinish = 1;       // misses / light hits of the specialisations without media are finished inside the trace kernel (PTB_TRACE_FINISH)
     int streamShade = 5;       // SHADE_* flags allowed for the first shade pass (PTB_STREAM_SHADE): 1 identity queue, 2 static chunks, 4 count-only
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
@@ -336,8 +336,8 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     // slot-ordered bounce 1 needs the tile-local material sorter (it drops the holes for k_shade) and is kept to scenes without alpha re-traces
     const bool useSlotOrder = c->slotOrder && c->sortMode == 3 && numKeys + 1 <= 4096 && !alphaScene && F.maxDepth >= 1 && !W.previewMode;
     if (useSlotOrder) CK(cudaMemsetAsync(c->slotKeys.p, 0x07, (size_t)W.nSlots * sizeof(uint32_t), c->stream));   // 0x07070707 clamps to 7 = ended / never live
-    // lights-only scenes: paths ending in a miss or on a light are finished by the trace kernel and leave the queues as holes (needs the tile-local sorter)
-    const bool finishInTrace = c->traceFinish && F.general == 0 && c->sortMode == 3 && numKeys + 1 <= 4096;
+    // scenes without media / alpha: paths ending in a miss or on a light are finished by the trace kernel and leave the queues as holes (needs the tile-local sorter)
+    const bool finishInTrace = c->traceFinish && F.general <= 1 && c->sortMode == 3 && numKeys + 1 <= 4096;
     int it = 0;
     while (true)
     {
