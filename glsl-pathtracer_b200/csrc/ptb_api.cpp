@@ -100,8 +100,9 @@ struct PtbCtx
     // wave state
     size_t slotCap = 0; bool stateGeneral = false;
     DevBuf<float4> state, shO[2], shD[2], shC[2];     // state: all per-path fields, interleaved (AoS) or as consecutive arrays (SoA)
-    int aos = 0; size_t stateStrideF4 = 0;   // interleaved layout measured slower (668 vs 720 spp/s): coherent bounce-0 passes lose more than sorted passes gain
+    int aos = 2; size_t stateStrideF4 = 0;   // path-state layout (PTB_AOS): 0 SoA of 16-byte fields, 1 one record per path (-7 %: the coherent first bounce loses), 2 SoA with (rayO, rayD) and (thr, rng) as 32-byte pairs — one full DRAM sector per scattered access of the sorted bounces (+0.4 %), 3-5 other pairings (+-0)
     DevBuf<uint32_t> queue[2], counters, sortKeys, sortedQueue, sortHist, slotKeys, slotSorted;
+    int sortFrom = 1;          // first bounce whose shade queue is material-sorted (PTB_SORT_FROM)
     int traceFinish = 1;       // misses / light hits of the specialisations without media are finished inside the trace kernel (PTB_TRACE_FINISH)
     int streamShade = 5;       // SHADE_* flags allowed for the first shade pass (PTB_STREAM_SHADE): 1 identity queue, 2 static chunks, 4 count-only
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
@@ -278,11 +279,35 @@ PathState pathState(PtbCtx* c)
     PathState P{};
     char* b = (char*)c->state.p;
     const size_t n = c->slotCap;
-    if (c->aos)
+    if (c->aos == 1)
     {   // field k of path i at b + i*stride + 16*k
         const uint32_t st = (uint32_t)(c->stateStrideF4 * 16);
         P.rayO = {b, st}; P.rayD = {b + 16, st}; P.thr = {b + 32, st}; P.rad = {b + 48, st}; P.rng = {b + 64, st}; P.hit = {b + 80, st};
         P.hitInst = {b + 96, st}; P.med = {b + 112, st}; P.medCol = {b + 128, st}; P.prevUV = {b + 144, st};
+    }
+    else if (c->aos == 4)
+    {   // pairs (rayO, rayD), (thr, rng), (rad, hit)
+        auto arr = [&](int k) { return b + (size_t)k * n * 16; };
+        P.rayO = {arr(0), 32}; P.rayD = {arr(0) + 16, 32}; P.thr = {arr(2), 32}; P.rng = {arr(2) + 16, 32}; P.rad = {arr(4), 32}; P.hit = {arr(4) + 16, 32};
+        P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
+    }
+    else if (c->aos == 5)
+    {   // 64-byte records (rayO, rayD, thr, rng)
+        auto arr = [&](int k) { return b + (size_t)k * n * 16; };
+        P.rayO = {arr(0), 64}; P.rayD = {arr(0) + 16, 64}; P.thr = {arr(0) + 32, 64}; P.rng = {arr(0) + 48, 64}; P.rad = {arr(4), 16}; P.hit = {arr(5), 16};
+        P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
+    }
+    else if (c->aos == 3)
+    {   // only the ray as a 32-byte pair
+        auto arr = [&](int k) { return b + (size_t)k * n * 16; };
+        P.rayO = {arr(0), 32}; P.rayD = {arr(0) + 16, 32}; P.thr = {arr(2), 16}; P.rad = {arr(3), 16}; P.rng = {arr(4), 16}; P.hit = {arr(5), 16};
+        P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
+    }
+    else if (c->aos == 2)
+    {   // SoA of 32-byte pairs (one DRAM sector per scattered access): (rayO, rayD), (thr, rng); the rest as in SoA
+        auto arr = [&](int k) { return b + (size_t)k * n * 16; };
+        P.rayO = {arr(0), 32}; P.rayD = {arr(0) + 16, 32}; P.thr = {arr(2), 32}; P.rng = {arr(2) + 16, 32}; P.rad = {arr(4), 16}; P.hit = {arr(5), 16};
+        P.hitInst = {arr(6), 4}; P.med = {arr(7), 16}; P.medCol = {arr(8), 16}; P.prevUV = {arr(9), 8};
     }
     else
     {   // SoA: array k at b + k*n*16
@@ -343,7 +368,7 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     {
         uint32_t* ci = ctr + (size_t)it * PTB_CTR_STRIDE;
         uint32_t* cn = ctr + (size_t)(it + 1) * PTB_CTR_STRIDE;
-        const bool sortThis = c->sortMode == 2 || ((c->sortMode == 1 || c->sortMode == 3) && it >= 1);
+        const bool sortThis = c->sortMode == 2 || ((c->sortMode == 1 || c->sortMode == 3) && it >= c->sortFrom);
         // bounce 1 over the slots in screen order (95 % of them still alive there): see slotOrder
         const bool slotIter = useSlotOrder && it == 1;
         const uint32_t nOv = (slotIter || (it == 0 && fusedCamera)) ? W.nSlots : 0u;      // queue length = slot count (holes inside)
@@ -358,10 +383,10 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
         mark(c, KIND_TRACE);
         if (it == 0 && fusedCamera)
             ptbk_trace_primary(L, c->S, F, W, P, ctr, lightsFromDepth, c->dstats.p, sortThis ? c->sortKeys.p : nullptr, globalHist,
-                               (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys, finishInTrace ? 1u : 0u);
+                               (uint32_t)((size_t)W.rw * W.rh * W.nSamples), (uint32_t)numKeys, finishInTrace ? (1u | (sortThis ? 0u : 4u)) : 0u);
         else
             ptbk_trace(L, c->S, F, P, traceQueue, ci + CTR_NPATHS, ci + CTR_FETCH_TRACE, lightsFromDepth, c->dstats.p,
-                       sortThis ? c->sortKeys.p : nullptr, globalHist, nOv, (uint32_t)numKeys, finishInTrace ? (1u | (it == 0 ? 2u : 0u)) : 0u);
+                       sortThis ? c->sortKeys.p : nullptr, globalHist, nOv, (uint32_t)numKeys, finishInTrace ? (1u | (it == 0 ? 2u : 0u) | (sortThis ? 0u : 4u)) : 0u);
         const uint32_t* shadeQueue = traceQueue;
         if (sortThis)
         {   // material-sorted shading: counting sort of the queue by (miss | light | material)
@@ -514,6 +539,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_FUSE_CAMERA")) c->fuseCamera = atoi(e);
     if (const char* e = getenv("PTB_STREAM_SHADE")) c->streamShade = atoi(e);
     if (const char* e = getenv("PTB_TRACE_FINISH")) c->traceFinish = atoi(e);
+    if (const char* e = getenv("PTB_SORT_FROM")) c->sortFrom = atoi(e);
     *out = c;
     return PTB_OK;
 }

@@ -118,7 +118,7 @@ __device__ __forceinline__ void lightHitInfo(const DevScene& S, int idx, float3 
 // Paths that end at this closest hit without shading work — a miss (pathtrace.glsl:305-339) or an analytic-light hit (:341-364) — are finished by the trace
 // kernel itself in the specialisations without media (F.general <= 1): radiance += MIS weight x emission x throughput, same expressions as shadePath.  On hyperion
 // 43 % of the closest-hit rays end this way (ibl_spheres 43 %, instancing 35 %); they never enter a shade queue (key = hole).
-enum { TRACE_FINISH = 1, TRACE_FIRST_ITER = 2 };
+enum { TRACE_FINISH = 1, TRACE_FIRST_ITER = 2, TRACE_MARK_DEAD = 4 };     // MARK_DEAD: the next shade pass is not fed by the sorter (which drops finished paths)
 template <bool GEN>
 __device__ __forceinline__ void finishPath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, int hi, float3 ro, float3 rd, float t, int depth,
                                            float prevPdf, bool firstIter)
@@ -247,7 +247,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             {
                 const bool firstIter = CAM || (tflags & TRACE_FIRST_ITER);
                 finishInTrace(S, F, P, p, hi, o, d, h.t, depth, prevPdf, firstIter);
-                if (firstIter) P.hitInst[p] = PTB_HIT_DEAD;       // the first shade pass may run over the identity queue: it skips the slot on this mark
+                if (tflags & TRACE_MARK_DEAD) P.hitInst[p] = PTB_HIT_DEAD;       // an unsorted shade pass (identity queue of the first bounce) skips the slot on this mark
             }
             else
             {

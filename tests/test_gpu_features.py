@@ -120,3 +120,27 @@ def test_malformed_scenes_are_rejected_not_dereferenced():
     ctx.reset_accum(); ctx.render_samples(1, 1)                                      # the context was left untouched by the rejected update
     assert ctx.read_accum().tobytes() == before.tobytes()
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["hyperion_rect_lights", "hyperion_sphere_light", "ibl_spheres", "feature:env_hide_bg", "feature:uniform_transparent",
+                                  "feature:stale_material", "feature:all_lights"])
+def test_paths_finished_in_the_trace_kernel_equal_paths_finished_in_the_shade_kernel(name, monkeypatch):
+    """Misses and light hits are finished by the trace kernel (finishInTrace) and never enter a shade queue; PTB_TRACE_FINISH=0 keeps them in
+    the shade kernel.  Same expressions on the same inputs: the two running sums may differ by FMA contraction only."""
+    from glsl_pathtracer_b200 import capi
+    sc = {"feature:env_hide_bg": fs.env_rotation_hide_emitters_background, "feature:uniform_transparent": fs.uniform_light_mollification_transparent,
+          "feature:stale_material": fs.mesh_emitter_stale_material, "feature:all_lights": fs.all_light_types}[name]() if name.startswith("feature:") else scene_at(name, 320, 180)
+    imgs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PTB_TRACE_FINISH", flag)
+        ctx = capi.Context(sc)
+        ctx.render_samples(1, 6)
+        imgs.append(np.nan_to_num(ctx.read_accum().astype(np.float64)))
+        st = ctx.stats(); ctx.close()
+        imgs.append((st["pathSegments"], st["shadowRays"]))
+    a, ca, b, cb = imgs
+    assert ca == cb, f"ray counts differ: {ca} vs {cb}"
+    assert a[..., :3].max() > 0
+    np.testing.assert_array_equal(a[..., 3], b[..., 3])                       # alpha: exact
+    scale = np.maximum(np.abs(b[..., :3]), 1e-3)
+    assert (np.abs(a[..., :3] - b[..., :3]) / scale).max() <= 2e-5
