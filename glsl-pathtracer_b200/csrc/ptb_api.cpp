@@ -105,6 +105,9 @@ struct PtbCtx
     int sortFrom = 1;          // first bounce whose shade queue is material-sorted (PTB_SORT_FROM)
     int traceFinish = 1;       // misses / light hits of the specialisations without media are finished inside the trace kernel (PTB_TRACE_FINISH)
     int streamShade = 5;       // SHADE_* flags allowed for the first shade pass (PTB_STREAM_SHADE): 1 identity queue, 2 static chunks, 4 count-only
+    int deferTransmit = 1;     // 1: EvalTransmittance rays of scenes without BLEND materials are queued for k_transmit instead of traced inside k_shade (PTB_DEFER_TRANSMIT)
+    int blockMajor = 1;        // 1: the 32-slot groups of a wave are ordered block-major (WaveParams::blockMajor, PTB_BLOCK_MAJOR)
+    int dirBins = 8;           // direction classes of the slot-ordered bounce 1: 8 = 8x8 octahedral cells, 0 = dominant axis + sign (PTB_DIR_BINS)
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
                                //    tiles of 2048 slots, instead of over the compacted arrival-order queue (PTB_SLOT_ORDER)
@@ -121,7 +124,7 @@ struct PtbCtx
 
     uint64_t samplesRendered = 0;
     unsigned long long launches = 0;          // kernels launched through this context
-    int traceBlocks = 1, shadowBlocks = 1, shadeBlocks[3] = {1, 1, 1}, configuredDepth = -1, configuredDepthAny = -1;   // per-device launch configuration (ptbk_configure_device)
+    int traceBlocks = 1, shadowBlocks = 1, shadeBlocks[4] = {1, 1, 1, 1}, transmitBlocks = 1, configuredDepth = -1, configuredDepthAny = -1;   // per-device launch configuration (ptbk_configure_device)
     uint64_t lastTraceRays = 0;
     bool timingValid = false;
 };
@@ -130,14 +133,14 @@ namespace {
 
 LaunchCfg cfg(PtbCtx* c)
 {
-    return LaunchCfg{c->numSMs, (void*)c->stream, c->traceBlocks, c->shadowBlocks, {c->shadeBlocks[0], c->shadeBlocks[1], c->shadeBlocks[2]}, &c->launches};
+    return LaunchCfg{c->numSMs, (void*)c->stream, c->traceBlocks, c->shadowBlocks, {c->shadeBlocks[0], c->shadeBlocks[1], c->shadeBlocks[2], c->shadeBlocks[3]}, c->transmitBlocks, &c->launches};
 }
 
 // kernel attributes / occupancy of this context's device for the current stack depth (the device must be current)
 int configureDevice(PtbCtx* c)
 {
     if (c->configuredDepth == c->S.stackDepth && c->configuredDepthAny == c->S.stackDepthAny) return PTB_OK;
-    cudaError_t e = (cudaError_t)ptbk_configure_device(c->S, &c->traceBlocks, &c->shadowBlocks, c->shadeBlocks);
+    cudaError_t e = (cudaError_t)ptbk_configure_device(c->S, &c->traceBlocks, &c->shadowBlocks, c->shadeBlocks, &c->transmitBlocks);
     if (e != cudaSuccess) { g_err = std::string("ptbk_configure_device: ") + cudaGetErrorString(e); return PTB_ERR_CUDA; }
     c->configuredDepth = c->S.stackDepth; c->configuredDepthAny = c->S.stackDepthAny;
     return PTB_OK;
@@ -187,7 +190,12 @@ void refreshDerivedFlags(PtbCtx* c)
     // shade specialisation: 0 = lights only, 1 = + env map / textures / emission / mollification, 2 = + media / alpha test / inline shadow rays
     F.general = (f & (PTB_OPT_MEDIUM | PTB_OPT_ALPHA_TEST)) ? 2
               : (((f & (PTB_OPT_ENVMAP | PTB_OPT_ROUGHNESS_MOLLIFICATION)) != 0u) || c->S.numTextures > 0 || anyEmission) ? 1 : 0;
-    F.inlineShadow = (((f & PTB_OPT_ALPHA_TEST) && !(f & PTB_OPT_MEDIUM) && anyBlend) || ((f & PTB_OPT_MEDIUM) && (f & PTB_OPT_VOL_MIS))) ? 1 : 0;
+    // Shadow rays that draw from the path RNG cannot be deferred without changing the reference's random-number order: AnyHit's BLEND alpha test
+    // (anyhit.glsl:118-141) and EvalTransmittance's (pathtrace.glsl:136).  Without a BLEND material neither draws anything.
+    const bool volMis = (f & PTB_OPT_MEDIUM) && (f & PTB_OPT_VOL_MIS);
+    const bool deferT = volMis && !anyBlend && c->deferTransmit;
+    F.inlineShadow = (((f & PTB_OPT_ALPHA_TEST) && !(f & PTB_OPT_MEDIUM) && anyBlend) || (volMis && !deferT)) ? 1 : 0;
+    F.deferTransmit = deferT ? 1 : 0;
 }
 
 // (re)build the per-column / per-row pixel tables when the resolution or the tile size changed
@@ -339,6 +347,7 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     c->pending.valid = false;                 // the wave state is about to be overwritten
     W.vw = (W.rw + 7) & ~7; W.vh = (W.rh + 3) & ~3;
     W.nSlots = (uint32_t)((size_t)W.vw * W.vh * W.nSamples);
+    W.blockMajor = (c->blockMajor && W.nSamples > 1) ? 1 : 0;
     int rc = ensureWaveState(c, W.nSlots);
     if (rc) return rc;
     PathState P = pathState(c);
@@ -360,7 +369,9 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     const int nominal = F.maxDepth + 1;
     // slot-ordered bounce 1 needs the tile-local material sorter (it drops the holes for k_shade) and is kept to scenes without alpha re-traces
     const bool useSlotOrder = c->slotOrder && c->sortMode == 3 && numKeys + 1 <= 4096 && !alphaScene && F.maxDepth >= 1 && !W.previewMode;
-    if (useSlotOrder) CK(cudaMemsetAsync(c->slotKeys.p, 0x07, (size_t)W.nSlots * sizeof(uint32_t), c->stream));   // 0x07070707 clamps to 7 = ended / never live
+    const bool octKeys = c->dirBins == 8;
+    const int slotHole = octKeys ? 64 : 7;
+    if (useSlotOrder) CK(cudaMemsetAsync(c->slotKeys.p, 0x7f, (size_t)W.nSlots * sizeof(uint32_t), c->stream));   // 0x7f7f7f7f clamps to the hole key = ended / never live
     // scenes without media / alpha: paths ending in a miss or on a light are finished by the trace kernel and leave the queues as holes (needs the tile-local sorter)
     const bool finishInTrace = c->traceFinish && F.general <= 1 && c->sortMode == 3 && numKeys + 1 <= 4096;
     int it = 0;
@@ -376,7 +387,7 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
         if (slotIter)
         {
             mark(c, KIND_SORT);
-            ptbk_sort_tile_local(L, nullptr, c->slotKeys.p, ci + CTR_NPATHS, 8, c->slotSorted.p, 7, W.nSlots);
+            ptbk_sort_tile_local(L, nullptr, c->slotKeys.p, ci + CTR_NPATHS, slotHole + 1, c->slotSorted.p, slotHole, W.nSlots);
             traceQueue = c->slotSorted.p;
         }
         uint32_t* globalHist = (c->sortMode == 3 && numKeys <= 4096) ? nullptr : c->sortHist.p;     // key histogram over the whole queue: global sorter only
@@ -402,14 +413,17 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
         // bounce 1 the continuing paths are only counted)
         uint32_t shadeFlags = 0;
         if (it == 0 && fusedCamera && !sortThis) shadeFlags = (uint32_t)c->streamShade & (1u | 2u | (useSlotOrder ? 4u : 0u));
+        if (useSlotOrder && it == 0 && octKeys) shadeFlags |= 8u;
         ptbk_shade(L, c->S, F, P, shadeQueue, ci, cn, P.queue[(it + 1) & 1], c->dstats.p, it == 0, (useSlotOrder && it == 0) ? c->slotKeys.p : nullptr, nOv, shadeFlags);
         if (!F.inlineShadow)
         {
             mark(c, KIND_SHADOW);
+            // binary visibility (AnyHit) or, under OPT_MEDIUM + OPT_VOL_MIS, the transmittance along the ray (EvalTransmittance)
+            auto nee = F.deferTransmit ? ptbk_transmit : ptbk_shadow;
             if (F.general && (F.features & PTB_OPT_ENVMAP) && !(F.features & PTB_OPT_UNIFORM_LIGHT))
-                ptbk_shadow(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
+                nee(L, c->S, F, P, 0, ci + CTR_NSHA, ci + CTR_FETCH_SHA, c->dstats.p);
             if (F.features & PTB_OPT_LIGHTS)
-                ptbk_shadow(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p);
+                nee(L, c->S, F, P, 1, ci + CTR_NSHB, ci + CTR_FETCH_SHB, c->dstats.p);
         }
         it++;
         if (it >= PTB_MAX_ITERS) break;                       // alpha-skip re-traces are unbounded in the reference (Q7); hard stop
@@ -537,9 +551,13 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_AOS")) c->aos = atoi(e);
     if (const char* e = getenv("PTB_SLOT_ORDER")) c->slotOrder = atoi(e);
     if (const char* e = getenv("PTB_FUSE_CAMERA")) c->fuseCamera = atoi(e);
+    if (const char* e = getenv("PTB_DEFER_TRANSMIT")) c->deferTransmit = atoi(e);
+    if (const char* e = getenv("PTB_BLOCK_MAJOR")) c->blockMajor = atoi(e);
+    if (const char* e = getenv("PTB_DIR_BINS")) c->dirBins = atoi(e);
     if (const char* e = getenv("PTB_STREAM_SHADE")) c->streamShade = atoi(e);
     if (const char* e = getenv("PTB_TRACE_FINISH")) c->traceFinish = atoi(e);
     if (const char* e = getenv("PTB_SORT_FROM")) c->sortFrom = atoi(e);
+    refreshDerivedFlags(c);
     *out = c;
     return PTB_OK;
 }

@@ -78,7 +78,8 @@ struct FrameParams
     // derived switches
     int cullBoxes;       // cull child boxes whose entry distance exceeds the current hit distance
     int inlineShadow;    // shadow rays consume path RNG draws (BLEND alpha in AnyHit / EvalTransmittance) -> traced inside shade
-    int general;         // shade kernel specialisation: 0 lights only, 1 + env/textures/emission, 2 + media/alpha/inline shadows
+    int general;         // shade kernel specialisation: 0 lights only, 1 + env/textures/emission, 2 + media/alpha (k_shade<2> when inlineShadow, else k_shade<3>)
+    int deferTransmit;   // OPT_MEDIUM + OPT_VOL_MIS without BLEND materials: EvalTransmittance draws no random number -> NEE rays are queued and k_transmit evaluates them
     // per-column / per-row tables of the pixel -> (frame texture coordinate, tile-local coordinate, tile) mapping (ptbd_build_pixel_tables); null = evaluate per pixel
     const float2* pixTabX; const float2* pixTabY;
 };
@@ -94,6 +95,9 @@ struct WaveParams
     int previewMode;           // preview.glsl: InitRNG(gl_FragCoord, 1), TexCoords over the whole image, depth 2
     uint32_t nSlots;           // vw*vh*nSamples
     int accFirst, accCount;    // k_accumulate adds the wave's passes [accFirst, accFirst+accCount) to the running sum (accCount 0 = all of them)
+    int blockMajor;            // order of the 32-slot groups (one 8x4 pixel block of one sample pass each): 0 = sample-major (all blocks of pass 0, then pass 1, ...),
+                               // 1 = block-major (all passes of block 0, then block 1, ...): a 2048-slot tile then holds the paths of a few neighbouring pixels,
+                               // so the tile-local grouping by direction yields warps whose rays share origin AND direction
 };
 
 // Path state fields are addressed as base + slot * stride.  stride = sizeof(T) gives SoA arrays; a common 128-byte (lights-only)
@@ -145,7 +149,8 @@ struct LaunchCfg
     int numSMs; void* stream;
     int traceBlocks;            // resident k_trace blocks per SM on this context's device (ptbk_configure_device)
     int shadowBlocks;           // same for k_shadow (its stack may be deeper: 4-wide hierarchy)
-    int shadeBlocks[3];         // same for the three k_shade specialisations
+    int shadeBlocks[4];         // same for the k_shade specialisations (0, 1, 2 = inline shadow rays, 3 = media / alpha with deferred shadow rays)
+    int transmitBlocks;         // same for k_transmit
     unsigned long long* launches;   // per-context count of kernel launches (may be null)
 };
 
@@ -162,6 +167,8 @@ void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const Pat
                 uint32_t flags = 0);     // flags: SHADE_* of ptb_kernels.cu (1 identity queue, 2 static chunks, 4 count the continuing paths only)
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
                  uint32_t* fetchCtr, DevStats* stats);
+void ptbk_transmit(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
+                   uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);
 void ptbk_tonemap(const LaunchCfg&, const float4* accum, int w, int h, float invSampleCounter, int enableTonemap, int enableAces,
                   int simpleAcesFit, const float* backgroundCol3, uint32_t features, uchar4* out, float4* outF = nullptr);
@@ -172,4 +179,4 @@ void ptbk_camera_rays(const LaunchCfg&, const FrameParams&, const WaveParams&, f
 int  ptbk_tlas_build(const LaunchCfg&, float* nodes, int top, const float4* transforms, int n, const int* blasRoot, const int* materialID, float* instBounds, float* cent,
                      int* nodeOf, void* recA, void* recB, void* recC, int* remap, int* result);     // rec buffers: (n + 2) records of ptbk_tlas_rec_size() bytes; remap: n + 2 ints
 int  ptbk_tlas_rec_size();
-int  ptbk_configure_device(const DevScene&, int* traceBlocks, int* shadowBlocks, int shadeBlocks[3]);   // per-device attributes; returns a cudaError_t value
+int  ptbk_configure_device(const DevScene&, int* traceBlocks, int* shadowBlocks, int shadeBlocks[4], int* transmitBlocks);   // per-device attributes; returns a cudaError_t value

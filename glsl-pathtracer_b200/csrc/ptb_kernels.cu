@@ -37,14 +37,21 @@ constexpr int SHADE_THREADS = 128;
 // Path slots of one sample pass are ordered in 8x4 pixel blocks so that a warp's primary rays are spatially coherent.
 __device__ __forceinline__ bool slotToPixel(const WaveParams& W, uint32_t slot, int& s, int& px, int& py)
 {
-    const uint32_t perSample = (uint32_t)W.vw * (uint32_t)W.vh;
-    s = (int)(slot / perSample);
-    uint32_t idx = slot - (uint32_t)s * perSample;
-    uint32_t b = idx >> 5, l = idx & 31u;
-    uint32_t blocksX = (uint32_t)W.vw >> 3;
+    const uint32_t blocksX = (uint32_t)W.vw >> 3, blocksPerSample = blocksX * ((uint32_t)W.vh >> 2);
+    const uint32_t g = slot >> 5, l = slot & 31u;
+    uint32_t b;
+    if (W.blockMajor) { b = g / (uint32_t)W.nSamples; s = (int)(g - b * (uint32_t)W.nSamples); }
+    else { s = (int)(g / blocksPerSample); b = g - (uint32_t)s * blocksPerSample; }
     px = (int)((b % blocksX) * 8u + (l & 7u));
     py = (int)((b / blocksX) * 4u + (l >> 3));
     return px < W.rw && py < W.rh;
+}
+
+// slot of sample pass k for the pixel with index idx (= block * 32 + lane) inside one pass
+__device__ __forceinline__ uint32_t slotOfSample(const WaveParams& W, uint32_t idx, uint32_t k)
+{
+    if (W.blockMajor) return (((idx >> 5) * (uint32_t)W.nSamples + k) << 5) | (idx & 31u);
+    return idx + k * (uint32_t)W.vw * (uint32_t)W.vh;
 }
 
 __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0)
@@ -201,7 +208,9 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
         if (CAM)
         {   // slot -> (sample, 8x4 block, pixel): the divisions are per fetch, not per pixel (n is a multiple of 32)
             const uint32_t b = base >> 5;
-            const uint32_t s = b / blocksPerSample, bb = b - s * blocksPerSample;
+            uint32_t s, bb;
+            if (W.blockMajor) { bb = b / (uint32_t)W.nSamples; s = b - bb * (uint32_t)W.nSamples; }
+            else { s = b / blocksPerSample; bb = b - s * blocksPerSample; }
             const uint32_t by = bb / blocksX, bx = bb - by * blocksX;
             const int px = (int)(bx * 8u + (lane & 7u)), py = (int)(by * 4u + (lane >> 3));
             const bool live = px < W.rw && py < W.rh;
@@ -610,9 +619,12 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
 {
     float3 Ld = f3(0.0f);
     const float3 scatterPos = sf.fhp + sf.normal * PTB_EPS;
-    constexpr bool GEN = MODE >= 1, FULL = MODE == 2;       // FULL: media, alpha test, RNG-consuming (inline) shadow rays
+    constexpr bool GEN = MODE >= 1, FULL = MODE >= 2;       // FULL: media, alpha test; MODE 2 also traces the RNG-consuming shadow rays inline
     const bool volMis = FULL && OPT(F, O_MEDIUM) && OPT(F, O_VOLMIS);
-    const bool inl = FULL && F.inlineShadow;
+    // MODE 3: every NEE ray is deferred — to k_shadow (binary AnyHit) or, under volMis, to k_transmit, which multiplies the queued contribution
+    // by EvalTransmittance (pathtrace.glsl:176, 242: Li *= EvalTransmittance(shadowRay); no random number is drawn without BLEND materials)
+    const bool inl = MODE == 2 && F.inlineShadow;
+    const bool inlT = MODE == 2 && volMis;                  // transmittance evaluated here
 
     if (GEN && OPT(F, O_ENVMAP) && !OPT(F, O_UNIFORM))
     {
@@ -620,9 +632,9 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
         float4 dirPdf = SampleEnvMap(S, F, rng, Li);
         float3 lightDir = f3(dirPdf);
         float lightPdf = dirPdf.w;
-        if (volMis) Li *= evalTransmittance(S, F, scatterPos, lightDir, rng, ic);
+        if constexpr (MODE == 2) { if (inlT) Li *= evalTransmittance(S, F, scatterPos, lightDir, rng, ic); }
         bool visible = true;
-        if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, lightDir, PTB_INF - PTB_EPS, rng, ic);
+        if constexpr (MODE == 2) { if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, lightDir, PTB_INF - PTB_EPS, rng, ic); }
         if (visible)
         {
             float3 f; float pdf;
@@ -636,7 +648,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 if (misWeight > 0.0f)
                 {
                     float3 c = misWeight * Li * f * F.envMapIntensity / lightPdf;
-                    if (volMis || inl) Ld += c;
+                    if (inlT || inl) Ld += c;
                     else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr);
                     else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; }
                 }
@@ -653,9 +665,9 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
         float3 Li = ls.emission;
         if (dot(ls.direction, ls.normal) < 0.0f)
         {
-            if (volMis) Li *= evalTransmittance(S, F, scatterPos, ls.direction, rng, ic);
+            if constexpr (MODE == 2) { if (inlT) Li *= evalTransmittance(S, F, scatterPos, ls.direction, rng, ic); }
             bool visible = true;
-            if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, ls.direction, ls.dist - PTB_EPS, rng, ic);
+            if constexpr (MODE == 2) { if (!volMis && inl) visible = !anyHitInline(S, F, scatterPos, ls.direction, ls.dist - PTB_EPS, rng, ic); }
             if (visible)
             {
                 float3 f; float pdf;
@@ -666,7 +678,7 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 if (pdf > 0.0f)
                 {
                     float3 c = misWeight * Li * f / ls.pdf;
-                    if (volMis || inl) Ld += c;
+                    if (inlT || inl) Ld += c;
                     else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr);
                     else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
                 }
@@ -691,7 +703,7 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
     bool inMedium = (fl & PTB_FLAG_INMEDIUM) != 0u, surfaceScatter = (fl & PTB_FLAG_SURFSCAT) != 0u;
     float3 ro = f3(ro4), rd = f3(rd4), thr = f3(thr4), rad = f3(rad4);
     float alpha = rad4.w, prevPdf = ro4.w, prevRough = thr4.w;
-    constexpr bool GEN = MODE >= 1, FULL = MODE == 2;
+    constexpr bool GEN = MODE >= 1, FULL = MODE >= 2;
     cont = false;
     if (hitInst == PTB_HIT_DEAD) return;          // finished by the trace kernel (finishInTrace)
 
@@ -875,7 +887,23 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
 //   SHADE_IDENTITY   entry i is path slot i (no queue read in front of the state loads; off-image slots of padded pixel blocks carry PTB_HIT_DEAD)
 //   SHADE_STATIC     chunks are dealt to the warps round-robin (uniform work per chunk: no fetch atomic to wait for)
 //   SHADE_COUNT_ONLY the continuing paths are counted, not queued (the next trace runs over the slots in screen order: slot-ordered bounce 1)
-enum { SHADE_IDENTITY = 1, SHADE_STATIC = 2, SHADE_COUNT_ONLY = 4 };
+//   SHADE_OCT_KEYS   direction class of the continuation ray = cell of an 8x8 octahedral map (64 classes, 64 = ended) instead of dominant axis + sign (6 classes, 7 = ended)
+enum { SHADE_IDENTITY = 1, SHADE_STATIC = 2, SHADE_COUNT_ONLY = 4, SHADE_OCT_KEYS = 8 };
+
+// Cell of direction d in an 8x8 octahedral map, rows walked boustrophedon so that consecutive cells are neighbours on the sphere.
+__device__ __forceinline__ uint32_t octCell(float dx, float dy, float dz)
+{
+    const float inv = rcpApprox(fabsf(dx) + fabsf(dy) + fabsf(dz));
+    float u = dx * inv, v = dy * inv;
+    if (dz < 0.f)
+    {
+        const float uu = (1.0f - fabsf(v)) * (u < 0.f ? -1.0f : 1.0f), vv = (1.0f - fabsf(u)) * (v < 0.f ? -1.0f : 1.0f);
+        u = uu; v = vv;
+    }
+    int iu = (int)((u * 0.5f + 0.5f) * 8.0f), iv = (int)((v * 0.5f + 0.5f) * 8.0f);
+    iu = min(max(iu, 0), 7); iv = min(max(iv, 0), 7);
+    return (uint32_t)(iv * 8 + ((iv & 1) ? 7 - iu : iu));
+}
 
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
@@ -909,12 +937,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
                 if (slotKeys)
                 {   // direction class of the continuation ray (dominant axis, sign) per path SLOT, 7 = path ended: the bounce-1 trace runs over
                     // the slots in screen order, grouped by this class inside tiles
-                    uint32_t k = 7u;
+                    uint32_t k = (flags & SHADE_OCT_KEYS) ? 64u : 7u;
                     if (cont)
                     {
                         const float4 d4 = P.rayD[p];
                         const float ax = fabsf(d4.x), ay = fabsf(d4.y), az = fabsf(d4.z);
-                        k = (ax >= ay && ax >= az) ? (d4.x < 0.f ? 1u : 0u) : (ay >= az ? (d4.y < 0.f ? 3u : 2u) : (d4.z < 0.f ? 5u : 4u));
+                        if (flags & SHADE_OCT_KEYS) k = octCell(d4.x, d4.y, d4.z);
+                        else k = (ax >= ay && ax >= az) ? (d4.x < 0.f ? 1u : 0u) : (ay >= az ? (d4.y < 0.f ? 3u : 2u) : (d4.z < 0.f ? 5u : 4u));
                     }
                     slotKeys[p] = k;
                 }
@@ -1005,6 +1034,71 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     else shadowLoop<false, false>(S, F, P, which, n, fetchCtr, NoAlpha());
 }
 
+// ------------------------------------------------------------------ transmittance (NEE under OPT_MEDIUM + OPT_VOL_MIS) -------
+// EvalTransmittance (pathtrace.glsl:119-155) for the queued NEE rays of a scene without BLEND materials (no random number is drawn then, so the
+// evaluation can leave the shading kernel): up to maxDepth closest hits along the ray — through refractive / alpha-masked surfaces, attenuated inside
+// media — with the wavefront kernels' shared-memory stack; the queued contribution (already misWeight * Li * f / pdf * throughput) times the
+// transmittance is added to the path's radiance.  One entry per path per queue: no atomics, deterministic.
+constexpr int TRANSMIT_MIN_BLOCKS = 3;
+__global__ void __launch_bounds__(TRACE_THREADS, TRANSMIT_MIN_BLOCKS) k_transmit(DevScene S, FrameParams F, PathState P, int which, const uint32_t* __restrict__ countPtr,
+                                                                uint32_t* fetchCtr, DevStats* stats)
+{
+    const uint32_t n = *countPtr;
+    const uint32_t lane = threadIdx.x & 31u;
+    SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
+    const bool lights = OPT(F, O_LIGHTS) && !OPT(F, O_HIDE);      // ClosestHit with a fresh State: depth 0 (closestFull)
+    uint32_t segs = 0;
+    while (true)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetchCtr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n)
+        {
+            const float4 o4 = P.shO[which][i], d4 = P.shD[which][i];
+            float3 ro = f3(o4);
+            const float3 rd = f3(d4);
+            float3 transmittance = f3(1.0f);
+            bool blocked = false;
+            for (int depth = 0; depth < F.maxDepth; depth++)
+            {
+                HitRec h; h.t = PTB_INF; h.prim = -1; h.inst = -1; h.light = -1; h.bu = h.bv = 0.f;
+                float t = PTB_INF;
+                segs++;
+                if (lights) closestLights(S, ro, rd, t, h.light);
+                traverse<false, false, true>(S, ro, rd, t, stk, h, NoAlpha());
+                if (h.t == PTB_INF || h.inst < 0) break;            // no hit, or an emitter: the transmittance so far
+                Surf sf;
+                const int matID = __float_as_int(__ldg(S.instTrav + (size_t)h.inst * 4 + 1).w);
+                triangleSurface(S, h.prim, h.inst, h.bu, h.bv, ro, rd, h.t, true, materialNeedsTangents(S, matID), sf);
+                Material mat; float eta;
+                getMaterial<2>(S, F, sf, rd, 0, 0.f, mat, eta);
+                const bool alphatest = mat.alphaMode == 2 && mat.opacity < mat.alphaCutoff;       // (no BLEND material in this mode: F.deferTransmit)
+                const bool refractive = (1.0f - mat.metallic) * mat.specTrans > 0.0f;
+                if (!(alphatest || refractive)) { blocked = true; break; }
+                if (dot(rd, sf.normal) > 0 && mat.medType != 0)
+                {
+                    const float3 color = mat.medType == 1 ? f3(1.0f) - mat.medColor : f3(1.0f);
+                    transmittance *= vexp(-color * mat.medDensity * sf.hitDist);
+                }
+                ro = sf.fhp + rd * PTB_EPS;
+            }
+            if (!blocked)
+            {
+                const uint32_t p = __float_as_uint(d4.w);
+                const float4 c = P.shC[which][i];
+                float4 r = P.rad[p];
+                r.x += c.x * transmittance.x; r.y += c.y * transmittance.y; r.z += c.z * transmittance.z;
+                P.rad[p] = r;
+            }
+        }
+    }
+    segs = __reduce_add_sync(0xffffffffu, segs);
+    if (lane == 0 && segs) atomicAdd(&stats->pathSegments, (unsigned long long)segs);
+}
+
 // ------------------------------------------------------------------ accumulate / tonemap ------------------------
 // tile.glsl:70-74: color = pixelColor + accumColor, one sample pass after the other (deterministic order).
 __global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W, PathState P, float4* accum, float4* previewOut)
@@ -1012,11 +1106,15 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W,
     const uint32_t perSample = (uint32_t)W.vw * (uint32_t)W.vh;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < perSample; idx += gridDim.x * blockDim.x)
     {
-        int s, px, py;
-        if (!slotToPixel(W, idx, s, px, py)) continue;
+        int px, py;
+        {   // pixel of index idx inside one pass (8x4 blocks, row-major)
+            const uint32_t b = idx >> 5, l = idx & 31u, blocksX = (uint32_t)W.vw >> 3;
+            px = (int)((b % blocksX) * 8u + (l & 7u)); py = (int)((b / blocksX) * 4u + (l >> 3));
+            if (!(px < W.rw && py < W.rh)) continue;
+        }
         if (W.previewMode)
         {
-            previewOut[(size_t)py * W.rw + px] = P.rad[idx];
+            previewOut[(size_t)py * W.rw + px] = P.rad[slotOfSample(W, idx, 0)];
             continue;
         }
         float4* dst = accum + (size_t)(W.y0 + py) * F.renderW + (W.x0 + px);
@@ -1024,7 +1122,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams F, WaveParams W,
         const int k0 = W.accCount > 0 ? W.accFirst : 0, k1 = W.accCount > 0 ? W.accFirst + W.accCount : W.nSamples;
         for (int k = k0; k < k1; k++)
         {
-            const float4 r = P.rad[idx + (uint32_t)k * perSample];
+            const float4 r = P.rad[slotOfSample(W, idx, (uint32_t)k)];
             a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
         }
         *dst = a;
@@ -1180,7 +1278,7 @@ static inline size_t stackBytesAny(const DevScene& S, int threads) { return (siz
 // Per-device kernel attributes for the current device: dynamic shared memory of the stack-carrying kernels (the default limit is 48 KB) and the
 // resident blocks per SM the persistent grids are sized with.  Called by the host side after cudaSetDevice whenever a context is created
 // or its stack depth changes; the results live in the context, not in process-wide statics.
-int ptbk_configure_device(const DevScene& S, int* traceBlocks, int* shadowBlocks, int shadeBlocks[3])
+int ptbk_configure_device(const DevScene& S, int* traceBlocks, int* shadowBlocks, int shadeBlocks[4], int* transmitBlocks)
 {
     const size_t smem = stackBytes(S, TRACE_THREADS), smemAny = stackBytesAny(S, TRACE_THREADS);
     cudaError_t e = cudaSuccess;
@@ -1188,6 +1286,7 @@ int ptbk_configure_device(const DevScene& S, int* traceBlocks, int* shadowBlocks
     upd(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_trace_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemAny));
+    upd(cudaFuncSetAttribute(k_transmit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_trace_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     upd(cudaFuncSetAttribute(k_any_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemAny));
     int nb = 0;
@@ -1199,7 +1298,11 @@ int ptbk_configure_device(const DevScene& S, int* traceBlocks, int* shadowBlocks
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[0], k_shade<0, 4>, SHADE_THREADS, 0));
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[1], k_shade<1, 5>, SHADE_THREADS, 0));
     upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[2], k_shade<2, 4>, SHADE_THREADS, 0));
-    for (int k = 0; k < 3; k++) if (shadeBlocks[k] < 1) shadeBlocks[k] = 1;
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadeBlocks[3], k_shade<3, 4>, SHADE_THREADS, 0));
+    for (int k = 0; k < 4; k++) if (shadeBlocks[k] < 1) shadeBlocks[k] = 1;
+    nb = 0;
+    upd(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_transmit, TRACE_THREADS, smem));
+    *transmitBlocks = nb > 0 ? nb : 1;
     return (int)e;
 }
 
@@ -1245,7 +1348,8 @@ void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, con
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride, uint32_t flags)
 {
     const int* bps = c.shadeBlocks;
-    if (F.general == 2) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+    if (F.general == 2 && F.inlineShadow) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+    else if (F.general == 2) k_shade<3, 4><<<c.numSMs * bps[3], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
     else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
     else if (PTB_SHADE_LATER_BLOCKS != 4 && !firstIter)
         k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
@@ -1258,6 +1362,13 @@ void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, co
 {
     const int bps = c.shadowBlocks;
     k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytesAny(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
+    COUNT_LAUNCH(c, 1);
+}
+
+void ptbk_transmit(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
+                   uint32_t* fetchCtr, DevStats* stats)
+{
+    k_transmit<<<c.numSMs * c.transmitBlocks, TRACE_THREADS, stackBytes(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
     COUNT_LAUNCH(c, 1);
 }
 

@@ -52,6 +52,7 @@ struct Lane
     int stack[64]; int sp;
     int pending = -2;        // parked leaf node (policy 1), -2 = none
     long steps = 0;
+    bool enteredInst = false;
     void begin(const Scene& S, const float* r)
     {
         o = {r[0], r[1], r[2]}; d = {r[3], r[4], r[5]}; ro = o; rd = d;
@@ -110,6 +111,7 @@ inline void enterInst(const Scene& S, Lane& L)
     L.stack[L.sp++] = -1;
     L.cur = (int)n[6];
     L.inBlas = true;
+    L.enteredInst = true;
 }
 inline void popMarker(Lane& L)
 {
@@ -130,6 +132,7 @@ inline int distinctLines(const long* addr, int n)
     return m;
 }
 
+bool g_stopAtInst = false;      // phase-1 model: a ray that reaches an instance leaf stops there (it is handed to phase 2)
 void runWarp(const Scene& S, const float* rays, const float* maxDist, int n, int policy, bool cull, float* outT, int32_t* outPrim, Stats& st)
 {
     Lane L[32];
@@ -203,17 +206,19 @@ void runWarp(const Scene& S, const float* rays, const float* maxDist, int n, int
         {
             if (L[i].done) continue;
             Kind k = kindOf(S, L[i].cur);
-            if (k == K_INST) { enterInst(S, L[i]); nInst++; }
+            if (k == K_INST) { if (g_stopAtInst) { L[i].done = true; L[i].enteredInst = true; continue; } enterInst(S, L[i]); nInst++; }
             else if (k == K_MARK) { popMarker(L[i]); nMark++; }
         }
         if (nInst) { st.slots += C_INST; st.otherSlots += C_INST; st.laneSlots += (double)C_INST * nInst; }
         if (nMark) { st.slots += C_POP; st.otherSlots += C_POP; st.laneSlots += (double)C_POP * nMark; }
     }
-    for (int i = 0; i < n; i++) { outT[i] = L[i].t; outPrim[i] = L[i].prim; }
+    for (int i = 0; i < n; i++) { outT[i] = L[i].t; outPrim[i] = L[i].anyHit ? ((L[i].occluded ? 1 : 0) | (L[i].enteredInst ? 2 : 0) | (int)(L[i].steps << 2)) : L[i].prim; }
     st.rays += n;
 }
 
 }  // namespace
+
+extern "C" void simd_sim_stop_at_inst(int on) { g_stopAtInst = on != 0; }
 
 extern "C" void simd_sim(const float* nodes, int numNodes, int top, const int32_t* vi, const float* verts, const float* invT,
                          const float* rays, int64_t n, int policy, int cull, int warp, float* outT, int32_t* outPrim, double* out9, const float* maxDist)

@@ -94,6 +94,15 @@ def media(medium_type, vol_mis):
     return sc
 
 
+def media_no_blend(medium_type):
+    """volume MIS with a purely refractive medium boundary (no BLEND material anywhere): EvalTransmittance draws no random number, the NEE rays are
+    deferred to k_transmit (F.deferTransmit)."""
+    sc = media(medium_type, True)
+    sc.materials[:, 29] = 0                        # alphaMode OPAQUE; the boundary stays transparent for shadow rays through specTrans = 1
+    sc.materials[:, 28] = 1.0
+    return sc
+
+
 def many_bounces_no_rr():
     sc = scene_at("cornell_box_sphere", 96, 96, 48, 48, 12)
     sc.renderOptions.enableRR = False
