@@ -164,9 +164,10 @@ void ptbk_sort(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, co
 void ptbk_sort_tile_local(const LaunchCfg&, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey = -1, uint32_t nOverride = 0);
 void ptbk_shade(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, const uint32_t* queue,
                 uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys = nullptr, uint32_t nOverride = 0,
-                uint32_t flags = 0);     // flags: SHADE_* of ptb_kernels.cu (1 identity queue, 2 static chunks, 4 count the continuing paths only)
+                uint32_t flags = 0,      // flags: SHADE_* of ptb_kernels.cu (1 identity queue, 2 static chunks, 4 count the continuing paths only, 8 octahedral direction classes)
+                uint32_t* shadowKeysA = nullptr, uint32_t* shadowKeysB = nullptr, int lightKeys = 0);   // slot-ordered shadow queues (SlotShadow in ptb_kernels.cu)
 void ptbk_shadow(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
-                 uint32_t* fetchCtr, DevStats* stats);
+                 uint32_t* fetchCtr, DevStats* stats, const uint32_t* idxQueue = nullptr, uint32_t nOverride = 0);
 void ptbk_transmit(const LaunchCfg&, const DevScene&, const FrameParams&, const PathState&, int which, const uint32_t* countPtr,
                    uint32_t* fetchCtr, DevStats* stats);
 void ptbk_accumulate(const LaunchCfg&, const FrameParams&, const WaveParams&, const PathState&, float4* accum, float4* previewOut);

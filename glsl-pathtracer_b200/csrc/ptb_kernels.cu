@@ -588,7 +588,23 @@ __device__ __noinline__ float3 evalTransmittance(const DevScene& S, const FrameP
 }
 
 // ------------------------------------------------------------------ shade ----------------------------------------
-struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
+// Cell of direction d in a GxG octahedral map, rows walked boustrophedon so that consecutive cells are neighbours on the sphere.
+template <int G = 8>
+__device__ __forceinline__ uint32_t octCell(float dx, float dy, float dz)
+{
+    const float inv = rcpApprox(fabsf(dx) + fabsf(dy) + fabsf(dz));
+    float u = dx * inv, v = dy * inv;
+    if (dz < 0.f)
+    {
+        const float uu = (1.0f - fabsf(v)) * (u < 0.f ? -1.0f : 1.0f), vv = (1.0f - fabsf(u)) * (v < 0.f ? -1.0f : 1.0f);
+        u = uu; v = vv;
+    }
+    int iu = (int)((u * 0.5f + 0.5f) * (float)G), iv = (int)((v * 0.5f + 0.5f) * (float)G);
+    iu = min(max(iu, 0), G - 1); iv = min(max(iv, 0), G - 1);
+    return (uint32_t)(iv * G + ((iv & 1) ? G - 1 - iu : iu));
+}
+
+struct ShadowOut { bool valid; float3 o, d, c; float maxDist; uint32_t light; };
 
 // Immediate push (k_shade<1>: env map + lights, two pending records = 20 registers): where a deferred shadow ray is produced it is appended
 // to its queue at once by the lanes that are converged there (one atomic per group), instead of being carried to a warp-converged push at
@@ -596,9 +612,27 @@ struct ShadowOut { bool valid; float3 o, d, c; float maxDist; };
 // to that path's radiance.  Measured on one box: ibl_spheres 944 -> 976 spp/s (with 5 blocks/SM); k_shade<0> (one record, hyperion) loses 2 %
 // with it (846 -> 828: the light-NEE queue of bounce 0 is no longer in pixel order), so modes 0 and 2 keep the converged push.
 template <int MODE> struct ImmediatePush { static constexpr bool value = (MODE == 1); };
-struct ShadowSink { const PathState* P; uint32_t* ctrA; uint32_t* ctrB; uint32_t path; };
-__device__ __forceinline__ void pushShadowNow(const ShadowSink& sk, int which, float3 o, float3 d, float maxDist, float3 c)
+// Slot-ordered shadow queues (first shade pass of a wave, block-major slot order): the record of path slot p is written AT index p and a sort key
+// per slot says what it is — the sampled light (queue B, 2..255 lights) or the octahedral cell of the ray direction, or "no ray" (the arrays are preset to the
+// hole key) — and the tile-local sorter turns that into an index queue in which the rays of a few neighbouring pixels towards one light / in one direction
+// are adjacent: k_shadow's warps then share origin and direction.  keys[which] == nullptr: compacted arrival-order queue (later bounces).
+struct SlotShadow { uint32_t* keys[2]; uint32_t lightKeys; };
+__device__ __forceinline__ uint32_t shadowKey(const SlotShadow& ss, int which, float3 d, uint32_t light)
 {
+    return (which == 1 && ss.lightKeys) ? light : octCell(d.x, d.y, d.z);
+}
+struct ShadowSink { const PathState* P; uint32_t* ctrA; uint32_t* ctrB; uint32_t path; SlotShadow ss; };
+__device__ __forceinline__ void pushShadowNow(const ShadowSink& sk, int which, float3 o, float3 d, float maxDist, float3 c, uint32_t light)
+{
+    if (sk.ss.keys[which])
+    {
+        const uint32_t k = sk.path;
+        sk.P->shO[which][k] = make_float4(o.x, o.y, o.z, maxDist);
+        sk.P->shD[which][k] = make_float4(d.x, d.y, d.z, __uint_as_float(k));
+        sk.P->shC[which][k] = make_float4(c.x, c.y, c.z, 0.f);
+        sk.ss.keys[which][k] = shadowKey(sk.ss, which, d, light);
+        return;
+    }
     const unsigned m = __activemask();
     const uint32_t lane = threadIdx.x & 31u;
     const int leader = __ffs(m) - 1;
@@ -649,8 +683,8 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f * F.envMapIntensity / lightPdf;
                     if (inlT || inl) Ld += c;
-                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr);
-                    else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; }
+                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 0, scatterPos, lightDir, PTB_INF - PTB_EPS, c * thr, 0u);
+                    else { sa.valid = true; sa.o = scatterPos; sa.d = lightDir; sa.maxDist = PTB_INF - PTB_EPS; sa.c = c * thr; sa.light = 0u; }
                 }
             }
         }
@@ -679,8 +713,8 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
                 {
                     float3 c = misWeight * Li * f / ls.pdf;
                     if (inlT || inl) Ld += c;
-                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr);
-                    else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; }
+                    else if constexpr (ImmediatePush<MODE>::value) pushShadowNow(sink, 1, scatterPos, ls.direction, ls.dist - PTB_EPS, c * thr, (uint32_t)idx);
+                    else { sb.valid = true; sb.o = scatterPos; sb.d = ls.direction; sb.maxDist = ls.dist - PTB_EPS; sb.c = c * thr; sb.light = (uint32_t)idx; }
                 }
             }
         }
@@ -691,9 +725,9 @@ __device__ __forceinline__ float3 directLight(const DevScene& S, const FramePara
 // One iteration of the PathTrace loop body after ClosestHit (pathtrace.glsl:303-471) for path slot p.
 template <int MODE>
 __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& F, const PathState& P, uint32_t p, bool firstIter, bool& cont, ShadowOut& sa, ShadowOut& sb, InlineCounters& ic,
-                                          uint32_t* ctrThis)
+                                          uint32_t* ctrThis, const SlotShadow& ss)
 {
-    const ShadowSink sink{&P, &ctrThis[CTR_NSHA], &ctrThis[CTR_NSHB], p};
+    const ShadowSink sink{&P, &ctrThis[CTR_NSHA], &ctrThis[CTR_NSHB], p, ss};
     const float4 ro4 = P.rayO[p], rd4 = P.rayD[p], hit4 = P.hit[p];
     const float4 thr4 = firstIter ? make_float4(1.f, 1.f, 1.f, 0.f) : P.thr[p], rad4 = firstIter ? make_float4(0.f, 0.f, 0.f, 1.f) : P.rad[p];
     const int hitInst = P.hitInst[p];
@@ -867,8 +901,19 @@ __device__ __forceinline__ void shadePath(const DevScene& S, const FrameParams& 
     }
 }
 
-__device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32_t* ctr, uint32_t lane, const ShadowOut& s, uint32_t p)
+__device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32_t* ctr, uint32_t lane, const ShadowOut& s, uint32_t p, const SlotShadow& ss)
 {
+    if (ss.keys[which])
+    {   // slot-ordered queue: the record goes to index p (see SlotShadow)
+        if (s.valid)
+        {
+            P.shO[which][p] = make_float4(s.o.x, s.o.y, s.o.z, s.maxDist);
+            P.shD[which][p] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(p));
+            P.shC[which][p] = make_float4(s.c.x, s.c.y, s.c.z, 0.f);
+            ss.keys[which][p] = shadowKey(ss, which, s.d, s.light);
+        }
+        return;
+    }
     unsigned m = __ballot_sync(0xffffffffu, s.valid);
     if (!m) return;
     uint32_t b = 0;
@@ -888,27 +933,13 @@ __device__ __forceinline__ void pushShadow(const PathState& P, int which, uint32
 //   SHADE_STATIC     chunks are dealt to the warps round-robin (uniform work per chunk: no fetch atomic to wait for)
 //   SHADE_COUNT_ONLY the continuing paths are counted, not queued (the next trace runs over the slots in screen order: slot-ordered bounce 1)
 //   SHADE_OCT_KEYS   direction class of the continuation ray = cell of an 8x8 octahedral map (64 classes, 64 = ended) instead of dominant axis + sign (6 classes, 7 = ended)
-enum { SHADE_IDENTITY = 1, SHADE_STATIC = 2, SHADE_COUNT_ONLY = 4, SHADE_OCT_KEYS = 8 };
+enum { SHADE_IDENTITY = 1, SHADE_STATIC = 2, SHADE_COUNT_ONLY = 4, SHADE_OCT_KEYS = 8, SHADE_OCT16_KEYS = 16 /* 16x16 cells, 256 = ended */ };
 
-// Cell of direction d in an 8x8 octahedral map, rows walked boustrophedon so that consecutive cells are neighbours on the sphere.
-__device__ __forceinline__ uint32_t octCell(float dx, float dy, float dz)
-{
-    const float inv = rcpApprox(fabsf(dx) + fabsf(dy) + fabsf(dz));
-    float u = dx * inv, v = dy * inv;
-    if (dz < 0.f)
-    {
-        const float uu = (1.0f - fabsf(v)) * (u < 0.f ? -1.0f : 1.0f), vv = (1.0f - fabsf(u)) * (v < 0.f ? -1.0f : 1.0f);
-        u = uu; v = vv;
-    }
-    int iu = (int)((u * 0.5f + 0.5f) * 8.0f), iv = (int)((v * 0.5f + 0.5f) * 8.0f);
-    iu = min(max(iu, 0), 7); iv = min(max(iv, 0), 7);
-    return (uint32_t)(iv * 8 + ((iv & 1) ? 7 - iu : iu));
-}
 
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, FrameParams F, PathState P, const uint32_t* __restrict__ queue, uint32_t* ctrThis,
                                                           uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* __restrict__ slotKeys, uint32_t nOverride,
-                                                          uint32_t flags)
+                                                          uint32_t flags, SlotShadow ss)
 {
     const uint32_t n = nOverride ? nOverride : ctrThis[CTR_NPATHS];
     const uint32_t lane = threadIdx.x & 31u;
@@ -933,16 +964,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
             p = (flags & SHADE_IDENTITY) ? (P.hitInst[i] == PTB_HIT_DEAD ? 0xffffffffu : i) : queue[i];
             if (p != 0xffffffffu)                     // (hole of a slot-ordered queue)
             {
-                shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis);
+                shadePath<MODE>(S, F, P, p, firstIter != 0, cont, sa, sb, ic, ctrThis, ss);
                 if (slotKeys)
                 {   // direction class of the continuation ray (dominant axis, sign) per path SLOT, 7 = path ended: the bounce-1 trace runs over
                     // the slots in screen order, grouped by this class inside tiles
-                    uint32_t k = (flags & SHADE_OCT_KEYS) ? 64u : 7u;
+                    uint32_t k = (flags & SHADE_OCT16_KEYS) ? 256u : (flags & SHADE_OCT_KEYS) ? 64u : 7u;
                     if (cont)
                     {
                         const float4 d4 = P.rayD[p];
                         const float ax = fabsf(d4.x), ay = fabsf(d4.y), az = fabsf(d4.z);
-                        if (flags & SHADE_OCT_KEYS) k = octCell(d4.x, d4.y, d4.z);
+                        if (flags & SHADE_OCT16_KEYS) k = octCell<16>(d4.x, d4.y, d4.z);
+                        else if (flags & SHADE_OCT_KEYS) k = octCell(d4.x, d4.y, d4.z);
                         else k = (ax >= ay && ax >= az) ? (d4.x < 0.f ? 1u : 0u) : (ay >= az ? (d4.y < 0.f ? 3u : 2u) : (d4.z < 0.f ? 5u : 4u));
                     }
                     slotKeys[p] = k;
@@ -960,8 +992,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(DevScene S, Frame
         }
         if constexpr (!ImmediatePush<MODE>::value)
         {
-            if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p);
-            pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p);
+            if (MODE >= 1) pushShadow(P, 0, &ctrThis[CTR_NSHA], lane, sa, p, ss);
+            pushShadow(P, 1, &ctrThis[CTR_NSHB], lane, sb, p, ss);
         }
     }
     if ((flags & SHADE_COUNT_ONLY) && lane == 0 && continued) atomicAdd(&ctrNext[CTR_NPATHS], continued);       // one reduction per warp, nothing waits for it
@@ -986,19 +1018,27 @@ struct AlphaMask   // deferred AnyHit alpha test: MASK only (BLEND needs the pat
 
 template <bool ALPHA, bool CULL, class AlphaFn>
 __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams& F, const PathState& P, int which, uint32_t n, uint32_t* fetchCtr,
-                                           AlphaFn alphaFn)
+                                           AlphaFn alphaFn, const uint32_t* __restrict__ idxQueue, DevStats* stats)
 {
     const uint32_t lane = threadIdx.x & 31u;
     SmemStack stk(g_stackSmem + threadIdx.x, (int)blockDim.x);
     const bool lights = OPT(F, O_LIGHTS);
+    uint32_t traced = 0;
     while (true)
     {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(fetchCtr, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n)
+        uint32_t i = base + lane;
+        bool live = i < n;
+        if (idxQueue)
+        {   // slot-ordered queue: entry = index of the record (the path slot), 0xffffffff = hole
+            i = live ? idxQueue[i] : 0xffffffffu;
+            live = i != 0xffffffffu;
+            traced += live ? 1u : 0u;
+        }
+        if (live)
         {
             const float4 o4 = P.shO[which][i], d4 = P.shD[which][i];
             const float3 o = f3(o4), d = f3(d4);
@@ -1021,17 +1061,23 @@ __device__ __forceinline__ void shadowLoop(const DevScene& S, const FrameParams&
             }
         }
     }
+    if (idxQueue)
+    {
+        traced = __reduce_add_sync(0xffffffffu, traced);
+        if (lane == 0 && traced) atomicAdd(&stats->shadowRays, (unsigned long long)traced);
+    }
 }
 
+// idxQueue != nullptr: slot-ordered queue of nOverride entries (record indices with holes, see SlotShadow); else the compacted queue of *countPtr records
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, FrameParams F, PathState P, int which, const uint32_t* __restrict__ countPtr,
-                                                           uint32_t* fetchCtr, DevStats* stats)
+                                                           uint32_t* fetchCtr, DevStats* stats, const uint32_t* __restrict__ idxQueue, uint32_t nOverride)
 {
-    const uint32_t n = *countPtr;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->shadowRays, (unsigned long long)n);
+    const uint32_t n = idxQueue ? nOverride : *countPtr;
+    if (!idxQueue && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats->shadowRays, (unsigned long long)n);
     const bool alpha = OPT(F, O_ALPHA) && !OPT(F, O_MEDIUM);
-    if (alpha) shadowLoop<true, true>(S, F, P, which, n, fetchCtr, AlphaMask{&S});
-    else if (F.cullBoxes) shadowLoop<false, true>(S, F, P, which, n, fetchCtr, NoAlpha());
-    else shadowLoop<false, false>(S, F, P, which, n, fetchCtr, NoAlpha());
+    if (alpha) shadowLoop<true, true>(S, F, P, which, n, fetchCtr, AlphaMask{&S}, idxQueue, stats);
+    else if (F.cullBoxes) shadowLoop<false, true>(S, F, P, which, n, fetchCtr, NoAlpha(), idxQueue, stats);
+    else shadowLoop<false, false>(S, F, P, which, n, fetchCtr, NoAlpha(), idxQueue, stats);
 }
 
 // ------------------------------------------------------------------ transmittance (NEE under OPT_MEDIUM + OPT_VOL_MIS) -------
@@ -1345,23 +1391,25 @@ void ptbk_sort(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, 
 }
 
 void ptbk_shade(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, const uint32_t* queue,
-                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride, uint32_t flags)
+                uint32_t* ctrThis, uint32_t* ctrNext, uint32_t* nextQueue, DevStats* stats, int firstIter, uint32_t* slotKeys, uint32_t nOverride, uint32_t flags,
+                uint32_t* shadowKeysA, uint32_t* shadowKeysB, int lightKeys)
 {
     const int* bps = c.shadeBlocks;
-    if (F.general == 2 && F.inlineShadow) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
-    else if (F.general == 2) k_shade<3, 4><<<c.numSMs * bps[3], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
-    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+    const SlotShadow ss{{shadowKeysA, shadowKeysB}, lightKeys ? 1u : 0u};
+    if (F.general == 2 && F.inlineShadow) k_shade<2, 4><<<c.numSMs * bps[2], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags, ss);
+    else if (F.general == 2) k_shade<3, 4><<<c.numSMs * bps[3], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags, ss);
+    else if (F.general == 1) k_shade<1, 5><<<c.numSMs * bps[1], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags, ss);
     else if (PTB_SHADE_LATER_BLOCKS != 4 && !firstIter)
-        k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
-    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags);
+        k_shade<0, PTB_SHADE_LATER_BLOCKS><<<c.numSMs * PTB_SHADE_LATER_BLOCKS, SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags, ss);
+    else k_shade<0, 4><<<c.numSMs * bps[0], SHADE_THREADS, 0, st(c)>>>(S, F, P, queue, ctrThis, ctrNext, nextQueue, stats, firstIter, slotKeys, nOverride, flags, ss);
     COUNT_LAUNCH(c, 1);
 }
 
 void ptbk_shadow(const LaunchCfg& c, const DevScene& S, const FrameParams& F, const PathState& P, int which, const uint32_t* countPtr,
-                 uint32_t* fetchCtr, DevStats* stats)
+                 uint32_t* fetchCtr, DevStats* stats, const uint32_t* idxQueue, uint32_t nOverride)
 {
     const int bps = c.shadowBlocks;
-    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytesAny(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats);
+    k_shadow<<<c.numSMs * bps, TRACE_THREADS, stackBytesAny(S, TRACE_THREADS), st(c)>>>(S, F, P, which, countPtr, fetchCtr, stats, idxQueue, nOverride);
     COUNT_LAUNCH(c, 1);
 }
 
