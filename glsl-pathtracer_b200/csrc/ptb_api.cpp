@@ -109,6 +109,7 @@ struct PtbCtx
     int blockMajor = 1;        // 1: the 32-slot groups of a wave are ordered block-major (WaveParams::blockMajor, PTB_BLOCK_MAJOR)
     int dirBins = 16;          // direction classes of the slot-ordered bounce 1: 16 / 8 = 16x16 / 8x8 octahedral cells, 0 = dominant axis + sign (PTB_DIR_BINS)
     int slotShadow = 1;        // 1: the NEE rays of the first shade pass are queued by path slot and grouped by light / direction inside tiles (SlotShadow, PTB_SLOT_SHADOW)
+    int warpSamplesLog2 = 5;   // upper bound of WaveParams::lps (PTB_WARP_SAMPLES_LOG2): 0 = a warp's primary rays are one 8x4 pixel block of one pass
     int fuseCamera = 1;        // 1: camera rays are generated inside the first closest-hit launch (PTB_FUSE_CAMERA)
     int slotOrder = 1;         // 1: bounce 1 runs over the path slots in screen order (holes for ended paths), grouped by direction class inside
                                //    tiles of 2048 slots, instead of over the compacted arrival-order queue (PTB_SLOT_ORDER)
@@ -349,6 +350,14 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     W.vw = (W.rw + 7) & ~7; W.vh = (W.rh + 3) & ~3;
     W.nSlots = (uint32_t)((size_t)W.vw * W.vh * W.nSamples);
     W.blockMajor = (c->blockMajor && W.nSamples > 1) ? 1 : 0;
+    W.lps = 0; W.lpw = 3;
+    if (W.blockMajor)
+    {   // passes per warp group: the largest power of two that divides the pass count, up to 32 (one pixel, 32 passes)
+        int lps = 0;
+        while (lps < 5 && lps < c->warpSamplesLog2 && (W.nSamples & ((2 << lps) - 1)) == 0) lps++;
+        static const int lpwOf[6] = {3, 2, 2, 1, 1, 0};      // sub-block 8x4, 4x4, 4x2, 2x2, 2x1, 1x1 pixels
+        W.lps = lps; W.lpw = lpwOf[lps];
+    }
     int rc = ensureWaveState(c, W.nSlots);
     if (rc) return rc;
     PathState P = pathState(c);
@@ -583,6 +592,7 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     if (const char* e = getenv("PTB_DEFER_TRANSMIT")) c->deferTransmit = atoi(e);
     if (const char* e = getenv("PTB_BLOCK_MAJOR")) c->blockMajor = atoi(e);
     if (const char* e = getenv("PTB_SLOT_SHADOW")) c->slotShadow = atoi(e);
+    if (const char* e = getenv("PTB_WARP_SAMPLES_LOG2")) c->warpSamplesLog2 = atoi(e);
     if (const char* e = getenv("PTB_DIR_BINS")) c->dirBins = atoi(e);
     if (const char* e = getenv("PTB_STREAM_SHADE")) c->streamShade = atoi(e);
     if (const char* e = getenv("PTB_TRACE_FINISH")) c->traceFinish = atoi(e);

@@ -95,6 +95,7 @@ struct WaveParams
     int previewMode;           // preview.glsl: InitRNG(gl_FragCoord, 1), TexCoords over the whole image, depth 2
     uint32_t nSlots;           // vw*vh*nSamples
     int accFirst, accCount;    // k_accumulate adds the wave's passes [accFirst, accFirst+accCount) to the running sum (accCount 0 = all of them)
+    int lps, lpw;              // block-major only: log2(sample passes per 32-slot group), log2(width of the group's pixel sub-block); see groupToPixel in ptb_kernels.cu
     int blockMajor;            // order of the 32-slot groups (one 8x4 pixel block of one sample pass each): 0 = sample-major (all blocks of pass 0, then pass 1, ...),
                                // 1 = block-major (all passes of block 0, then block 1, ...): a 2048-slot tile then holds the paths of a few neighbouring pixels,
                                // so the tile-local grouping by direction yields warps whose rays share origin AND direction

@@ -34,24 +34,51 @@ constexpr int SHADE_THREADS = 128;
 #endif
 
 // ------------------------------------------------------------------ slot <-> pixel mapping ----------------------
-// Path slots of one sample pass are ordered in 8x4 pixel blocks so that a warp's primary rays are spatially coherent.
+// A wave holds nSamples sample passes of a pixel rectangle padded to 8x4 pixel blocks; 32 consecutive slots ("group") are the primary rays of one warp.
+//   sample-major (blockMajor = 0): group = one 8x4 block of one pass; all blocks of pass 0, then pass 1, ...
+//   block-major  (blockMajor = 1): the 32 * nSamples slots of an 8x4 block are consecutive (a 2048-slot tile then holds the paths of a few neighbouring pixels,
+//     which is what lets the tile-local grouping by direction / light build warps that share origin AND direction).  Inside the block a group is
+//     2^lps consecutive passes of a (2^lpw x 2^lph)-pixel sub-block (lpw + lph + lps = 5): lps = 0 -> the 8x4 block of one pass, lps = 5 -> 32 passes of ONE pixel —
+//     rays through one pixel differ by the sub-pixel jitter only, so the warp stays converged in the traversal and hits one material in the first shade pass.
+// group -> (sample pass, pixel) of lane `lane`
+__device__ __forceinline__ void groupToPixel(const WaveParams& W, uint32_t g, uint32_t lane, uint32_t blocksX, uint32_t blocksPerSample, int& s, int& px, int& py)
+{
+    uint32_t b, pxin = lane & 7u, pyin = lane >> 3;
+    if (W.blockMajor)
+    {
+        const uint32_t nS = (uint32_t)W.nSamples, lps = (uint32_t)W.lps, lpw = (uint32_t)W.lpw, lpp = 5u - lps /* log2(pixels per sub-block) */;
+        b = g / nS;
+        const uint32_t gi = g - b * nS;                  // group inside the block: sub-block major, then sample group
+        const uint32_t nsg = nS >> lps;                  // sample groups per sub-block
+        const uint32_t pb = gi / nsg, sg = gi - pb * nsg;
+        const uint32_t ls = lane >> lpp, pi = lane & ((1u << lpp) - 1u);
+        s = (int)((sg << lps) + ls);
+        const uint32_t pbx = pb & ((8u >> lpw) - 1u), pby = pb >> (3u - lpw);
+        pxin = (pbx << lpw) + (pi & ((1u << lpw) - 1u));
+        pyin = (pby << (lpp - lpw)) + (pi >> lpw);
+    }
+    else { s = (int)(g / blocksPerSample); b = g - (uint32_t)s * blocksPerSample; }
+    const uint32_t by = b / blocksX, bx = b - by * blocksX;
+    px = (int)(bx * 8u + pxin);
+    py = (int)(by * 4u + pyin);
+}
 __device__ __forceinline__ bool slotToPixel(const WaveParams& W, uint32_t slot, int& s, int& px, int& py)
 {
     const uint32_t blocksX = (uint32_t)W.vw >> 3, blocksPerSample = blocksX * ((uint32_t)W.vh >> 2);
-    const uint32_t g = slot >> 5, l = slot & 31u;
-    uint32_t b;
-    if (W.blockMajor) { b = g / (uint32_t)W.nSamples; s = (int)(g - b * (uint32_t)W.nSamples); }
-    else { s = (int)(g / blocksPerSample); b = g - (uint32_t)s * blocksPerSample; }
-    px = (int)((b % blocksX) * 8u + (l & 7u));
-    py = (int)((b / blocksX) * 4u + (l >> 3));
+    groupToPixel(W, slot >> 5, slot & 31u, blocksX, blocksPerSample, s, px, py);
     return px < W.rw && py < W.rh;
 }
 
-// slot of sample pass k for the pixel with index idx (= block * 32 + lane) inside one pass
+// slot of sample pass k for the pixel with index idx (= 8x4 block * 32 + row-major pixel inside the block)
 __device__ __forceinline__ uint32_t slotOfSample(const WaveParams& W, uint32_t idx, uint32_t k)
 {
-    if (W.blockMajor) return (((idx >> 5) * (uint32_t)W.nSamples + k) << 5) | (idx & 31u);
-    return idx + k * (uint32_t)W.vw * (uint32_t)W.vh;
+    if (!W.blockMajor) return idx + k * (uint32_t)W.vw * (uint32_t)W.vh;
+    const uint32_t nS = (uint32_t)W.nSamples, lps = (uint32_t)W.lps, lpw = (uint32_t)W.lpw, lpp = 5u - lps, lph = lpp - lpw;
+    const uint32_t pxin = idx & 7u, pyin = (idx >> 3) & 3u;
+    const uint32_t pb = ((pyin >> lph) << (3u - lpw)) + (pxin >> lpw);
+    const uint32_t pi = ((pyin & ((1u << lph) - 1u)) << lpw) + (pxin & ((1u << lpw) - 1u));
+    const uint32_t gi = pb * (nS >> lps) + (k >> lps);
+    return ((((idx >> 5) * nS + gi) << 5) | ((k & ((1u << lps) - 1u)) << lpp)) + pi;
 }
 
 __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0)
@@ -207,12 +234,8 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
         float3 o, d; int depth = 0; float prevPdf = 0.0f;
         if (CAM)
         {   // slot -> (sample, 8x4 block, pixel): the divisions are per fetch, not per pixel (n is a multiple of 32)
-            const uint32_t b = base >> 5;
-            uint32_t s, bb;
-            if (W.blockMajor) { bb = b / (uint32_t)W.nSamples; s = b - bb * (uint32_t)W.nSamples; }
-            else { s = b / blocksPerSample; bb = b - s * blocksPerSample; }
-            const uint32_t by = bb / blocksX, bx = bb - by * blocksX;
-            const int px = (int)(bx * 8u + (lane & 7u)), py = (int)(by * 4u + (lane >> 3));
+            int s, px, py;
+            groupToPixel(W, base >> 5, lane, blocksX, blocksPerSample, s, px, py);
             const bool live = px < W.rw && py < W.rh;
             pq = live ? i : 0xffffffffu;
             P.queue[0][i] = pq;
@@ -220,7 +243,7 @@ __device__ __forceinline__ void traceLoop(const DevScene& S, const FrameParams& 
             if (live)
             {
                 Rng rng;
-                cameraRay(F, W, W.x0 + px, W.y0 + py, W.firstSample + (int)s * W.sampleStride, rng, o, d);
+                cameraRay(F, W, W.x0 + px, W.y0 + py, W.firstSample + s * W.sampleStride, rng, o, d);
                 P.rayO[i] = make_float4(o.x, o.y, o.z, 0.0f);
                 P.rayD[i] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
                 P.rng[i] = rng.s;             // throughput (1) / radiance (0) / alpha (1) are implied in the first shade iteration
