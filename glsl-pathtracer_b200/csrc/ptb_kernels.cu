@@ -27,7 +27,10 @@ enum {
 };
 
 constexpr int TRACE_THREADS = 256;
-constexpr int TRACE_MIN_BLOCKS = 5;     // 48 registers: measured 772 spp/s vs 720 (3 blocks, 72 regs), 767 (4), 753 (6)
+#ifndef PTB_TRACE_MINB
+#define PTB_TRACE_MINB 5
+#endif
+constexpr int TRACE_MIN_BLOCKS = PTB_TRACE_MINB;     // 48 registers: measured 772 spp/s vs 720 (3 blocks, 72 regs), 767 (4), 753 (6)
 constexpr int SHADE_THREADS = 128;
 #ifndef PTB_SHADE_LATER_BLOCKS
 #define PTB_SHADE_LATER_BLOCKS 4      // resident k_shade<0> blocks per SM for the bounces after the first (latency-bound: scattered, material-sorted state)
@@ -378,7 +381,10 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
 // while every warp still touches path slots from one 2048-entry window, so the scattered state fetches stay sector/page local.
 // queue == nullptr: the entries are the indices themselves (slot order).  Entries whose key is holeKey come out as 0xffffffff ("hole") at the
 // end of their tile; keys above numKeys-1 are clamped.  nOverride != 0 replaces *countPtr as the number of entries.
-__global__ void __launch_bounds__(256) k_sort_tile_local(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
+#ifndef PTB_SORT_MINB
+#define PTB_SORT_MINB 6      // resident sorter blocks per SM (40 registers): 1.26 -> 1.07 ms of sorting per hyperion step against 4
+#endif
+__global__ void __launch_bounds__(256, PTB_SORT_MINB) k_sort_tile_local(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
                                                           uint32_t* __restrict__ sorted, int numKeys, int holeKey, uint32_t nOverride)
 {
     extern __shared__ uint32_t sm[];
@@ -1400,7 +1406,7 @@ void ptbk_trace_primary(const LaunchCfg& c, const DevScene& S, const FrameParams
 
 void ptbk_sort_tile_local(const LaunchCfg& c, const uint32_t* queue, const uint32_t* keys, const uint32_t* countPtr, int numKeys, uint32_t* sorted, int holeKey, uint32_t nOverride)
 {
-    k_sort_tile_local<<<c.numSMs * 4, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys, holeKey, nOverride);
+    k_sort_tile_local<<<c.numSMs * PTB_SORT_MINB, 256, (size_t)numKeys * 2 * sizeof(uint32_t), st(c)>>>(queue, keys, countPtr, sorted, numKeys, holeKey, nOverride);
     COUNT_LAUNCH(c, 1);
 }
 
