@@ -170,15 +170,16 @@ def peaks():
 
 
 def capture(workload):
-    """ncu-derived figures of the committed capture (profiles/r02_capture.json, written by scripts/make_profiles.py from the raw ncu
+    """ncu-derived figures of the committed capture (profiles/rNN_capture.json of the latest round, written by scripts/make_profiles.py from the raw ncu
     reports): DRAM bytes of the dominant kernel per step, thread/warp instructions of the traversal kernels, L2 bytes.  They are
     properties of the kernels at the capture's commit (recorded in the file), not of this run — bench.py cannot count instructions
     without a profiler — and are passed through labelled as such; absent file or other workload: None."""
-    p = os.path.join(ROOT, "profiles", "r02_capture.json")
-    if os.path.exists(p):
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_capture.json")), reverse=True):      # the latest round's capture
         with open(p) as f:
             c = json.load(f)
         if c.get("workload") == workload:
+            c["file"] = os.path.relpath(p, ROOT)
             return c
     return None
 
@@ -480,7 +481,7 @@ def run_ours(args):
                                   "l2_peak_gbs": l2_peak, "l2_peak_source": "profiles/r02_l2_peak.json (scripts/measure_l2_peak.py: L2-resident copy, read+write)",
                                   "frac": (ti / (sms * 4 * 32 * clk_hz * trace_ms_last * 1e-3) if ti and trace_ms_last > 0 else None),
                                   "k_shadow_frac_in_capture": cap.get("k_shadow_lane_issue_frac"), "k_trace_frac_in_capture": cap.get("k_trace_lane_issue_frac"),
-                                  "l2_gbs_in_capture": cap.get("k_trace_l2_gbs"), "capture_commit": cap.get("commit"), "capture_file": "profiles/r02_capture.json",
+                                  "l2_gbs_in_capture": cap.get("k_trace_l2_gbs"), "capture_commit": cap.get("commit"), "capture_file": cap.get("file"),
                                   "what": "thread instructions / (148 SMs x 4 issue slots x 32 lanes x SM clock x k_trace time of this run)"}
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": warm,

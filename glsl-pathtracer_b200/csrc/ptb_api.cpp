@@ -77,6 +77,8 @@ struct PtbCtx
     int numNodes = 0, topLevelIndex = 0;
 
     DevBuf<float> nodes, lights, envImg, envCdf;
+    DevBuf<uint32_t> envGuide;   // guide table of the env-map CDF search (ptbd_build_env_guide)
+    int envGuideOn = 1;          // PTB_ENV_GUIDE
     DevBuf<int> vertIndices;
     DevBuf<float4> triShade, wide;
     DevBuf<uint32_t> lightGrid;
@@ -236,6 +238,18 @@ void refreshFrameParams(PtbCtx* c)
     F.aspect = (float)o.renderH / (float)o.renderW;
     F.camScale = tanf(cam.fov * 0.5f); F.camFocalDist = cam.focalDist; F.camAperture = cam.aperture;
     refreshDerivedFlags(c);
+}
+
+// guide table of the env-map CDF search; absent (null) when the CDF is not monotone: the kernels then run the reference's two binary searches
+int buildEnvGuide(PtbCtx* c, const float* cdf, int w, int h, float totalSum)
+{
+    std::vector<uint32_t> g; float scale = 0.f;
+    c->S.envGuide = nullptr; c->S.envGuideN = 0; c->S.envGuideScale = 0.f;
+    if (!c->envGuideOn || !cdf || w <= 0 || ptbd_build_env_guide(cdf, w, h, totalSum, g, scale) != 0) return PTB_OK;
+    CK(c->envGuide.upload(g.data(), g.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->S.envGuide = c->envGuide.p; c->S.envGuideN = (int)g.size() - 1; c->S.envGuideScale = scale;
+    return PTB_OK;
 }
 
 int buildLightsPre(PtbCtx* c, const float* lights, int n)
@@ -568,6 +582,8 @@ int ptb_create(const PtbSceneDesc* d, const PtbOptions* o, int device, PtbCtx** 
     S.numMaterials = d->numMaterials; S.numInstances = d->numInstances; S.numLights = d->numLights;
     S.numTextures = d->numTextures; S.texW = d->texW; S.texH = d->texH;
     S.envW = d->envImg ? d->envW : 0; S.envH = d->envImg ? d->envH : 0; S.envTotalSum = d->envTotalSum;
+    if (const char* e = getenv("PTB_ENV_GUIDE")) c->envGuideOn = atoi(e);
+    if (d->envImg && d->envW > 0) { int grc = buildEnvGuide(c, d->envCdf, d->envW, d->envH, d->envTotalSum); if (grc) { ptb_destroy(c); return grc; } }
 
     if (const char* e = getenv("PTB_WIDE_ANY")) c->wideAny = atoi(e);
     int rc;
@@ -607,7 +623,7 @@ int ptb_destroy(PtbCtx* c)
     if (!c) return PTB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->vertIndices.release();
+    c->nodes.release(); c->lights.release(); c->envImg.release(); c->envCdf.release(); c->envGuide.release(); c->vertIndices.release();
     c->verticesUVX.release(); c->normalsUVY.release(); c->materials.release(); c->transforms.release(); c->inner.release(); c->tris.release(); c->triShade.release(); c->wide.release(); c->tlasBlasRoot.release(); c->tlasMatID.release(); c->tlasNodeOf.release(); c->tlasRemap.release(); c->tlasResult.release(); c->tlasBounds.release(); c->tlasCent.release(); for (int k = 0; k < 3; k++) c->tlasRec[k].release();
     c->instTrav.release(); c->instShade.release(); c->lightsPre.release(); c->lightGroups.release(); c->lightGrid.release(); c->textures.release(); c->accum.release(); c->preview.release(); c->out8.release(); c->snapshot.release(); c->snapshotF.release(); c->pixTabX.release(); c->pixTabY.release();
     c->state.release();
@@ -770,6 +786,7 @@ int ptb_update_envmap(PtbCtx* c, const float* img, const float* cdf, int32_t w, 
     CK(c->envCdf.upload(cdf, (size_t)w * h, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->S.envImg = c->envImg.p; c->S.envCdf = c->envCdf.p; c->S.envW = w; c->S.envH = h; c->S.envTotalSum = totalSum;
+    { int grc = buildEnvGuide(c, cdf, w, h, totalSum); if (grc) return grc; }
     c->sceneVersion++;
     int cull = c->F.cullBoxes;
     refreshFrameParams(c);

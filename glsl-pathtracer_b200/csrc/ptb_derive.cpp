@@ -550,3 +550,25 @@ int ptbd_build_tlas_host(const float* N, int topLevelIndex, const float* transfo
     if (heightOut) *heightOut = B.height;
     return 0;
 }
+
+int ptbd_build_env_guide(const float* cdf, int w, int h, float totalSum, std::vector<uint32_t>& guide, float& scale)
+{
+    guide.clear(); scale = 0.f;
+    const size_t n = (size_t)w * h;
+    if (!cdf || n < 2 || n >= (1u << 30) || !(totalSum > 0.f) || !std::isfinite(totalSum)) return 1;
+    for (size_t i = 0; i < n; i++)
+        if (!std::isfinite(cdf[i]) || (i && cdf[i] < cdf[i - 1])) return 1;
+    uint32_t G = 1024;
+    while (G < (1u << 20) && (size_t)G * 2 <= n) G *= 2;          // about two texels per bucket, 4 KB .. 4 MB
+    scale = (float)G / totalSum;
+    if (!std::isfinite(scale) || !(scale > 0.f)) return 1;
+    guide.assign((size_t)G + 1, 0u);
+    const float top = (float)(G - 1);
+    for (size_t i = 0; i < n; i++)
+    {
+        const float x = std::fmin(std::fmax(cdf[i] * scale, 0.0f), top);     // the same single-precision product and clamp as the device
+        guide[(size_t)(int)x + 1]++;
+    }
+    for (uint32_t b = 0; b < G; b++) guide[b + 1] += guide[b];
+    return 0;
+}

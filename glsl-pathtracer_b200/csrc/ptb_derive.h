@@ -53,3 +53,9 @@ void ptbd_instance_bounds(const float* nodes, const float* transforms, int numIn
 void ptbd_build_lights(const float* lights, int n, PtbDerivedLights& out);
 // per-column / per-row pixel tables: {frame texture coordinate of the pixel centre (tile.glsl:43), bits(tile-local coordinate | tile index << 16)}
 int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std::vector<float2>& tabX, std::vector<float2>& tabY, std::string& err);
+// Guide table for the environment-map CDF search (envmap.glsl:28-55, envBinarySearch in ptb_device.cuh).  The CDF is ONE running sum over the image
+// (EnvironmentMap.cpp:52-58), so when it is non-decreasing the reference's two binary searches (row, then column) return the position of the first
+// texel whose CDF exceeds the value, whatever the probing sequence.  guide[b] = number of texels whose CDF value falls in a bucket below b, with
+// bucket(v) = (int)clamp(v * scale, 0, G - 1), G = guide.size() - 1: the first texel above a value of bucket b lies in [guide[b], guide[b + 1]].
+// Returns 0 and fills guide / scale, or 1 when the table does not apply (CDF not monotone / not finite): the device then runs the reference's search.
+int ptbd_build_env_guide(const float* cdf, int w, int h, float totalSum, std::vector<uint32_t>& guide, float& scale);

@@ -58,6 +58,8 @@ struct DevScene
     int numNodes, topLevelIndex, numIndices, numVertices, numMaterials, numInstances, numLights;
     int numTextures, texW, texH, envW, envH;
     float envTotalSum;
+    const uint32_t* envGuide;   // guide table of the CDF search (ptbd_build_env_guide): envGuideN + 1 entries; null = the reference's two binary searches
+    float envGuideScale; int envGuideN;
     int stackDepth;             // traversal stack entries needed (bottom sentinel + TLAS path + marker + BLAS path) in the binary hierarchy
     int stackDepthAny;          // ... by the any-hit kernels: max of the binary and the 4-wide hierarchy's bound
 };

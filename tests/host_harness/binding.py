@@ -23,6 +23,7 @@ def lib():
         L.hh_wide_nodes.argtypes = [vp]
         L.hh_build_tlas.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
+        L.hh_env_search.argtypes = [vp, i32, i32, f32, vp, i32, vp, vp]; L.hh_env_search.restype = i32
         _LIB = L
     return _LIB
 
@@ -94,3 +95,11 @@ def build_tlas(nodes, top, transforms, material_ids=None):
     if rc:
         raise RuntimeError(f"ptbd_build_tlas_host failed: {rc}")
     return out, h.value
+
+
+def env_search(cdf, w, h, total_sum, values):
+    """(has_guide, uv with the guide table, uv of the reference's two binary searches) for the product's envBinarySearch compiled for the host"""
+    cdf = np.ascontiguousarray(cdf, np.float32).ravel(); values = np.ascontiguousarray(values, np.float32)
+    fast = np.zeros((len(values), 2), np.float32); ref = np.zeros((len(values), 2), np.float32)
+    have = lib().hh_env_search(cdf.ctypes.data, w, h, float(total_sum), values.ctypes.data, len(values), fast.ctypes.data, ref.ctypes.data)
+    return bool(have), fast, ref

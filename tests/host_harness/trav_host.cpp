@@ -133,6 +133,20 @@ void hh_camera_rays(int renderW, int renderH, int tileW, int tileH, const float*
     }
 }
 
+// Environment-map CDF search (envBinarySearch): with the guide table (ptbd_build_env_guide) and as the reference's two binary searches.  Returns 1 when a guide
+// exists for this CDF (0: the device would run the reference search; outFast then repeats it).
+int hh_env_search(const float* cdf, int w, int h, float totalSum, const float* values, int n, float* outFast, float* outRef)
+{
+    DevScene S{};
+    S.envCdf = cdf; S.envW = w; S.envH = h; S.envTotalSum = totalSum;
+    std::vector<uint32_t> guide; float scale = 0.f;
+    const int have = ptbd_build_env_guide(cdf, w, h, totalSum, guide, scale) == 0;
+    for (int i = 0; i < n; i++) { const float2 r = envBinarySearch(S, values[i]); outRef[i * 2] = r.x; outRef[i * 2 + 1] = r.y; }
+    if (have) { S.envGuide = guide.data(); S.envGuideN = (int)guide.size() - 1; S.envGuideScale = scale; }
+    for (int i = 0; i < n; i++) { const float2 r = envBinarySearch(S, values[i]); outFast[i * 2] = r.x; outFast[i * 2 + 1] = r.y; }
+    return have;
+}
+
 // TLAS rebuild (ptbd_build_tlas_host) from the scene's own arrays: blasRoot / materialID per instance are read from the current TLAS leaves
 int hh_build_tlas(const float* nodes, int numNodes, int topLevelIndex, const float* transforms, int numInstances, const int32_t* materialIDs, float* tlasOut, int* heightOut)
 {

@@ -77,3 +77,32 @@ def test_tlas_rebuild_after_an_instance_edit_matches_the_reference(name):
     mats = np.zeros(len(leaves), np.int32); mats[(-leaves[:, 8] - 1).astype(int)] = leaves[:, 7].astype(np.int32)     # meshInstances[i].materialID after the edit
     tlas, _ = build_tlas(nodes, sc.topLevelIndex, sc2.transforms, mats)     # old node array (BLAS boxes, BLAS roots) + NEW transforms and material ids
     assert tlas.tobytes() == want.tobytes()
+
+
+def test_env_cdf_guide_table_returns_the_texel_of_the_reference_search():
+    """SampleEnvMap's BinarySearch (envmap.glsl:28-55) through the guide table of ptbd_build_env_guide == the two binary searches, bit for bit: on the
+    fixture's CDF and on adversarial ones (long runs of equal values = black texels, a single bright texel, values on / next to every CDF entry,
+    0, totalSum and beyond).  A non-monotone CDF gets no table."""
+    from host_harness import binding as hb
+    rng = np.random.default_rng(5)
+    sc = scene_at("ibl_spheres", 64, 36)
+    h, w = sc.envImg.shape[:2]
+    cases = [(np.asarray(sc.envCdf, np.float32).ravel(), w, h, float(sc.envTotalSum))]
+    for (cw, ch) in ((64, 32), (37, 19), (2048, 8)):
+        lum = rng.random(cw * ch).astype(np.float32) ** 8
+        lum[rng.random(cw * ch) < 0.6] = 0.0                         # runs of equal CDF values
+        lum[rng.integers(cw * ch)] = 5000.0                          # one texel holds most of the mass
+        cdf = np.zeros(cw * ch, np.float32); acc = np.float32(0)
+        for i, v in enumerate(lum):                                  # the reference's float running sum (EnvironmentMap.cpp:52-58)
+            acc = np.float32(acc + v); cdf[i] = acc
+        cases.append((cdf, cw, ch, float(cdf[-1])))
+    for cdf, cw, ch, total in cases:
+        v = [rng.random(20000).astype(np.float32) * np.float32(total), cdf, np.nextafter(cdf, np.float32(-1)), np.nextafter(cdf, np.float32(1e30)),
+             np.array([0.0, total, total * 1.5, -1.0, 1e-30], np.float32)]
+        v = np.concatenate(v).astype(np.float32)
+        have, fast, ref = hb.env_search(cdf, cw, ch, total, v)
+        assert have
+        assert fast.tobytes() == ref.tobytes()
+    bad = cases[1][0].copy(); bad[100] = bad[99] - 1.0
+    have, fast, ref = hb.env_search(bad, 64, 32, float(bad[-1]), np.array([1.0], np.float32))
+    assert not have and fast.tobytes() == ref.tobytes()
