@@ -10,6 +10,7 @@ import feature_scenes as fs
 
 cases = [(n, scene_at(n, 64, 36, 40, 20)) for n in ("cornell_box_orig", "hyperion_rect_lights", "ibl_spheres", "volume_cube", "instancing", "gltf_mix")]
 cases += [("variant_" + v, fs.resized(fs.build(v), 64, 36, 40, 20)) for v in ("alpha_mask", "alpha_blend", "medium_scatter", "texture_maps_gl", "all_light_types")]
+cases += [("variant_medium_deferred_transmittance", fs.resized(fs.media_no_blend(2), 64, 36, 40, 20))]      # k_shade<3> + k_transmit
 for name, sc in cases:
     ctx = capi.Context(sc)
     ctx.render_samples(1, 2)
