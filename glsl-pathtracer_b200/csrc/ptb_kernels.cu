@@ -384,6 +384,9 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
 #ifndef PTB_SORT_MINB
 #define PTB_SORT_MINB 6      // resident sorter blocks per SM (40 registers): 1.26 -> 1.07 ms of sorting per hyperion step against 4
 #endif
+#ifndef PTB_SORT_MANY_KEYS
+#define PTB_SORT_MANY_KEYS 100
+#endif
 __global__ void __launch_bounds__(256, PTB_SORT_MINB) k_sort_tile_local(const uint32_t* __restrict__ queue, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ countPtr,
                                                           uint32_t* __restrict__ sorted, int numKeys, int holeKey, uint32_t nOverride)
 {
@@ -392,6 +395,7 @@ __global__ void __launch_bounds__(256, PTB_SORT_MINB) k_sort_tile_local(const ui
     const uint32_t n = nOverride ? nOverride : *countPtr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tileSize = 256u * SORT_ITEMS;
+    const bool manyKeys = numKeys > PTB_SORT_MANY_KEYS;
     for (uint32_t tile = blockIdx.x * tileSize; tile < n; tile += gridDim.x * tileSize)
     {
         for (int k = threadIdx.x; k < numKeys; k += 256) hist[k] = 0;
@@ -402,6 +406,17 @@ __global__ void __launch_bounds__(256, PTB_SORT_MINB) k_sort_tile_local(const ui
         {
             const uint32_t i = tile + j * 256u + threadIdx.x;
             key[j] = i < n ? min(keys[i], (uint32_t)(numKeys - 1)) : 0xffffffffu;
+            if (manyKeys)
+            {   // many classes (16x16 direction cells): a warp's 32 keys are mostly distinct — one shared-memory atomic each beats the warp match; only the hole
+                // key (ended paths, up to half of a tile) is aggregated
+                const bool hole = (int)key[j] == holeKey;
+                const unsigned hm = __ballot_sync(0xffffffffu, hole);
+                uint32_t off = 0;
+                if (hole) { const int leader = __ffs(hm) - 1; if ((int)lane == leader) off = atomicAdd(&hist[key[j]], (uint32_t)__popc(hm)); off = __shfl_sync(hm, off, leader) + __popc(hm & ((1u << lane) - 1u)); }
+                else if (key[j] != 0xffffffffu) off = atomicAdd(&hist[key[j]], 1u);
+                rank[j] = off;
+                continue;
+            }
             const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
             const int leader = __ffs(peers) - 1;
             uint32_t off = 0;
