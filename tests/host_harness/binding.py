@@ -21,6 +21,7 @@ def lib():
         L.hh_trace_closest.argtypes = [vp, vp, C.c_longlong, i32, i32, vp]
         L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, vp]
         L.hh_wide_nodes.argtypes = [vp]
+        L.hh_any_stack_high.argtypes = [vp]
         L.hh_build_tlas.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
         L.hh_env_search.argtypes = [vp, i32, i32, f32, vp, i32, vp, vp]; L.hh_env_search.restype = i32
@@ -67,6 +68,10 @@ class HostTrav:
 
     def wide_nodes(self):
         return lib().hh_wide_nodes(self.h)
+
+    def any_stack(self):
+        """(deepest any-hit stack seen so far, entries the kernels reserve)"""
+        return lib().hh_any_stack_high(self.h), lib().hh_stack_depth(self.h)
 
     def camera_rays(self, sample=1, tables=True):
         ro, cam = self.scene.renderOptions, self.scene.camera

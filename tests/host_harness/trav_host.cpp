@@ -14,12 +14,13 @@ struct HHScene
     DevScene S{};
     PtbDerivedHierarchy dh; PtbDerivedLights dl; PtbDerivedWide dw; std::vector<float4> tris;
     std::vector<float> nodes, transforms; std::vector<int> vertIndices; std::vector<float4> verticesUVX;
+    int anyStackHigh = 0;      // deepest any-hit stack over all hh_trace_any calls
 };
 struct BigStack      // thread-local stack sized for the wide hierarchy's bound (96)
 {
-    uint32_t a[128]; int sp = 0;
+    uint32_t a[128]; int sp = 0, high = 0;      // high: deepest the stack has been (checked against the bound the kernels reserve shared memory for)
     void reset() { sp = 0; }
-    void push(uint32_t v) { a[sp++] = v; }
+    void push(uint32_t v) { a[sp++] = v; if (sp > high) high = sp; }
     uint32_t pop() { return a[--sp]; }
 };
 struct HHHit { float t; int kind, instance, matID, primSlot, triIDx; float bary[3]; int lightIdx; };
@@ -52,6 +53,7 @@ HHScene* hh_create(const float* nodes, int numNodes, int topLevelIndex, const in
 }
 void hh_destroy(HHScene* h) { delete h; }
 int hh_stack_depth(HHScene* h) { return h->S.stackDepthAny; }
+int hh_any_stack_high(HHScene* h) { return h->anyStackHigh; }
 int hh_wide_nodes(HHScene* h) { return h->dw.ok ? (int)(h->dw.wide.size() / 8) : -1; }
 
 // k_trace_batch of ptb_kernels.cu, one ray after the other
@@ -87,8 +89,8 @@ void hh_trace_closest(HHScene* h, const float* rays, long long n, int lights, in
 void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long n, int lights, int cull, int wide, int* out, long long* fallbacks)
 {
     const DevScene& S = h->S;
-    long long fb = 0;
-#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fb)
+    long long fb = 0; int high = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fb) reduction(max : high)
     for (long long i = 0; i < n; i++)
     {
         BigStack stk;
@@ -106,7 +108,9 @@ void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long
             else occ = r != 0;
         }
         out[i] = occ ? 1 : 0;
+        if (stk.high > high) high = stk.high;
     }
+    h->anyStackHigh = std::max(h->anyStackHigh, high);
     if (fallbacks) *fallbacks = fb;
 }
 
