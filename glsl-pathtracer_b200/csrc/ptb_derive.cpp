@@ -330,6 +330,7 @@ struct WideBuilder
     std::vector<float4>& wide;
     const std::vector<char>& transOnly;
     bool ok = true;
+    int areaOrder = 0;
     bool orderByNeed = false;       // permute the slots of a node by ascending stack need of the children (smaller worst-case stack, same boolean)
     std::vector<int> memo;          // binary inner node -> wide index (a BLAS shared by several instances is collapsed once)
     std::vector<int> need;          // stack entries needed below a wide node (siblings pushed while descending)
@@ -386,6 +387,10 @@ struct WideBuilder
         float box[24]; uint32_t meta[4];
         const float qnan = std::nanf("");
         int childNeed[4] = {0, 0, 0, 0};
+        if (ok && areaOrder)
+        {   // measurement aid (PTB_WIDE_ORDER = 2 / 3): slots by descending / ascending box area
+            for (int a = 1; a < nk; a++) for (int b = a; b > 0 && (areaOrder == 2 ? area(N + (size_t)kids[b - 1] * 9) < area(N + (size_t)kids[b] * 9) : area(N + (size_t)kids[b - 1] * 9) > area(N + (size_t)kids[b] * 9)); b--) std::swap(kids[b - 1], kids[b]);
+        }
         if (ok && orderByNeed)
         {   // Any-hit visits the hit children in slot order and keeps the later ones on the stack meanwhile: with the deepest subtree in the LAST slot nothing
             // waits on the stack while it is traversed.  The visiting order does not change the boolean (ptb_device.cuh: traverseWideAny), so the slots may be
@@ -417,12 +422,13 @@ struct WideBuilder
 
 } // namespace
 
-static void buildWideOnce(const float* N, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, bool orderByNeed, PtbDerivedWide& out)
+// mode: slot order inside the wide nodes — 0 binary order, 1 ascending stack need, 2 / 3 descending / ascending box area
+static void buildWideOnce(const float* N, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, int mode, PtbDerivedWide& out)
 {
     out = PtbDerivedWide();
     out.instRootMeta.assign((size_t)numInstances, PTB_META_NONE);
     WideBuilder B(N, numNodes, numIndices, out.wide, transOnly);
-    B.orderByNeed = orderByNeed;
+    B.orderByNeed = mode == 1; B.areaOrder = mode >= 2 ? mode : 0;
     auto rootOf = [&](int node, int& needOut) -> uint32_t
     {
         if (node < 0 || node >= numNodes) { B.ok = false; return PTB_META_NONE; }
@@ -441,20 +447,21 @@ static void buildWideOnce(const float* N, int numNodes, int topLevelIndex, int n
     out.ok = B.ok && out.stackDepth <= 96 && out.wide.size() / 8 < (1u << 30);
 }
 
-// Slot order inside the wide nodes.  Binary order (largest-area subtree expanded in place) finds occluders soonest: hyperion's k_shadow runs 6.29 ms with it, 6.62 ms with the
-// slots sorted by stack need.  But the stack bound decides how much of the SM's 256 KB is left as L1 next to 5 resident blocks of 256 stacks: up to 31 entries fit the
-// 164 KB shared-memory configuration (92 KB of L1), more takes the 196 / 228 KB ones (60 / 28 KB of L1) — the 10 001-instance scene needs 42 entries in binary order and 32
-// sorted by need, and its k_shadow runs 123.6 -> 112.9 ms with the smaller stack.  So: binary order unless its bound exceeds 31 entries and the sorted order's is smaller.
-// PTB_WIDE_ORDER = 0 / 1 forces one of them (measurement aid).
+// Slot order inside the wide nodes.  Any-hit may visit the children in any order (same boolean), and the order decides how soon an occluded ray finds its occluder:
+// measured on hyperion's k_shadow — largest box first 5.84 ms, binary order 6.30, ascending stack need 6.62, smallest box first 6.55.  Largest box first ships.
+// The order also sets the stack bound, i.e. how much of the SM's 256 KB is left as L1 next to 5 resident blocks of 256 stacks: up to 31 entries fit the 164 KB
+// shared-memory configuration (92 KB of L1), more takes the 196 / 228 KB ones (60 / 28 KB of L1), which k_shadow feels.  When the shipped order
+// needs more than 31 entries and sorting by stack need (deepest subtree last: nothing waits on the stack while it is traversed) needs fewer, that order is used
+// instead — the 10 001-instance scene: 32 entries, k_shadow 123.6 -> 112.9 ms against binary order.  PTB_WIDE_ORDER = 0..3 forces one order (measurement aid).
 void ptbd_build_wide(const float* N, int numNodes, int topLevelIndex, int numIndices, int numInstances, const std::vector<char>& transOnly, PtbDerivedWide& out)
 {
     const char* e = getenv("PTB_WIDE_ORDER");
-    if (e) { buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, atoi(e) != 0, out); return; }
-    buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, false, out);
+    if (e) { buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, atoi(e), out); return; }
+    buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, 2, out);
     if (out.ok && out.stackDepth > 31)
     {
         PtbDerivedWide alt;
-        buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, true, alt);
+        buildWideOnce(N, numNodes, topLevelIndex, numIndices, numInstances, transOnly, 1, alt);
         if (alt.ok && alt.stackDepth < out.stackDepth) out = std::move(alt);
     }
 }
