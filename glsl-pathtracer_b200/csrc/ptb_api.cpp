@@ -369,11 +369,7 @@ int renderWave(PtbCtx* c, const FrameParams& F, WaveParams& W, float4* previewOu
     {   // passes per warp group: the largest power of two that divides the pass count, up to 32 (one pixel, 32 passes)
         // (a look-ahead wave of ptb_render_pass is added to the running sum ONE pass per call: groups of one pass keep those 256 reads per wave contiguous —
         // the drop-in loop runs 1112 spp/s with lps = 0 against 1076 with lps = 5, although the wave itself traces 1.2 % slower)
-        int lps = 0;
-        const int maxLps = W.accCount > 0 ? 0 : c->warpSamplesLog2;
-        while (lps < 5 && lps < maxLps && (W.nSamples & ((2 << lps) - 1)) == 0) lps++;
-        static const int lpwOf[6] = {3, 2, 2, 1, 1, 0};      // sub-block 8x4, 4x4, 4x2, 2x2, 2x1, 1x1 pixels
-        W.lps = lps; W.lpw = lpwOf[lps];
+        ptbd_wave_groups(W.nSamples, W.accCount > 0 ? 0 : c->warpSamplesLog2, &W.lps, &W.lpw);
     }
     int rc = ensureWaveState(c, W.nSlots);
     if (rc) return rc;

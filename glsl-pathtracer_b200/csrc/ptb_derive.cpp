@@ -611,3 +611,11 @@ int ptbd_build_env_guide(const float* cdf, int w, int h, float totalSum, std::ve
     for (uint32_t b = 0; b < G; b++) guide[b + 1] += guide[b];
     return 0;
 }
+
+void ptbd_wave_groups(int nSamples, int maxLps, int* lpsOut, int* lpwOut)
+{
+    int lps = 0;
+    while (lps < 5 && lps < maxLps && (nSamples & ((2 << lps) - 1)) == 0) lps++;
+    static const int lpwOf[6] = {3, 2, 2, 1, 1, 0};
+    *lpsOut = lps; *lpwOut = lpwOf[lps];
+}

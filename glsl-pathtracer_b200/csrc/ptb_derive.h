@@ -59,3 +59,6 @@ int ptbd_build_pixel_tables(int renderW, int renderH, int tileW, int tileH, std:
 // bucket(v) = (int)clamp(v * scale, 0, G - 1), G = guide.size() - 1: the first texel above a value of bucket b lies in [guide[b], guide[b + 1]].
 // Returns 0 and fills guide / scale, or 1 when the table does not apply (CDF not monotone / not finite): the device then runs the reference's search.
 int ptbd_build_env_guide(const float* cdf, int w, int h, float totalSum, std::vector<uint32_t>& guide, float& scale);
+// Warp groups of a block-major wave (WaveParams::lps / lpw, groupToPixel in ptb_device.cuh): passes per group = the largest power of two that divides the pass
+// count, at most 2^maxLps (<= 32); the group's pixel sub-block is 8x4, 4x4, 4x2, 2x2, 2x1, 1x1 for 1, 2, 4, 8, 16, 32 passes.
+void ptbd_wave_groups(int nSamples, int maxLps, int* lps, int* lpw);

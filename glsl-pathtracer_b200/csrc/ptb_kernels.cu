@@ -36,53 +36,7 @@ constexpr int SHADE_THREADS = 128;
 #define PTB_SHADE_LATER_BLOCKS 4      // resident k_shade<0> blocks per SM for the bounces after the first (latency-bound: scattered, material-sorted state)
 #endif
 
-// ------------------------------------------------------------------ slot <-> pixel mapping ----------------------
-// A wave holds nSamples sample passes of a pixel rectangle padded to 8x4 pixel blocks; 32 consecutive slots ("group") are the primary rays of one warp.
-//   sample-major (blockMajor = 0): group = one 8x4 block of one pass; all blocks of pass 0, then pass 1, ...
-//   block-major  (blockMajor = 1): the 32 * nSamples slots of an 8x4 block are consecutive (a 2048-slot tile then holds the paths of a few neighbouring pixels,
-//     which is what lets the tile-local grouping by direction / light build warps that share origin AND direction).  Inside the block a group is
-//     2^lps consecutive passes of a (2^lpw x 2^lph)-pixel sub-block (lpw + lph + lps = 5): lps = 0 -> the 8x4 block of one pass, lps = 5 -> 32 passes of ONE pixel —
-//     rays through one pixel differ by the sub-pixel jitter only, so the warp stays converged in the traversal and hits one material in the first shade pass.
-// group -> (sample pass, pixel) of lane `lane`
-__device__ __forceinline__ void groupToPixel(const WaveParams& W, uint32_t g, uint32_t lane, uint32_t blocksX, uint32_t blocksPerSample, int& s, int& px, int& py)
-{
-    uint32_t b, pxin = lane & 7u, pyin = lane >> 3;
-    if (W.blockMajor)
-    {
-        const uint32_t nS = (uint32_t)W.nSamples, lps = (uint32_t)W.lps, lpw = (uint32_t)W.lpw, lpp = 5u - lps /* log2(pixels per sub-block) */;
-        b = g / nS;
-        const uint32_t gi = g - b * nS;                  // group inside the block: sub-block major, then sample group
-        const uint32_t nsg = nS >> lps;                  // sample groups per sub-block
-        const uint32_t pb = gi / nsg, sg = gi - pb * nsg;
-        const uint32_t ls = lane >> lpp, pi = lane & ((1u << lpp) - 1u);
-        s = (int)((sg << lps) + ls);
-        const uint32_t pbx = pb & ((8u >> lpw) - 1u), pby = pb >> (3u - lpw);
-        pxin = (pbx << lpw) + (pi & ((1u << lpw) - 1u));
-        pyin = (pby << (lpp - lpw)) + (pi >> lpw);
-    }
-    else { s = (int)(g / blocksPerSample); b = g - (uint32_t)s * blocksPerSample; }
-    const uint32_t by = b / blocksX, bx = b - by * blocksX;
-    px = (int)(bx * 8u + pxin);
-    py = (int)(by * 4u + pyin);
-}
-__device__ __forceinline__ bool slotToPixel(const WaveParams& W, uint32_t slot, int& s, int& px, int& py)
-{
-    const uint32_t blocksX = (uint32_t)W.vw >> 3, blocksPerSample = blocksX * ((uint32_t)W.vh >> 2);
-    groupToPixel(W, slot >> 5, slot & 31u, blocksX, blocksPerSample, s, px, py);
-    return px < W.rw && py < W.rh;
-}
-
-// slot of sample pass k for the pixel with index idx (= 8x4 block * 32 + row-major pixel inside the block)
-__device__ __forceinline__ uint32_t slotOfSample(const WaveParams& W, uint32_t idx, uint32_t k)
-{
-    if (!W.blockMajor) return idx + k * (uint32_t)W.vw * (uint32_t)W.vh;
-    const uint32_t nS = (uint32_t)W.nSamples, lps = (uint32_t)W.lps, lpw = (uint32_t)W.lpw, lpp = 5u - lps, lph = lpp - lpw;
-    const uint32_t pxin = idx & 7u, pyin = (idx >> 3) & 3u;
-    const uint32_t pb = ((pyin >> lph) << (3u - lpw)) + (pxin >> lpw);
-    const uint32_t pi = ((pyin & ((1u << lph) - 1u)) << lpw) + (pxin & ((1u << lpw) - 1u));
-    const uint32_t gi = pb * (nS >> lps) + (k >> lps);
-    return ((((idx >> 5) * nS + gi) << 5) | ((k & ((1u << lps) - 1u)) << lpp)) + pi;
-}
+// slot <-> pixel mapping: groupToPixel / slotToPixel / slotOfSample in ptb_device.cuh (compiled for the host by the test harness, too)
 
 __global__ void __launch_bounds__(256) k_camera(DevScene S, FrameParams F, WaveParams W, PathState P, uint32_t* ctr0)
 {

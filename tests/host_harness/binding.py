@@ -24,6 +24,7 @@ def lib():
         L.hh_any_stack_high.argtypes = [vp]
         L.hh_build_tlas.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
+        L.hh_slot_map.argtypes = [i32, i32, i32, i32, i32, vp, vp]
         L.hh_env_search.argtypes = [vp, i32, i32, f32, vp, i32, vp, vp]; L.hh_env_search.restype = i32
         _LIB = L
     return _LIB
@@ -108,3 +109,11 @@ def env_search(cdf, w, h, total_sum, values):
     fast = np.zeros((len(values), 2), np.float32); ref = np.zeros((len(values), 2), np.float32)
     have = lib().hh_env_search(cdf.ctypes.data, w, h, float(total_sum), values.ctypes.data, len(values), fast.ctypes.data, ref.ctypes.data)
     return bool(have), fast, ref
+
+
+def slot_map(w, h, n_samples, block_major=True, max_lps=5):
+    """(rows of {pass, px, py, slotOfSample(pixel, pass)} per slot of the padded wave, passes per warp group as log2)"""
+    vw, vh = (w + 7) & ~7, (h + 3) & ~3
+    out = np.zeros((vw * vh * n_samples, 4), np.int32); lps = C.c_int32(0)
+    lib().hh_slot_map(w, h, n_samples, int(block_major), max_lps, out.ctypes.data, C.byref(lps))
+    return out, lps.value

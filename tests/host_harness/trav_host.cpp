@@ -151,6 +151,23 @@ int hh_env_search(const float* cdf, int w, int h, float totalSum, const float* v
     return have;
 }
 
+// Slot layout of a wave (groupToPixel / slotOfSample, ptbd_wave_groups): for every slot of a w x h rectangle with nSamples passes, out[slot] = {pass, px, py, slotOfSample(pixel index, pass)}
+void hh_slot_map(int w, int h, int nSamples, int blockMajor, int maxLps, int32_t* out, int32_t* lpsOut)
+{
+    WaveParams W{};
+    W.rw = w; W.rh = h; W.vw = (w + 7) & ~7; W.vh = (h + 3) & ~3; W.nSamples = nSamples; W.nSlots = (uint32_t)((size_t)W.vw * W.vh * nSamples);
+    W.blockMajor = (blockMajor && nSamples > 1) ? 1 : 0; W.lps = 0; W.lpw = 3;
+    if (W.blockMajor) ptbd_wave_groups(nSamples, maxLps, &W.lps, &W.lpw);
+    *lpsOut = W.lps;
+    for (uint32_t slot = 0; slot < W.nSlots; slot++)
+    {
+        int s, px, py;
+        slotToPixel(W, slot, s, px, py);
+        const uint32_t idx = (uint32_t)(((py >> 2) * (W.vw >> 3) + (px >> 3)) * 32 + (py & 3) * 8 + (px & 7));
+        out[(size_t)slot * 4 + 0] = s; out[(size_t)slot * 4 + 1] = px; out[(size_t)slot * 4 + 2] = py; out[(size_t)slot * 4 + 3] = (int32_t)slotOfSample(W, idx, (uint32_t)s);
+    }
+}
+
 // TLAS rebuild (ptbd_build_tlas_host) from the scene's own arrays: blasRoot / materialID per instance are read from the current TLAS leaves
 int hh_build_tlas(const float* nodes, int numNodes, int topLevelIndex, const float* transforms, int numInstances, const int32_t* materialIDs, float* tlasOut, int* heightOut)
 {

@@ -138,3 +138,30 @@ def test_wide_hierarchy_slot_order_does_not_change_occlusion_and_bounds_the_stac
         assert bounds["hyperion_rect_lights"] <= 25 and bounds["instancing"] <= 32
     if order == "auto":
         assert bounds["hyperion_rect_lights"] <= 31 and bounds["instancing"] <= 32
+
+
+@pytest.mark.parametrize("block_major,max_lps", [(False, 5), (True, 0), (True, 3), (True, 5)])
+def test_slot_layout_of_a_wave_is_a_bijection_with_coherent_tiles(block_major, max_lps):
+    """groupToPixel / slotOfSample (ptb_device.cuh) for pass counts 1..96 and a padded rectangle: every (pass, pixel) of the padded 8x4 blocks has exactly one slot,
+    slotOfSample inverts the map, a 32-slot group is 2^lps passes of one pixel sub-block, and in block-major order the 32 * S slots of an 8x4 block are consecutive
+    (that is what makes a 2048-slot sorting tile hold all passes of neighbouring pixels)."""
+    from host_harness import binding as hb
+    w, h = 21, 10                                   # padded to 24 x 12: 3 x 3 blocks with off-image pixels
+    vw, vh = 24, 12
+    for ns in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 96):
+        m, lps = hb.slot_map(w, h, ns, block_major, max_lps)
+        s, px, py, back = m[:, 0], m[:, 1], m[:, 2], m[:, 3]
+        assert (s >= 0).all() and (s < ns).all() and (px >= 0).all() and (px < vw).all() and (py >= 0).all() and (py < vh).all()
+        key = (s.astype(np.int64) * vh + py) * vw + px
+        assert len(np.unique(key)) == len(key) == vw * vh * ns, f"{ns} passes: not a bijection"
+        assert np.array_equal(back, np.arange(len(m))), f"{ns} passes: slotOfSample does not invert the map"
+        if not (block_major and ns > 1):
+            assert lps == 0
+            continue
+        assert ns % (1 << lps) == 0 and lps <= max_lps
+        blk = (py // 4) * (vw // 8) + px // 8
+        assert np.array_equal(blk, np.arange(len(m)) // (32 * ns)), "the slots of an 8x4 block must be consecutive"
+        g = m.reshape(-1, 32, 4)
+        assert ((g[:, :, 0].max(axis=1) - g[:, :, 0].min(axis=1)) == (1 << lps) - 1).all()          # 2^lps consecutive passes per group
+        npix = np.array([len({(a, b) for a, b in zip(r[:, 1], r[:, 2])}) for r in g])
+        assert (npix == 32 >> lps).all()                                                              # ... of 32 / 2^lps pixels
