@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <cstdlib>
 #include <limits>
 
@@ -330,7 +331,7 @@ struct WideBuilder
     std::vector<float4>& wide;
     const std::vector<char>& transOnly;
     bool ok = true;
-    int areaOrder = 0;
+    int areaOrder = 0, areaOrderTlas = 0, topLevel = 1 << 30;      // areaOrderTlas: a different order for the TLAS nodes (study aid: PTB_WIDE_ORDER = 10 * tlas + blas)
     bool orderByNeed = false;       // permute the slots of a node by ascending stack need of the children (smaller worst-case stack, same boolean)
     std::vector<int> memo;          // binary inner node -> wide index (a BLAS shared by several instances is collapsed once)
     std::vector<int> need;          // stack entries needed below a wide node (siblings pushed while descending)
@@ -387,9 +388,25 @@ struct WideBuilder
         float box[24]; uint32_t meta[4];
         const float qnan = std::nanf("");
         int childNeed[4] = {0, 0, 0, 0};
+        const int areaOrder = r >= topLevel ? (areaOrderTlas ? areaOrderTlas : this->areaOrder) : this->areaOrder;
         if (ok && areaOrder)
-        {   // measurement aid (PTB_WIDE_ORDER = 2 / 3): slots by descending / ascending box area
-            for (int a = 1; a < nk; a++) for (int b = a; b > 0 && (areaOrder == 2 ? area(N + (size_t)kids[b - 1] * 9) < area(N + (size_t)kids[b] * 9) : area(N + (size_t)kids[b - 1] * 9) > area(N + (size_t)kids[b] * 9)); b--) std::swap(kids[b - 1], kids[b]);
+        {   // slots by a score, best first (stable): 2 / 3 box area descending / ascending; study modes of scripts/anyhit_order.py: 4 / 9 leaves first, then box area
+            // descending / ascending; 8 leaves first, binary order otherwise
+            float score[4];
+            for (int k = 0; k < nk; k++)
+            {
+                const float a = area(N + (size_t)kids[k] * 9);
+                const bool leaf = !inner(kids[k]);
+                switch (areaOrder)
+                {
+                case 2: score[k] = a; break;
+                case 3: score[k] = -a; break;
+                case 4: score[k] = leaf ? 1e30f + a : a; break;
+                case 8: score[k] = leaf ? 1.0f : 0.0f; break;
+                default: score[k] = leaf ? 1e30f - a : -a; break;
+                }
+            }
+            for (int a = 1; a < nk; a++) for (int b = a; b > 0 && score[b - 1] < score[b]; b--) { std::swap(score[b - 1], score[b]); std::swap(kids[b - 1], kids[b]); }
         }
         if (ok && orderByNeed)
         {   // Any-hit visits the hit children in slot order and keeps the later ones on the stack meanwhile: with the deepest subtree in the LAST slot nothing
@@ -428,7 +445,7 @@ static void buildWideOnce(const float* N, int numNodes, int topLevelIndex, int n
     out = PtbDerivedWide();
     out.instRootMeta.assign((size_t)numInstances, PTB_META_NONE);
     WideBuilder B(N, numNodes, numIndices, out.wide, transOnly);
-    B.orderByNeed = mode == 1; B.areaOrder = mode >= 2 ? mode : 0;
+    B.orderByNeed = mode == 1; B.areaOrder = mode >= 2 ? mode % 10 : 0; B.areaOrderTlas = mode >= 10 ? mode / 10 : 0; B.topLevel = topLevelIndex;
     auto rootOf = [&](int node, int& needOut) -> uint32_t
     {
         if (node < 0 || node >= numNodes) { B.ok = false; return PTB_META_NONE; }
@@ -448,7 +465,8 @@ static void buildWideOnce(const float* N, int numNodes, int topLevelIndex, int n
 }
 
 // Slot order inside the wide nodes.  Any-hit may visit the children in any order (same boolean), and the order decides how soon an occluded ray finds its occluder:
-// measured on hyperion's k_shadow — largest box first 5.84 ms, binary order 6.30, ascending stack need 6.62, smallest box first 6.55.  Largest box first ships.
+// measured on hyperion's k_shadow — largest box first 5.84 ms, binary order 6.30, ascending stack need 6.62, smallest box first 6.55.  Largest box first ships.  Nearly all of it
+// is decided at the TLAS (largest instance first + binary order inside the BLASes: 5.79; + leaves first inside the BLASes: 5.76 — PTB_WIDE_ORDER = 10 * tlas + blas).
 // The order also sets the stack bound, i.e. how much of the SM's 256 KB is left as L1 next to 5 resident blocks of 256 stacks: up to 31 entries fit the 164 KB
 // shared-memory configuration (92 KB of L1), more takes the 196 / 228 KB ones (60 / 28 KB of L1), which k_shadow feels.  When the shipped order
 // needs more than 31 entries and sorting by stack need (deepest subtree last: nothing waits on the stack while it is traversed) needs fewer, that order is used

@@ -22,6 +22,7 @@ def lib():
         L.hh_trace_any.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, vp]
         L.hh_wide_nodes.argtypes = [vp]
         L.hh_any_stack_high.argtypes = [vp]
+        L.hh_any_bytes.argtypes = [vp]; L.hh_any_bytes.restype = C.c_double
         L.hh_build_tlas.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
         L.hh_camera_rays.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, i32, i32, vp]
         L.hh_slot_map.argtypes = [i32, i32, i32, i32, i32, vp, vp]
@@ -69,6 +70,10 @@ class HostTrav:
 
     def wide_nodes(self):
         return lib().hh_wide_nodes(self.h)
+
+    def any_bytes(self):
+        """bytes the last trace_any call fetched through the read-only path (work measure)"""
+        return lib().hh_any_bytes(self.h)
 
     def any_stack(self):
         """(deepest any-hit stack seen so far, entries the kernels reserve)"""

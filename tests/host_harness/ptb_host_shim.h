@@ -19,7 +19,9 @@
 #define __restrict__
 #endif
 
-template <class T> static inline T __ldg(const T* p) { return *p; }
+// bytes fetched through the read-only path by the calling thread: a work measure for order studies of the any-hit hierarchy (scripts/anyhit_order.py)
+static thread_local unsigned long long g_hh_ldg_bytes = 0;
+template <class T> static inline T __ldg(const T* p) { g_hh_ldg_bytes += sizeof(T); return *p; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -15,6 +15,7 @@ struct HHScene
     PtbDerivedHierarchy dh; PtbDerivedLights dl; PtbDerivedWide dw; std::vector<float4> tris;
     std::vector<float> nodes, transforms; std::vector<int> vertIndices; std::vector<float4> verticesUVX;
     int anyStackHigh = 0;      // deepest any-hit stack over all hh_trace_any calls
+    unsigned long long anyBytes = 0;   // bytes the last hh_trace_any call fetched (nodes, triangles, instance rows, lights)
 };
 struct BigStack      // thread-local stack sized for the wide hierarchy's bound (96)
 {
@@ -54,6 +55,7 @@ HHScene* hh_create(const float* nodes, int numNodes, int topLevelIndex, const in
 void hh_destroy(HHScene* h) { delete h; }
 int hh_stack_depth(HHScene* h) { return h->S.stackDepthAny; }
 int hh_any_stack_high(HHScene* h) { return h->anyStackHigh; }
+double hh_any_bytes(HHScene* h) { return (double)h->anyBytes; }
 int hh_wide_nodes(HHScene* h) { return h->dw.ok ? (int)(h->dw.wide.size() / 8) : -1; }
 
 // k_trace_batch of ptb_kernels.cu, one ray after the other
@@ -89,11 +91,12 @@ void hh_trace_closest(HHScene* h, const float* rays, long long n, int lights, in
 void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long n, int lights, int cull, int wide, int* out, long long* fallbacks)
 {
     const DevScene& S = h->S;
-    long long fb = 0; int high = 0;
-#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fb) reduction(max : high)
+    long long fb = 0; int high = 0; unsigned long long bytes = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fb) reduction(max : high) reduction(+ : bytes)
     for (long long i = 0; i < n; i++)
     {
         BigStack stk;
+        const unsigned long long b0 = g_hh_ldg_bytes;
         const float3 o = f3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]), d = f3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
         bool occ = lights && anyLights(S, o, d, maxDist[i]);
         if (!occ)
@@ -109,7 +112,9 @@ void hh_trace_any(HHScene* h, const float* rays, const float* maxDist, long long
         }
         out[i] = occ ? 1 : 0;
         if (stk.high > high) high = stk.high;
+        bytes += g_hh_ldg_bytes - b0;
     }
+    h->anyBytes = bytes;
     h->anyStackHigh = std::max(h->anyStackHigh, high);
     if (fallbacks) *fallbacks = fb;
 }
