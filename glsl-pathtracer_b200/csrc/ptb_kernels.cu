@@ -1,12 +1,15 @@
 // ptb_kernels.cu — sm_100a kernels of the wavefront path tracer and their launchers.
 //
-// Pipeline per wave (S sample passes of a pixel rectangle, all paths resident in HBM as SoA float4 state):
-//   k_camera      tile.glsl:41-68      camera rays + RNG seeding, initial queue
+// Pipeline per wave (S sample passes of a pixel rectangle, all paths resident in HBM as SoA float4 state, slots in block-major order: ptb_device.cuh):
+//   k_trace_primary  tile.glsl:41-68 + closest_hit.glsl   camera rays generated in registers and traced at once (k_camera: preview target only)
 //   loop over bounces:
-//     k_trace     closest_hit.glsl     persistent warps, dynamic 32-ray fetch, shared-memory stacks, 64-byte node fetches
+//     k_sort_tile_local                   tile-local grouping of queue entries: by direction cell before the bounce-1 trace, by material before a shade pass,
+//                                         by sampled light before the first k_shadow
+//     k_trace     closest_hit.glsl     persistent warps, dynamic 32-ray fetch, shared-memory stacks, 64-byte node fetches; finishes paths that end at the hit
 //     k_shade     pathtrace.glsl       hit attributes, GetMaterial, emission/MIS, media, alpha, NEE sample + DisneyEval,
-//                                      DisneySample, Russian roulette; warp-ballot compaction into next/shadow queues
-//     k_shadow    anyhit.glsl          any-hit for the queued NEE rays, adds the unoccluded contributions
+//                                      DisneySample, Russian roulette; next / shadow queues (warp-ballot compaction, or records by path slot)
+//     k_shadow    anyhit.glsl          any-hit for the queued NEE rays (4-wide hierarchy), adds the unoccluded contributions
+//     k_transmit  pathtrace.glsl:119   EvalTransmittance for the queued NEE rays of volume-MIS scenes without BLEND materials
 //   k_accumulate  tile.glsl:70-74      sum of the wave's samples into the running-sum buffer
 //   k_tonemap     tonemap.glsl         on readback
 #include "ptb_device.cuh"
