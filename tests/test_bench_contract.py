@@ -39,3 +39,18 @@ def test_our_arm_has_no_cpu_fallback():
         pytest.skip("a GPU is present")
     r = run(["--steps", "1", "--warmup", "1", "--workload", "cornell_box_orig"])
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_roofline_figures_come_from_the_latest_committed_capture():
+    """bench.py cannot count instructions or DRAM bytes without a profiler: it quotes them from the ncu capture committed under profiles/ (labelled with the
+    capture's commit and file).  The capture it picks must be the latest round's, must belong to the headline workload and must carry the figures the line uses."""
+    import glob, importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    cap = b.capture("hyperion_rect_lights")
+    latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_capture.json")))[-1]
+    assert cap is not None and os.path.join(ROOT, cap["file"]) == latest
+    for k in ("commit", "k_trace_dram_bytes_per_step", "k_trace_thread_inst_per_step", "k_trace_lane_issue_frac", "k_shadow_lane_issue_frac", "k_trace_l2_gbs"):
+        assert cap.get(k), k
+    assert 0.0 < cap["k_trace_lane_issue_frac"] < 1.0 and 0.0 < cap["k_shadow_lane_issue_frac"] < 1.0
+    assert b.capture("cornell_box_orig") is None            # no capture of that workload: nothing is quoted
